@@ -1,0 +1,134 @@
+"""ctypes binding of libclid_sdf.so (C ABI declared in include/clid_sdf.h).
+
+There is no CPU or PyTorch fallback behind this module: if the shared library is missing or
+a tensor is not on a CUDA device the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libclid_sdf.so")
+
+MAX_LEVELS = 3
+MAX_KNN = 8
+MAX_KC = 256
+
+# enum ClidFlags
+TRAINING_MODE = 1 << 0
+QUERY_LOCALLY = 1 << 1
+TIME_FILTER = 1 << 2
+LAYER_NORM = 1 << 3
+LEAKY_RELU = 1 << 4
+USE_BRICKS = 1 << 5
+
+_f32p = C.c_void_p  # device pointers travel as plain addresses
+
+
+class ClidBricks(C.Structure):
+    _fields_ = [
+        ("mask", C.c_void_p), ("base", C.c_void_p), ("records", C.c_void_p), ("stencil", C.c_void_p),
+        ("origin", C.c_int32 * 3), ("dims", C.c_int32 * 3), ("span", C.c_int32), ("n_records", C.c_int32),
+    ]
+
+
+class ClidMap(C.Structure):
+    _fields_ = [
+        ("buffer_pt_index", C.c_void_p), ("buffer_size", C.c_int64), ("primes", C.c_int64 * 3),
+        ("neural_points", C.c_void_p), ("point_ts_create", C.c_void_p), ("n_global", C.c_int64),
+        ("travel_dist", C.c_void_p), ("n_travel", C.c_int32), ("cur_ts", C.c_int32),
+        ("diff_travel_dist_local", C.c_float), ("resolution", C.c_float), ("max_valid_dist2", C.c_float),
+        ("kc", C.c_int32), ("neighbor_dx", C.c_void_p), ("global2local", C.c_void_p),
+        ("gather_points", C.c_void_p), ("gather_features", C.c_void_p), ("gather_certainties", C.c_void_p),
+        ("certainty_accum", C.c_void_p), ("gather_ts_update", C.c_void_p), ("n_gather", C.c_int64),
+        ("feature_dim", C.c_int32), ("knn", C.c_int32), ("bricks", C.POINTER(ClidBricks)),
+    ]
+
+
+class ClidDecoder(C.Structure):
+    _fields_ = [
+        ("weight", C.c_void_p * MAX_LEVELS), ("bias", C.c_void_p * MAX_LEVELS),
+        ("out_weight", C.c_void_p), ("out_bias", C.c_void_p),
+        ("in_dim", C.c_int32), ("hidden_dim", C.c_int32), ("levels", C.c_int32), ("sdf_scale", C.c_float),
+    ]
+
+
+class ClidQueryOut(C.Structure):
+    _fields_ = [
+        ("sdf", C.c_void_p), ("grad", C.c_void_p), ("z", C.c_void_p), ("weights", C.c_void_p),
+        ("knn_idx", C.c_void_p), ("nn_count", C.c_void_p), ("certainty", C.c_void_p),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+
+# every symbol include/clid_sdf.h declares: (name, restype, argtypes)
+_SIGNATURES = [
+    ("clid_version", C.c_int, []),
+    ("clid_last_error", C.c_char_p, []),
+    ("clid_query_forward", C.c_int,
+     [C.POINTER(ClidMap), C.POINTER(ClidDecoder), C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32,
+      C.POINTER(ClidQueryOut), C.c_void_p]),
+    ("clid_query_backward", C.c_int,
+     [C.POINTER(ClidMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p,
+      C.c_void_p]),
+    ("clid_query_backward_backward", C.c_int,
+     [C.POINTER(ClidMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p,
+      C.c_void_p, C.c_void_p]),
+    ("clid_radius_search", C.c_int,
+     [C.POINTER(ClidMap), C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("clid_query_certainty", C.c_int,
+     [C.POINTER(ClidMap), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+]
+
+
+def exported_symbols():
+    return [s[0] for s in _SIGNATURES]
+
+
+def load() -> C.CDLL:
+    """Load libclid_sdf.so (built in-tree by clid_slam_b200.build).  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension is required (no CPU fallback). "
+            "Build it with `python -m clid_slam_b200.build`."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, restype, argtypes in _SIGNATURES:
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().clid_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed with code {rc}: {msg}")
+
+
+def ptr(t: Optional[torch.Tensor], dtype: torch.dtype, what: str) -> Optional[int]:
+    """Device address of a contiguous CUDA tensor of the given dtype (None passes through)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what} is on {t.device}: the neural-SDF hot path runs only on CUDA (no CPU fallback)"
+        )
+    if t.dtype != dtype:
+        raise TypeError(f"{what}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{what} must be contiguous")
+    return t.data_ptr()
+
+
+def current_stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream

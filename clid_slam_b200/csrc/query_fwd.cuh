@@ -1,0 +1,350 @@
+// Fused forward: voxel-hash kNN search -> IDW feature blend -> decoder MLP -> closed-form
+// d sdf / d x.  One thread per query; everything between the probe and the outputs lives
+// in registers.  Replaces (reference, CPU/GPU eager torch):
+//   model/neural_points.py:971-1030 radius_neighborhood_search
+//   model/neural_points.py:553-769  query_feature (weighted_first)
+//   model/decoder.py:58-82          Decoder.mlp / sdf
+//   utils/tools.py:298-311          get_gradient
+#pragma once
+#include "common.cuh"
+
+namespace clid {
+
+struct QueryParams {
+  ClidMap map;
+  ClidDecoder dec;
+  ClidQueryOut out;
+  ClidBricks bricks;
+  const float* x;
+  const int32_t* ts;
+  int64_t n;
+  uint32_t flags;
+};
+
+// ascending top-K by squared distance, ties keep the earlier candidate
+template <int K>
+struct TopK {
+  float d[K];
+  int id[K];
+  float vx[K], vy[K], vz[K];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int k = 0; k < K; ++k) { d[k] = __int_as_float(0x7f800000); id[k] = -1; vx[k] = vy[k] = vz[k] = 0.f; }
+  }
+  __device__ __forceinline__ void insert(float dc, int ic, float x, float y, float z) {
+    if (!(dc < d[K - 1])) return;
+#pragma unroll
+    for (int k = K - 1; k >= 1; --k) {
+      bool shift = dc < d[k - 1];  // candidate lands before slot k: slot k takes slot k-1
+      bool here = !shift && dc < d[k];
+      d[k] = shift ? d[k - 1] : (here ? dc : d[k]);
+      id[k] = shift ? id[k - 1] : (here ? ic : id[k]);
+      vx[k] = shift ? vx[k - 1] : (here ? x : vx[k]);
+      vy[k] = shift ? vy[k - 1] : (here ? y : vy[k]);
+      vz[k] = shift ? vz[k - 1] : (here ? z : vz[k]);
+    }
+    if (dc < d[0]) { d[0] = dc; id[0] = ic; vx[0] = x; vy[0] = y; vz[0] = z; }
+  }
+};
+
+// ---- candidate enumeration through the reference's hash table ----------------------------
+template <int K>
+__device__ __forceinline__ int search_hashed(const ClidMap& m, const int64_t* __restrict__ cell_mod, float px,
+                                             float py, float pz, const bool kLocal, const bool kTimeFilter,
+                                             TopK<K>& top) {
+  constexpr int U = 9;
+  const int gx = cell_of(px, m.resolution), gy = cell_of(py, m.resolution), gz = cell_of(pz, m.resolution);
+  const int64_t B = m.buffer_size;
+  const int64_t m0 = floor_mod((int64_t)gx * m.primes[0] + (int64_t)gy * m.primes[1] + (int64_t)gz * m.primes[2], B);
+  float td_cur = 0.f;
+  if (kTimeFilter) td_cur = m.travel_dist[m.cur_ts];
+  int count = 0;
+  for (int c0 = 0; c0 < m.kc; c0 += U) {
+    int gi[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int c = c0 + u;
+      int64_t v = -1;
+      if (c < m.kc) {
+        int64_t slot = m0 + cell_mod[c];
+        slot = slot >= B ? slot - B : slot;
+        v = __ldg(m.buffer_pt_index + slot);
+      }
+      gi[u] = (int)v;
+    }
+    float cx[U], cy[U], cz[U];
+    int li[U];
+    int tsc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int g = gi[u] < 0 ? 0 : gi[u];  // invalid lanes read row 0 (always mapped); result discarded
+      const float* p = m.neural_points + 3 * (int64_t)g;
+      cx[u] = __ldg(p); cy[u] = __ldg(p + 1); cz[u] = __ldg(p + 2);
+      li[u] = kLocal ? (int)__ldg(m.global2local + g) : g;
+      tsc[u] = kTimeFilter ? __ldg(m.point_ts_create + g) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      bool ok = gi[u] >= 0;
+      if (kTimeFilter) {
+        float gap = fabsf(td_cur - __ldg(m.travel_dist + tsc[u]));
+        ok = ok && (gap < m.diff_travel_dist_local);
+      }
+      float ex = cx[u] - px, ey = cy[u] - py, ez = cz[u] - pz;  // neighbour - query, as the reference
+      float d2 = dist2_torch(ex, ey, ez);
+      ok = ok && !(d2 > m.max_valid_dist2) && li[u] >= 0;
+      if (ok) {
+        ++count;
+        top.insert(d2, li[u], -ex, -ey, -ez);
+      }
+    }
+  }
+  return count;
+}
+
+// ---- candidate enumeration through the brick index ---------------------------------------
+template <int K>
+__device__ __forceinline__ int search_bricks(const ClidMap& m, const ClidBricks& b, float px, float py, float pz,
+                                             TopK<K>& top) {
+  const int gx = cell_of(px, m.resolution) - b.origin[0];
+  const int gy = cell_of(py, m.resolution) - b.origin[1];
+  const int gz = cell_of(pz, m.resolution) - b.origin[2];
+  // first brick the neighbourhood can touch; the stencil table is indexed by the in-brick
+  // position of the query cell and the brick offset inside the span^3 block
+  const int pad = 4 * (b.span - 1);  // cells of slack so (g + pad)/4 never goes negative for in-range queries
+  const int bx0 = ((gx + pad - 2) >> 2) - (b.span - 1), by0 = ((gy + pad - 2) >> 2) - (b.span - 1),
+            bz0 = ((gz + pad - 2) >> 2) - (b.span - 1);
+  const int lx = (gx + pad - 2) & 3, ly = (gy + pad - 2) & 3, lz = (gz + pad - 2) & 3;
+  const uint64_t* st = b.stencil + (size_t)((lz * 4 + ly) * 4 + lx) * (b.span * b.span * b.span);
+  int count = 0;
+  for (int dz = 0; dz < b.span; ++dz) {
+    int bz = bz0 + dz;
+    if ((unsigned)bz >= (unsigned)b.dims[2]) continue;
+    for (int dy = 0; dy < b.span; ++dy) {
+      int by = by0 + dy;
+      if ((unsigned)by >= (unsigned)b.dims[1]) continue;
+      for (int dx = 0; dx < b.span; ++dx) {
+        int bx = bx0 + dx;
+        if ((unsigned)bx >= (unsigned)b.dims[0]) continue;
+        int64_t bi = ((int64_t)bz * b.dims[1] + by) * b.dims[0] + bx;
+        uint64_t occ = __ldg(b.mask + bi);
+        uint64_t want = occ & __ldg(st + (dz * b.span + dy) * b.span + dx);
+        if (!want) continue;
+        int base = __ldg(b.base + bi);
+        while (want) {
+          int bit = __ffsll((long long)want) - 1;
+          want &= want - 1;
+          int rec = base + __popcll(occ & ((1ull << bit) - 1ull));
+          float4 r = __ldg(reinterpret_cast<const float4*>(b.records) + rec);
+          float ex = r.x - px, ey = r.y - py, ez = r.z - pz;
+          float d2 = dist2_torch(ex, ey, ez);
+          if (!(d2 > m.max_valid_dist2)) {
+            ++count;
+            top.insert(d2, __float_as_int(r.w), -ex, -ey, -ez);
+          }
+        }
+      }
+    }
+  }
+  return count;
+}
+
+template <int H, int L, int K, bool kBricks>
+__global__ void __launch_bounds__(128) query_forward_kernel(const __grid_constant__ QueryParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float* sm_dec = smem;
+  constexpr int kDecFloats = H > 0 ? MlpLayout<(H > 0 ? H : 4), (H > 0 ? L : 1)>::kFloats : 0;
+  int64_t* cell_mod = reinterpret_cast<int64_t*>(smem + kDecFloats);
+  const ClidMap& m = p.map;
+
+  if constexpr (H > 0) stage_decoder<H, L>(sm_dec, p.dec);
+  if constexpr (!kBricks) {
+    for (int c = threadIdx.x; c < m.kc; c += blockDim.x) {
+      int64_t h = m.neighbor_dx[3 * c] * m.primes[0] + m.neighbor_dx[3 * c + 1] * m.primes[1] +
+                  m.neighbor_dx[3 * c + 2] * m.primes[2];
+      cell_mod[c] = floor_mod(h, m.buffer_size);
+    }
+  }
+  __syncthreads();
+
+  const bool training = p.flags & CLID_TRAINING_MODE;
+  const bool local = p.flags & CLID_QUERY_LOCALLY;
+  const bool time_filter = p.flags & CLID_TIME_FILTER;
+  const bool layer_norm = p.flags & CLID_LAYER_NORM;
+  const float slope = (p.flags & CLID_LEAKY_RELU) ? kLeakySlope : 0.f;
+  const int knn = m.knn;
+
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < p.n; q += (int64_t)gridDim.x * blockDim.x) {
+    const float px = p.x[3 * q], py = p.x[3 * q + 1], pz = p.x[3 * q + 2];
+    TopK<K> top;
+    top.init();
+    int count;
+    if constexpr (kBricks) count = search_bricks<K>(m, p.bricks, px, py, pz, top);
+    else count = search_hashed<K>(m, cell_mod, px, py, pz, local, time_filter, top);
+
+    // ---- inverse-distance weights (neural_points.py:688-706)
+    float w[K], u[K];
+    float S = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      bool valid = k < knn && top.id[k] >= 0;
+      if (!valid) top.id[k] = -1;
+      u[k] = valid ? 1.0f / (top.d[k] + kIdwEps) : 0.f;
+      S += u[k];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) w[k] = top.id[k] >= 0 ? u[k] / S : 0.f;
+
+    // ---- gather + blend
+    float z[kIn];
+#pragma unroll
+    for (int i = 0; i < kIn; ++i) z[i] = 0.f;
+    float cert = 0.f;
+    float f[K][kFeat];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (top.id[k] >= 0) {
+        const float4* row = reinterpret_cast<const float4*>(m.gather_features + (int64_t)top.id[k] * kFeat);
+        float4 f0 = __ldg(row), f1 = __ldg(row + 1);
+        f[k][0] = f0.x; f[k][1] = f0.y; f[k][2] = f0.z; f[k][3] = f0.w;
+        f[k][4] = f1.x; f[k][5] = f1.y; f[k][6] = f1.z; f[k][7] = f1.w;
+        if (layer_norm) { float mu, rs; layer_norm8(f[k], mu, rs); }
+        if (p.out.certainty) cert = fmaf(__ldg(m.gather_certainties + top.id[k]), w[k], cert);
+#pragma unroll
+        for (int i = 0; i < kFeat; ++i) z[i] = fmaf(w[k], f[k][i], z[i]);
+        z[8] = fmaf(w[k], top.vx[k], z[8]);
+        z[9] = fmaf(w[k], top.vy[k], z[9]);
+        z[10] = fmaf(w[k], top.vz[k], z[10]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kFeat; ++i) f[k][i] = 0.f;
+      }
+    }
+
+    // ---- side effects (neural_points.py:708-733)
+    if (training) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (top.id[k] >= 0) {
+          atomicAdd(m.certainty_accum + top.id[k], w[k]);
+          if (p.ts && m.gather_ts_update) atomicMax(m.gather_ts_update + top.id[k], p.ts[q]);
+        }
+      }
+    }
+
+    // ---- outputs of the query
+    if (p.out.nn_count) p.out.nn_count[q] = count;
+    if (p.out.certainty) p.out.certainty[q] = cert;
+    if (p.out.z) {
+#pragma unroll
+      for (int i = 0; i < kIn; ++i) p.out.z[q * kIn + i] = z[i];
+    }
+    if (p.out.weights) {
+      for (int k = 0; k < knn; ++k) {
+        float wk = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < K; ++kk) wk = kk == k ? w[kk] : wk;
+        p.out.weights[q * knn + k] = wk;
+      }
+    }
+    if (p.out.knn_idx) {
+      for (int k = 0; k < knn; ++k) {
+        int ik = -1;
+#pragma unroll
+        for (int kk = 0; kk < K; ++kk) ik = kk == k ? top.id[kk] : ik;
+        p.out.knn_idx[q * knn + k] = ik;
+      }
+    }
+
+    // ---- decoder + closed-form spatial gradient
+    if constexpr (H > 0) {
+      float o, a[kIn];
+      mlp_value_and_input_grad<H, L>(sm_dec, z, slope, o, a);
+      const float s = p.dec.sdf_scale;
+      if (p.out.sdf) p.out.sdf[q] = o * s;
+      if (p.out.grad) {
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+        if (count > 0) {
+          float cbar = 0.f;
+#pragma unroll
+          for (int i = 0; i < kIn; ++i) cbar = fmaf(z[i], a[i], cbar);
+          const float invS = 1.0f / S;
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            if (top.id[k] >= 0) {
+              float ck = a[8] * top.vx[k] + a[9] * top.vy[k] + a[10] * top.vz[k];
+#pragma unroll
+              for (int i = 0; i < kFeat; ++i) ck = fmaf(f[k][i], a[i], ck);
+              // d u_k / d x = -2 u_k^2 v_k ; sum_k c_k d w_k / d x = (1/S) sum_k (c_k - cbar) d u_k / d x
+              float coef = (ck - cbar) * (-2.f * u[k] * u[k]) * invS;
+              gx = fmaf(coef, top.vx[k], gx);
+              gy = fmaf(coef, top.vy[k], gy);
+              gz = fmaf(coef, top.vz[k], gz);
+            }
+          }
+          gx += a[8]; gy += a[9]; gz += a[10];  // sum_k w_k == 1
+        }
+        p.out.grad[3 * q] = gx * s;
+        p.out.grad[3 * q + 1] = gy * s;
+        p.out.grad[3 * q + 2] = gz * s;
+      }
+    }
+  }
+}
+
+// ---- API-compat kernels: the raw neighbourhood table and the per-query max certainty ------
+// model/neural_points.py:971-1030 radius_neighborhood_search -> dist2 [n,kc] f32, idx [n,kc] i64
+// model/neural_points.py:1032-1051 query_certainty           -> max over cells of certainty
+// One thread per (query, cell) so both outputs are written fully coalesced.
+__global__ void __launch_bounds__(256) radius_search_kernel(const ClidMap m, const float* __restrict__ x, int64_t n,
+                                                            bool time_filter, float* __restrict__ dist2_out,
+                                                            int64_t* __restrict__ idx_out) {
+  const int64_t total = n * m.kc;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = t / m.kc;
+    const int c = (int)(t - q * m.kc);
+    const float px = x[3 * q], py = x[3 * q + 1], pz = x[3 * q + 2];
+    const int64_t gx = cell_of(px, m.resolution) + m.neighbor_dx[3 * c];
+    const int64_t gy = cell_of(py, m.resolution) + m.neighbor_dx[3 * c + 1];
+    const int64_t gz = cell_of(pz, m.resolution) + m.neighbor_dx[3 * c + 2];
+    const int64_t slot = floor_mod(gx * m.primes[0] + gy * m.primes[1] + gz * m.primes[2], m.buffer_size);
+    int64_t gi = m.buffer_pt_index[slot];
+    if (time_filter && gi >= 0) {
+      float gap = fabsf(m.travel_dist[m.cur_ts] - m.travel_dist[m.point_ts_create[gi]]);
+      if (!(gap < m.diff_travel_dist_local)) gi = -1;
+    }
+    float d2 = m.max_valid_dist2;
+    if (gi >= 0) {
+      const float* p = m.neural_points + 3 * gi;
+      d2 = dist2_torch(p[0] - px, p[1] - py, p[2] - pz);
+      if (d2 > m.max_valid_dist2) gi = -1;
+    }
+    dist2_out[t] = d2;
+    idx_out[t] = gi;
+  }
+}
+
+__global__ void __launch_bounds__(256) query_certainty_kernel(const ClidMap m, const float* __restrict__ x, int64_t n,
+                                                              const float* __restrict__ certainties,
+                                                              float* __restrict__ out) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    const float px = x[3 * q], py = x[3 * q + 1], pz = x[3 * q + 2];
+    const int64_t cx = cell_of(px, m.resolution), cy = cell_of(py, m.resolution), cz = cell_of(pz, m.resolution);
+    float best = -__int_as_float(0x7f800000);
+    for (int c = 0; c < m.kc; ++c) {
+      const int64_t gx = cx + m.neighbor_dx[3 * c], gy = cy + m.neighbor_dx[3 * c + 1], gz = cz + m.neighbor_dx[3 * c + 2];
+      const int64_t slot = floor_mod(gx * m.primes[0] + gy * m.primes[1] + gz * m.primes[2], m.buffer_size);
+      const int64_t gi = m.buffer_pt_index[slot];
+      float v = 0.f;  // invalid candidates count as certainty 0 (neural_points.py:1045)
+      if (gi >= 0) {
+        const float* p = m.neural_points + 3 * gi;
+        float d2 = dist2_torch(p[0] - px, p[1] - py, p[2] - pz);
+        if (!(d2 > m.max_valid_dist2)) v = certainties[gi];
+      }
+      best = fmaxf(best, v);
+    }
+    out[q] = best;
+  }
+}
+
+}  // namespace clid

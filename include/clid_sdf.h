@@ -1,0 +1,171 @@
+/*
+ * clid_sdf.h -- C ABI of libclid_sdf.so: the B200 (sm_100a) implementation of CLID-SLAM's
+ * per-scan neural-SDF training/query hot path.
+ *
+ * The reference (DUTRobot/CLID-SLAM @ 5c4f9e7) is 100 % Python/PyTorch and has no FFI of
+ * its own; every entry point below therefore cites the *Python function(s)* whose
+ * arithmetic it replaces (paths relative to the reference tree).  The host-side mirror of
+ * the reference's operator interface (model.decoder.Decoder, model.neural_points.
+ * NeuralPoints, utils.mapper.Mapper, utils.loss) lives in clid_slam_b200/ and binds these
+ * symbols through ctypes (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers borrowed for the duration of the call; the library
+ *    never allocates, frees or retains device memory.  Layouts are the reference's
+ *    (row-major, fp32 values, int64 hash table / remap, int32 timestamps).
+ *  - Work is enqueued on the caller's stream; no call synchronises or reads back.
+ *  - Return value: 0 (CLID_OK) or a negative CLID_E* code; clid_last_error() returns a
+ *    thread-local message for the last failure.  n == 0 is a successful no-op.
+ */
+#ifndef CLID_SDF_H_
+#define CLID_SDF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLID_ABI_VERSION 1
+#define CLID_MAX_LEVELS 3   /* hidden layers of the decoder MLP */
+#define CLID_MAX_KNN 8      /* query_nn_k */
+#define CLID_MAX_KC 256     /* probed cells per query */
+
+#define CLID_API __attribute__((visibility("default")))
+
+typedef void* clid_stream_t; /* cudaStream_t */
+
+enum ClidStatus {
+  CLID_OK = 0,
+  CLID_EINVAL = -1,       /* null / misaligned / out-of-range argument */
+  CLID_EUNSUPPORTED = -2, /* shape outside the compiled kernel set */
+  CLID_ECUDA = -3         /* CUDA launch or runtime failure */
+};
+
+enum ClidFlags {
+  CLID_TRAINING_MODE = 1 << 0, /* certainty scatter-add and, with ts, ts_update amax (neural_points.py:708-733) */
+  CLID_QUERY_LOCALLY = 1 << 1, /* remap through global2local, gather from the local window (:595-598) */
+  CLID_TIME_FILTER = 1 << 2,   /* travel-distance window on point_ts_create (:1003-1009) */
+  CLID_LAYER_NORM = 1 << 3,    /* F.layer_norm over the feature dim, no affine, eps 1e-5 (:632-633) */
+  CLID_LEAKY_RELU = 1 << 4,    /* decoder.py:66-74, slope 0.01 */
+  CLID_USE_BRICKS = 1 << 5     /* probe through ClidMap.bricks instead of the hash table */
+};
+
+/* Compact per-frame voxel index derived from the hash table (see DESIGN.md "brick index").
+ * Built by clid_bricks_build(); gives bit-identical candidate sets to the hashed probe. */
+typedef struct ClidBricks {
+  const uint64_t* mask;   /* [nb] occupancy of the 4x4x4 cells of a brick                     */
+  const int32_t* base;    /* [nb] first record of the brick                                   */
+  const float* records;   /* [n_records,4] = (px, py, pz, bit-cast int32 gather row)          */
+  const uint64_t* stencil;/* [64 * span^3] neighbourhood masks by in-brick cell position      */
+  int32_t origin[3];      /* cell coordinate of brick (0,0,0)'s first cell                    */
+  int32_t dims[3];        /* bricks per axis                                                  */
+  int32_t span;           /* bricks per axis a neighbourhood can touch (2 for num_nei_cells<=2) */
+  int32_t n_records;
+} ClidBricks;
+
+/* Neural-point map state read by a query.  model/neural_points.py:79-133 */
+typedef struct ClidMap {
+  const int64_t* buffer_pt_index; /* [buffer_size] voxel hash -> global point id, -1 empty  */
+  int64_t buffer_size;
+  int64_t primes[3];
+  const float* neural_points;     /* [n_global,3]                                           */
+  const int32_t* point_ts_create; /* [n_global]  (read only with CLID_TIME_FILTER)          */
+  int64_t n_global;
+  const float* travel_dist;       /* [n_travel]  (CLID_TIME_FILTER)                         */
+  int32_t n_travel;
+  int32_t cur_ts;
+  float diff_travel_dist_local;
+  float resolution;               /* voxel_size_m                                           */
+  float max_valid_dist2;
+  int32_t kc;                     /* rows of neighbor_dx                                    */
+  const int64_t* neighbor_dx;     /* [kc,3] cell offsets (set_search_neighborhood, :931-969) */
+  const int64_t* global2local;    /* [n_global+1] (CLID_QUERY_LOCALLY)                      */
+  /* arrays the k nearest neighbours are gathered from: local_* with CLID_QUERY_LOCALLY,
+   * else the global ones */
+  const float* gather_points;     /* [n_gather,3]                                           */
+  const float* gather_features;   /* [n_gather+1,feature_dim]                               */
+  const float* gather_certainties;/* [n_gather]                                             */
+  float* certainty_accum;         /* [n_gather] += weights in training mode; may alias
+                                     gather_certainties (then queried certainty races, as
+                                     nobody reads it in training) or be a separate buffer   */
+  int32_t* gather_ts_update;      /* [n_gather] amax target, or NULL                        */
+  int64_t n_gather;
+  int32_t feature_dim;            /* 8                                                      */
+  int32_t knn;                    /* query_nn_k <= CLID_MAX_KNN                             */
+  const ClidBricks* bricks;       /* HOST pointer to a ClidBricks or NULL                   */
+} ClidMap;
+
+/* model/decoder.py:13-82: Linear(in->H) act [Linear(H->H) act]^(levels-1) Linear(H->1), x sdf_scale */
+typedef struct ClidDecoder {
+  const float* weight[CLID_MAX_LEVELS]; /* [H,in] then [H,H], row-major like nn.Linear.weight */
+  const float* bias[CLID_MAX_LEVELS];   /* [H] or NULL (mlp_bias_on = False)                  */
+  const float* out_weight;              /* [1,H]                                              */
+  const float* out_bias;                /* [1] or NULL                                        */
+  int32_t in_dim;                       /* feature_dim + 3                                    */
+  int32_t hidden_dim;
+  int32_t levels;                       /* 1..CLID_MAX_LEVELS                                 */
+  float sdf_scale;
+} ClidDecoder;
+
+/* Outputs of a forward query; any pointer may be NULL (not produced). */
+typedef struct ClidQueryOut {
+  float* sdf;        /* [n]        Decoder.sdf(z)                       (needs a decoder)   */
+  float* grad;       /* [n,3]      d sdf / d x, closed form of get_gradient (needs decoder) */
+  float* z;          /* [n,F+3]    weighted_first geo_features_vector                       */
+  float* weights;    /* [n,knn]    weight_vector                                             */
+  int32_t* knn_idx;  /* [n,knn]    gather row of each neighbour, ascending distance, -1 pad  */
+  int32_t* nn_count; /* [n]        valid candidates among the kc cells (not clamped to knn)  */
+  float* certainty;  /* [n]        queried_certainty                                        */
+} ClidQueryOut;
+
+CLID_API int clid_version(void);
+CLID_API const char* clid_last_error(void);
+
+/* Fused forward of the path
+ *   NeuralPoints.radius_neighborhood_search (model/neural_points.py:971-1030)
+ *   NeuralPoints.query_feature              (model/neural_points.py:553-769, weighted_first)
+ *   Decoder.sdf                             (model/decoder.py:58-82)
+ *   get_gradient                            (utils/tools.py:298-311, closed form)
+ * x: [n,3] query points; ts: [n] int32 query timestamps or NULL; dec may be NULL when only
+ * z / weights / counts are wanted. */
+CLID_API int clid_query_forward(const ClidMap* map, const ClidDecoder* dec, const float* x,
+                       const int32_t* ts, int64_t n, uint32_t flags, const ClidQueryOut* out,
+                       clid_stream_t stream);
+
+/* Backward of query_feature for callers that differentiate through it with torch autograd
+ * (what autograd does through index / sort / div / sum at model/neural_points.py:585-749 when
+ * utils/tools.py:298-311 get_gradient or loss.backward() runs).  knn_idx is the forward's
+ * ClidQueryOut.knn_idx; only the gather_* arrays, knn and feature_dim of `map` are read.
+ *   gx    [n,3]   = (d z / d x)^T gz                       (may be NULL)
+ *   gfeat [n_gather+1,F] += w_k * gz[:F] per neighbour     (may be NULL; caller zero-fills) */
+CLID_API int clid_query_backward(const ClidMap* map, const float* x, const int32_t* knn_idx,
+                                 const float* gz, int64_t n, uint32_t flags, float* gx,
+                                 float* gfeat, clid_stream_t stream);
+
+/* Backward of the above with respect to gz and the features (grad-of-grad: the analytic
+ * eikonal loss differentiates d sdf / d x, utils/mapper.py:695-696,780-798,835).
+ *   g_gz  [n,F+3] = (d z / d x) ggx
+ *   gfeat [n_gather+1,F] += (d w_k / d x . ggx) * gz[:F] per neighbour   (may be NULL)
+ * Second derivatives with respect to x itself are not produced (no caller needs them). */
+CLID_API int clid_query_backward_backward(const ClidMap* map, const float* x,
+                                          const int32_t* knn_idx, const float* gz,
+                                          const float* ggx, int64_t n, uint32_t flags,
+                                          float* g_gz, float* gfeat, clid_stream_t stream);
+
+/* NeuralPoints.radius_neighborhood_search (model/neural_points.py:971-1030): the raw candidate
+ * table.  dist2_out [n,kc] f32, idx_out [n,kc] int64 global ids (-1 invalid).  Only
+ * CLID_TIME_FILTER is read from flags. */
+CLID_API int clid_radius_search(const ClidMap* map, const float* x, int64_t n, uint32_t flags,
+                                float* dist2_out, int64_t* idx_out, clid_stream_t stream);
+
+/* NeuralPoints.query_certainty (model/neural_points.py:1032-1051): max of the GLOBAL
+ * point_certainties over the probed cells, invalid cells counting as 0.  out [n]. */
+CLID_API int clid_query_certainty(const ClidMap* map, const float* x, int64_t n,
+                                  const float* point_certainties, float* out, clid_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLID_SDF_H_ */

@@ -1,0 +1,84 @@
+"""CPU-side checks of the C-ABI boundary: the library builds, loads, exports every symbol that
+include/clid_sdf.h declares, validates arguments, and the product refuses CPU tensors."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from clid_slam_b200 import _lib
+    from clid_slam_b200 import build as _build
+
+    _build.build()
+    return _lib.load()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from clid_slam_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "clid_sdf.h")).read()
+    declared = set(re.findall(r"CLID_API\s+[\w\s\*]+?\b(clid_\w+)\s*\(", header))
+    assert declared, "no CLID_API declarations found"
+    assert declared == set(_lib.exported_symbols()), "ctypes signature table out of sync with the header"
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_version_and_error_string(lib):
+    assert lib.clid_version() == 1
+    rc = lib.clid_query_forward(None, None, None, None, 5, 0, None, None)
+    assert rc == -1
+    assert b"NULL" in lib.clid_last_error()
+
+
+def test_zero_queries_is_a_noop(lib):
+    from clid_slam_b200 import _lib
+
+    m, out = _lib.ClidMap(), _lib.ClidQueryOut()
+    assert lib.clid_query_forward(C.byref(m), None, None, None, 0, 0, C.byref(out), None) == 0
+    assert lib.clid_query_forward(C.byref(m), None, None, None, -3, 0, C.byref(out), None) == -1
+
+
+def test_struct_sizes_match_the_header(lib):
+    """Compile a tiny C program against the header and compare sizeof() with ctypes."""
+    import subprocess
+    import tempfile
+
+    from clid_slam_b200 import _lib
+
+    src = r"""
+    #include <stdio.h>
+    #include "clid_sdf.h"
+    int main(void) {
+      printf("%zu %zu %zu %zu\n", sizeof(ClidMap), sizeof(ClidDecoder), sizeof(ClidQueryOut), sizeof(ClidBricks));
+      return 0;
+    }"""
+    with tempfile.TemporaryDirectory() as tmp:
+        c_path, exe = os.path.join(tmp, "s.c"), os.path.join(tmp, "s")
+        open(c_path, "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c_path, "-o", exe])
+        sizes = [int(v) for v in subprocess.check_output([exe]).split()]
+    assert sizes == [C.sizeof(_lib.ClidMap), C.sizeof(_lib.ClidDecoder), C.sizeof(_lib.ClidQueryOut),
+                     C.sizeof(_lib.ClidBricks)]
+
+
+def test_product_refuses_cpu_tensors():
+    from clid_slam_b200.config import Config
+    from clid_slam_b200.model.neural_points import NeuralPoints
+
+    cfg = Config()
+    cfg.device = "cpu"
+    cfg.buffer_size = 1009
+    npm = NeuralPoints(cfg)
+    npm.travel_dist = torch.zeros(1)
+    pts = torch.rand(500, 3) * 10
+    npm.update(pts, torch.zeros(3), torch.eye(3), 0)  # host-side map maintenance works anywhere
+    assert npm.count() > 0
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        npm.query_feature(pts[:4])
