@@ -31,8 +31,9 @@ _f32p = C.c_void_p  # device pointers travel as plain addresses
 
 class ClidBricks(C.Structure):
     _fields_ = [
-        ("mask", C.c_void_p), ("base", C.c_void_p), ("records", C.c_void_p), ("stencil", C.c_void_p),
-        ("origin", C.c_int32 * 3), ("dims", C.c_int32 * 3), ("span", C.c_int32), ("n_records", C.c_int32),
+        ("headers", C.c_void_p), ("records", C.c_void_p), ("stencil", C.c_void_p),
+        ("origin", C.c_int32 * 3), ("dims", C.c_int32 * 3), ("span", C.c_int32), ("reach", C.c_int32),
+        ("n_records", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

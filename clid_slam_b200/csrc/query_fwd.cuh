@@ -103,41 +103,42 @@ __device__ __forceinline__ int search_hashed(const ClidMap& m, const int64_t* __
 }
 
 // ---- candidate enumeration through the brick index ---------------------------------------
+// Visits only occupied cells: span^3 header loads (16 B each), then one 16-byte record per
+// occupied neighbourhood cell.  `stencil` is this block's shared-memory copy of the table.
 template <int K>
-__device__ __forceinline__ int search_bricks(const ClidMap& m, const ClidBricks& b, float px, float py, float pz,
+__device__ __forceinline__ int search_bricks(const ClidMap& m, const ClidBricks& b,
+                                             const uint64_t* __restrict__ stencil, float px, float py, float pz,
                                              TopK<K>& top) {
-  const int gx = cell_of(px, m.resolution) - b.origin[0];
-  const int gy = cell_of(py, m.resolution) - b.origin[1];
-  const int gz = cell_of(pz, m.resolution) - b.origin[2];
-  // first brick the neighbourhood can touch; the stencil table is indexed by the in-brick
-  // position of the query cell and the brick offset inside the span^3 block
-  const int pad = 4 * (b.span - 1);  // cells of slack so (g + pad)/4 never goes negative for in-range queries
-  const int bx0 = ((gx + pad - 2) >> 2) - (b.span - 1), by0 = ((gy + pad - 2) >> 2) - (b.span - 1),
-            bz0 = ((gz + pad - 2) >> 2) - (b.span - 1);
-  const int lx = (gx + pad - 2) & 3, ly = (gy + pad - 2) & 3, lz = (gz + pad - 2) & 3;
-  const uint64_t* st = b.stencil + (size_t)((lz * 4 + ly) * 4 + lx) * (b.span * b.span * b.span);
+  // lower corner of the neighbourhood, in cells relative to the brick grid origin
+  const int rx = cell_of(px, m.resolution) - b.origin[0] - b.reach;
+  const int ry = cell_of(py, m.resolution) - b.origin[1] - b.reach;
+  const int rz = cell_of(pz, m.resolution) - b.origin[2] - b.reach;
+  const int bx0 = rx >> 2, by0 = ry >> 2, bz0 = rz >> 2;  // arithmetic shifts: floor for negatives
+  const int span = b.span;
+  const uint64_t* st = stencil + (((rz & 3) * 4 + (ry & 3)) * 4 + (rx & 3)) * (span * span * span);
+  const uint4* headers = reinterpret_cast<const uint4*>(b.headers);
+  const float4* records = reinterpret_cast<const float4*>(b.records);
   int count = 0;
-  for (int dz = 0; dz < b.span; ++dz) {
-    int bz = bz0 + dz;
+  for (int dz = 0; dz < span; ++dz) {
+    const int bz = bz0 + dz;
     if ((unsigned)bz >= (unsigned)b.dims[2]) continue;
-    for (int dy = 0; dy < b.span; ++dy) {
-      int by = by0 + dy;
+    for (int dy = 0; dy < span; ++dy) {
+      const int by = by0 + dy;
       if ((unsigned)by >= (unsigned)b.dims[1]) continue;
-      for (int dx = 0; dx < b.span; ++dx) {
-        int bx = bx0 + dx;
+      const int64_t row = ((int64_t)bz * b.dims[1] + by) * b.dims[0];
+      for (int dx = 0; dx < span; ++dx) {
+        const int bx = bx0 + dx;
         if ((unsigned)bx >= (unsigned)b.dims[0]) continue;
-        int64_t bi = ((int64_t)bz * b.dims[1] + by) * b.dims[0] + bx;
-        uint64_t occ = __ldg(b.mask + bi);
-        uint64_t want = occ & __ldg(st + (dz * b.span + dy) * b.span + dx);
-        if (!want) continue;
-        int base = __ldg(b.base + bi);
+        const uint4 h = __ldg(headers + row + bx);
+        const uint64_t occ = ((uint64_t)h.y << 32) | h.x;
+        uint64_t want = occ & st[(dz * span + dy) * span + dx];
         while (want) {
-          int bit = __ffsll((long long)want) - 1;
+          const int bit = __ffsll((long long)want) - 1;
           want &= want - 1;
-          int rec = base + __popcll(occ & ((1ull << bit) - 1ull));
-          float4 r = __ldg(reinterpret_cast<const float4*>(b.records) + rec);
-          float ex = r.x - px, ey = r.y - py, ez = r.z - pz;
-          float d2 = dist2_torch(ex, ey, ez);
+          const int rec = (int)h.z + __popcll(occ & ((1ull << bit) - 1ull));
+          const float4 r = __ldg(records + rec);
+          const float ex = r.x - px, ey = r.y - py, ez = r.z - pz;
+          const float d2 = dist2_torch(ex, ey, ez);
           if (!(d2 > m.max_valid_dist2)) {
             ++count;
             top.insert(d2, __float_as_int(r.w), -ex, -ey, -ez);
@@ -154,11 +155,15 @@ __global__ void __launch_bounds__(128) query_forward_kernel(const __grid_constan
   extern __shared__ __align__(16) float smem[];
   float* sm_dec = smem;
   constexpr int kDecFloats = H > 0 ? MlpLayout<(H > 0 ? H : 4), (H > 0 ? L : 1)>::kFloats : 0;
-  int64_t* cell_mod = reinterpret_cast<int64_t*>(smem + kDecFloats);
+  int64_t* cell_mod = reinterpret_cast<int64_t*>(smem + kDecFloats);  // hashed: per-cell hash residues
+  uint64_t* stencil = reinterpret_cast<uint64_t*>(smem + kDecFloats);  // bricks: neighbourhood stencils
   const ClidMap& m = p.map;
 
   if constexpr (H > 0) stage_decoder<H, L>(sm_dec, p.dec);
-  if constexpr (!kBricks) {
+  if constexpr (kBricks) {
+    const int n_st = 64 * p.bricks.span * p.bricks.span * p.bricks.span;
+    for (int i = threadIdx.x; i < n_st; i += blockDim.x) stencil[i] = p.bricks.stencil[i];
+  } else {
     for (int c = threadIdx.x; c < m.kc; c += blockDim.x) {
       int64_t h = m.neighbor_dx[3 * c] * m.primes[0] + m.neighbor_dx[3 * c + 1] * m.primes[1] +
                   m.neighbor_dx[3 * c + 2] * m.primes[2];
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(128) query_forward_kernel(const __grid_constan
     TopK<K> top;
     top.init();
     int count;
-    if constexpr (kBricks) count = search_bricks<K>(m, p.bricks, px, py, pz, top);
+    if constexpr (kBricks) count = search_bricks<K>(m, p.bricks, stencil, px, py, pz, top);
     else count = search_hashed<K>(m, cell_mod, px, py, pz, local, time_filter, top);
 
     // ---- inverse-distance weights (neural_points.py:688-706)

@@ -87,7 +87,38 @@ class NeuralPoints(nn.Module):
 
         self.cur_memory_mb = 0.0
         self.memory_footprint = []
+        self._map_version = 0      # bumped by every method that changes what a query can return
+        self._brick_cache = {}     # query_locally -> (key, BrickIndex | None); never pickled
         self.to(self.device)
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_brick_cache"] = {}
+        return state
+
+    def _touch(self) -> None:
+        self._map_version = getattr(self, "_map_version", 0) + 1
+
+    def brick_index(self, query_locally: bool):
+        """Cached brick index for the current map state (rebuilt lazily after any change), or None
+        when the compact index is not exact for this table (see ops/bricks.py)."""
+        from ..ops import bricks as _bricks
+
+        def addr(t):
+            return 0 if t is None else (t.data_ptr(), tuple(t.shape))
+
+        key = (getattr(self, "_map_version", 0), addr(self.buffer_pt_index), addr(self.neural_points),
+               addr(self.neighbor_dx), int(self.cur_ts), float(self.max_valid_dist2),
+               addr(self.local_neural_points) if query_locally else 0,
+               addr(self.global2local) if query_locally else 0,
+               addr(self.travel_dist) if query_locally else 0,
+               bool(self.temporal_local_map_on))
+        cache = self.__dict__.setdefault("_brick_cache", {})
+        hit = cache.get(bool(query_locally))
+        if hit is None or hit[0] != key:
+            hit = (key, _bricks.build(self, query_locally))
+            cache[bool(query_locally)] = hit
+        return hit[1]
 
     # ------------------------------------------------------------------ bookkeeping
     def is_empty(self) -> bool:
@@ -173,6 +204,7 @@ class NeuralPoints(nn.Module):
             self.color_features = torch.cat((self.color_features[:-1], fresh_col), 0)
         self.point_certainties = torch.cat((self.point_certainties, torch.zeros(n_new, device=dev, dtype=f32)), 0)
 
+        self._touch()
         self.reset_local_map(sensor_position, sensor_orientation, cur_ts, reboot_map=True)
         return new_point_ratio
 
@@ -181,6 +213,7 @@ class NeuralPoints(nn.Module):
         """Select the local window (travel-distance window on the creation stamp AND within
         local_map_radius of the sensor) and rebuild the local_* copies, the global->local remap and
         the trainable ``local_geo_features`` Parameter (model/neural_points.py:439-536)."""
+        self._touch()
         self.cur_ts = cur_ts
         self.max_ts = max(self.max_ts, cur_ts)
         dev = self.device
@@ -276,6 +309,7 @@ class NeuralPoints(nn.Module):
             return False
         if not self.silence:
             print("# Prune neural points: ", n_drop)
+        self._touch()
         keep = ~drop
         self.neural_points = self.neural_points[keep]
         self.point_orientations = self.point_orientations[keep]
@@ -298,6 +332,7 @@ class NeuralPoints(nn.Module):
         """Refill the voxel hash from scratch, one winner per voxel (closest creation stamp, or
         highest certainty), optionally dropping the losers (model/neural_points.py:840-929)."""
         res = self.resolution
+        self._touch()
         self.buffer_pt_index = torch.full((self.buffer_size,), -1, dtype=self.idx_dtype, device=self.device)
         if with_ts:
             if self.config.use_mid_ts:
@@ -341,10 +376,12 @@ class NeuralPoints(nn.Module):
         self.neighbor_dx = cube[inside].contiguous()
         self.neighbor_K = self.neighbor_dx.shape[0]
         self.max_valid_dist2 = 3 * ((num_nei_cells + 1) * self.resolution) ** 2
-        self.num_nei_cells_cur = int(num_nei_cells)
+        self._touch()
 
     def clear_temp(self, clean_more: bool = False) -> None:
         """Drop everything that is rebuilt on load before pickling (model/neural_points.py:1054-1074)."""
+        self._touch()
+        self._brick_cache = {}
         self.buffer_pt_index = None
         self.local_neural_points = None
         self.local_point_orientations = None

@@ -1,0 +1,166 @@
+"""Brick index: a compact per-frame voxel index that answers the hash probes of
+NeuralPoints.radius_neighborhood_search (model/neural_points.py:971-1030) without touching the
+400 MB `buffer_pt_index` table.
+
+Why it is exact.  A probe of cell C returns v = table[hash(C)].  By construction of the table
+(update / recreate_hash) hash(cell(v)) == hash(C).  If cell(v) != C the point sits in an aliasing
+cell C' = C + d with  d . primes == 0 (mod buffer_size),  d != 0.  A candidate is only kept when
+|p_v - x|^2 <= max_valid_dist2 = 3 ((n+1) res)^2, which bounds |C' - Q|_inf <= floor(sqrt(3)(n+1)+1)
+for the query cell Q, hence |d|_inf <= floor(sqrt(3)(n+1)+1) + n.  `hash_is_alias_free` checks by
+enumeration that no such d exists for the (primes, buffer_size) in use; then every surviving
+candidate of cell C is the point that (a) lies in C and (b) owns C's slot -- exactly what the index
+stores, with the per-point predicates (travel-distance window, global->local remap) folded in at
+build time.  When the check fails (tiny tables) callers stay on the hashed kernel.
+
+The index is rebuilt lazily whenever the map changes (per frame), with torch ops on the device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from functools import lru_cache
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+_PRIMES = (73856093, 19349669, 83492791)
+MAX_BRICKS = 1 << 26  # dense header array cap (1 GiB); larger boxes use the hashed kernel
+
+
+@lru_cache(maxsize=64)
+def hash_is_alias_free(buffer_size: int, reach: int) -> bool:
+    bound = int(math.floor(math.sqrt(3.0) * (reach + 1) + 1)) + reach
+    r = np.arange(-bound, bound + 1, dtype=np.int64)
+    d = np.stack(np.meshgrid(r, r, r, indexing="ij"), -1).reshape(-1, 3)
+    h = (d * np.array(_PRIMES, dtype=np.int64)).sum(-1) % int(buffer_size)
+    return int((h == 0).sum()) == 1  # only d == 0
+
+
+_STENCILS = {}
+
+
+def _stencil_table(offsets_cpu: torch.Tensor, reach: int, span: int) -> torch.Tensor:
+    key = (offsets_cpu.numpy().tobytes(), reach, span)
+    if key not in _STENCILS:
+        _STENCILS[key] = _make_stencil_table(offsets_cpu, reach, span)
+    return _STENCILS[key]
+
+
+def _make_stencil_table(offsets_cpu: torch.Tensor, reach: int, span: int) -> torch.Tensor:
+    inside = {tuple(int(v) for v in row) for row in offsets_cpu.tolist()}
+    table = np.zeros((64, span**3), dtype=np.uint64)
+    width = 2 * reach
+    for lz in range(4):
+        for ly in range(4):
+            for lx in range(4):
+                pos = (lz * 4 + ly) * 4 + lx
+                for dz in range(span):
+                    for dy in range(span):
+                        for dx in range(span):
+                            bits = 0
+                            for k in range(4):
+                                tz = 4 * dz + k - lz
+                                if tz < 0 or tz > width:
+                                    continue
+                                for j in range(4):
+                                    ty = 4 * dy + j - ly
+                                    if ty < 0 or ty > width:
+                                        continue
+                                    for i in range(4):
+                                        tx = 4 * dx + i - lx
+                                        if tx < 0 or tx > width:
+                                            continue
+                                        if (tx - reach, ty - reach, tz - reach) in inside:
+                                            bits |= 1 << (i + 4 * j + 16 * k)
+                            table[pos, (dz * span + dy) * span + dx] = bits
+    return torch.from_numpy(table.view(np.int64).reshape(-1).copy())
+
+
+class BrickIndex:
+    """Device tensors of one index plus the ClidBricks struct that points at them."""
+
+    def __init__(self, headers, records, stencil, origin, dims, span, reach):
+        self.headers, self.records, self.stencil = headers, records, stencil
+        s = _lib.ClidBricks()
+        s.headers = headers.data_ptr()
+        s.records = records.data_ptr()
+        s.stencil = stencil.data_ptr()
+        for i in range(3):
+            s.origin[i] = int(origin[i])
+            s.dims[i] = int(dims[i])
+        s.span, s.reach, s.n_records = int(span), int(reach), int(records.shape[0])
+        self.struct = s
+        self.n_bricks = int(dims[0]) * int(dims[1]) * int(dims[2])
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.headers, self.records, self.stencil))
+
+
+def build(npm, query_locally: bool) -> Optional[BrickIndex]:
+    """Index of the points a query of `npm` can return; None when the fast path is not exact or
+    not applicable (then the hashed kernel is used)."""
+    offsets_cpu = npm.neighbor_dx.detach().cpu()
+    reach = int(offsets_cpu.abs().max().item()) if offsets_cpu.numel() else 0
+    span = (2 * reach + 7) // 4
+    if span > 3 or npm.count() == 0:
+        return None
+    if not hash_is_alias_free(int(npm.buffer_size), reach):
+        return None
+    dev = npm.neural_points.device
+    res = float(npm.resolution)
+    primes = npm.primes
+
+    if query_locally:
+        gids = torch.nonzero(npm.local_mask[:-1]).flatten()
+        pts = npm.local_neural_points
+        rows = torch.arange(pts.shape[0], device=dev, dtype=torch.int32)
+    else:
+        gids = torch.arange(npm.count(), device=dev)
+        pts = npm.neural_points
+        rows = gids.to(torch.int32)
+    if pts.shape[0] == 0:
+        return None
+    cells = (pts / res).floor().to(torch.int64)
+    slots = torch.fmod((cells * primes).sum(-1), int(npm.buffer_size))
+    keep = npm.buffer_pt_index[slots] == gids  # the point owns its voxel's slot
+    if query_locally and npm.temporal_local_map_on:
+        td = npm.travel_dist.to(device=dev, dtype=torch.float32)
+        gap = torch.abs(td[npm.cur_ts] - td[npm.point_ts_create[gids].long()])
+        keep = keep & (gap < npm.diff_travel_dist_local)
+    if not bool(keep.any()):
+        return None
+    cells, pts, rows = cells[keep], pts[keep], rows[keep]
+
+    lo = cells.amin(0)
+    hi = cells.amax(0)
+    lo_c, hi_c = lo.cpu(), hi.cpu()
+    dims = [int((hi_c[i] - lo_c[i]) // 4 + 1) for i in range(3)]
+    n_bricks = dims[0] * dims[1] * dims[2]
+    if n_bricks > MAX_BRICKS:
+        return None
+    rel = cells - lo
+    brick = (rel[:, 0] >> 2) + dims[0] * ((rel[:, 1] >> 2) + dims[1] * (rel[:, 2] >> 2))
+    bit = (rel[:, 0] & 3) + 4 * (rel[:, 1] & 3) + 16 * (rel[:, 2] & 3)
+    order = torch.argsort(brick * 64 + bit)
+    brick, bit = brick[order], bit[order]
+
+    records = torch.empty(order.shape[0], 4, dtype=torch.float32, device=dev)
+    records[:, :3] = pts[order]
+    records[:, 3] = rows[order].view(torch.float32)
+
+    one = torch.ones((), dtype=torch.int64, device=dev)
+    mask = torch.zeros(n_bricks, dtype=torch.int64, device=dev)
+    mask.scatter_add_(0, brick, one << bit)  # distinct bits per brick: the sum is the OR
+    count = torch.zeros(n_bricks, dtype=torch.int64, device=dev)
+    count.scatter_add_(0, brick, torch.ones_like(brick))
+    base = torch.cumsum(count, 0) - count
+    headers = torch.empty(n_bricks, 4, dtype=torch.int32, device=dev)
+    headers[:, :2] = mask.view(torch.int32).view(n_bricks, 2)
+    headers[:, 2] = base.to(torch.int32)
+    headers[:, 3] = count.to(torch.int32)
+
+    stencil = _stencil_table(offsets_cpu, reach, span).to(dev)
+    return BrickIndex(headers, records, stencil, lo_c.tolist(), dims, span, reach)

@@ -3,6 +3,7 @@ launches libclid_sdf.so on the current CUDA stream.  CUDA only (no CPU fallback)
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -95,8 +96,12 @@ def _prep_ts(ts: Optional[torch.Tensor], n: int) -> Optional[torch.Tensor]:
 
 def forward(npm, decoder, x: torch.Tensor, ts: Optional[torch.Tensor], training_mode: bool, query_locally: bool,
             want_sdf=False, want_grad=False, want_z=False, want_weights=False, want_idx=False, want_count=False,
-            want_certainty=False, certainty_accum: Optional[torch.Tensor] = None, use_bricks: bool = False):
-    """One launch of clid_query_forward.  Returns a dict of the requested outputs."""
+            want_certainty=False, certainty_accum: Optional[torch.Tensor] = None,
+            use_bricks: Optional[bool] = None):
+    """One launch of clid_query_forward.  Returns a dict of the requested outputs.
+
+    use_bricks: None = use the brick index whenever it is exact for this map (default), False =
+    probe the reference's hash table, True = require the brick index."""
     lib = _lib.load()
     xd = _prep_points(x)
     n = xd.shape[0]
@@ -108,6 +113,18 @@ def forward(npm, decoder, x: torch.Tensor, ts: Optional[torch.Tensor], training_
     m, flags = map_struct(npm, query_locally, certainty_accum if training_mode else None)
     if training_mode:
         flags |= _lib.TRAINING_MODE
+    if use_bricks is None:
+        use_bricks = os.environ.get("CLID_DISABLE_BRICKS", "0") != "1"
+        bricks = npm.brick_index(query_locally) if use_bricks else None
+    elif use_bricks:
+        bricks = npm.brick_index(query_locally)
+        if bricks is None:
+            raise RuntimeError("the brick index is not available for this map (hash aliasing or empty map)")
+    else:
+        bricks = None
+    if bricks is not None:
+        m.bricks = C.pointer(bricks.struct)
+        flags |= _lib.USE_BRICKS
     dec_struct = None
     if decoder is not None:
         dec_struct = decoder.abi_struct()

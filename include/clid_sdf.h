@@ -52,17 +52,32 @@ enum ClidFlags {
   CLID_USE_BRICKS = 1 << 5     /* probe through ClidMap.bricks instead of the hash table */
 };
 
-/* Compact per-frame voxel index derived from the hash table (see DESIGN.md "brick index").
- * Built by clid_bricks_build(); gives bit-identical candidate sets to the hashed probe. */
+/* Brick index: a compact, per-frame restatement of "which neural point does the voxel hash
+ * return for cell C, and does it survive the time / locality filters" (DESIGN.md section 3).
+ * Space is cut into bricks of 4x4x4 voxels laid out densely over the bounding box of the
+ * indexed points.  Each brick header holds a 64-bit occupancy mask (bit = x + 4 y + 16 z) and
+ * the index of its first record; records are sorted by (brick, bit) so the record of an
+ * occupied cell is base + popcount(mask below its bit).  A query ANDs the masks of the
+ * span^3 bricks around it with a precomputed stencil of its neighbourhood and visits only
+ * occupied cells.  Candidate sets are identical to the hashed probe (the builder verifies
+ * the no-near-collision condition that makes this exact, else the hashed path is used). */
+typedef struct ClidBrickHeader {
+  uint64_t mask;
+  int32_t base;
+  int32_t count;
+} ClidBrickHeader;
+
 typedef struct ClidBricks {
-  const uint64_t* mask;   /* [nb] occupancy of the 4x4x4 cells of a brick                     */
-  const int32_t* base;    /* [nb] first record of the brick                                   */
-  const float* records;   /* [n_records,4] = (px, py, pz, bit-cast int32 gather row)          */
-  const uint64_t* stencil;/* [64 * span^3] neighbourhood masks by in-brick cell position      */
-  int32_t origin[3];      /* cell coordinate of brick (0,0,0)'s first cell                    */
-  int32_t dims[3];        /* bricks per axis                                                  */
-  int32_t span;           /* bricks per axis a neighbourhood can touch (2 for num_nei_cells<=2) */
+  const ClidBrickHeader* headers; /* [dims[0]*dims[1]*dims[2]], x fastest                      */
+  const float* records;           /* [n_records,4] = (px, py, pz, bit-cast int32 gather row)   */
+  const uint64_t* stencil;        /* [64][span^3] neighbourhood masks by in-brick position of
+                                     the neighbourhood's lower corner, then brick offset      */
+  int32_t origin[3];              /* cell coordinate of the first cell of brick (0,0,0)        */
+  int32_t dims[3];                /* bricks per axis                                           */
+  int32_t span;                   /* bricks per axis one neighbourhood can touch               */
+  int32_t reach;                  /* num_nei_cells: the neighbourhood is [-reach, reach]^3     */
   int32_t n_records;
+  int32_t reserved;
 } ClidBricks;
 
 /* Neural-point map state read by a query.  model/neural_points.py:79-133 */

@@ -48,8 +48,9 @@ def test_query_feature_matches_reference_fixture(name):
         gio.assert_close(npm.point_certainties, fx["after_certainties"], 1e-5, 1e-5, "certainty side effect")
 
 
+@pytest.mark.parametrize("bricks", [False, True], ids=["hashed", "bricks"])
 @pytest.mark.parametrize("name", gio.names("query"))
-def test_fused_forward_matches_reference_fixture(name):
+def test_fused_forward_matches_reference_fixture(name, bricks):
     from clid_slam_b200 import fused
 
     fx = gio.load("query", name)
@@ -58,7 +59,10 @@ def test_fused_forward_matches_reference_fixture(name):
     dec = hp.product_decoder(m.cfg, gio.decoder_params(fx))
     locally = bool(fx["query_locally"])
     x = gio.t(fx["x"]).cuda()
-    sdf, grad, nn, cert = fused.sdf_and_gradient(npm, dec, x, None, training_mode=False, query_locally=locally)
+    if bricks:
+        assert npm.brick_index(locally) is not None, "brick index unexpectedly unavailable"
+    sdf, grad, nn, cert = fused.sdf_and_gradient(npm, dec, x, None, training_mode=False, query_locally=locally,
+                                                 use_bricks=bricks)
     assert torch.equal(nn.cpu().long(), gio.t(fx["out_nn"]))
     gio.assert_close(sdf, fx["out_sdf"], hp.SDF_RTOL, hp.SDF_ATOL, "fused sdf")
     gio.assert_close(grad, fx["out_grad"], hp.GRAD_RTOL, hp.GRAD_ATOL, "fused grad")
@@ -67,8 +71,9 @@ def test_fused_forward_matches_reference_fixture(name):
     gio.assert_close(npm.local_point_certainties, m.local_certainties, 0, 0, "no side effect")
 
 
+@pytest.mark.parametrize("bricks", [False, True], ids=["hashed", "bricks"])
 @pytest.mark.parametrize("layer_norm,levels,hidden", [(False, 1, 64), (True, 1, 64), (False, 2, 32)])
-def test_fused_forward_matches_oracle_large(layer_norm, levels, hidden):
+def test_fused_forward_matches_oracle_large(layer_norm, levels, hidden, bricks):
     from clid_slam_b200 import fused
 
     cfg = oc.OracleConfig(buffer_size=2_000_003, layer_norm_on=layer_norm, geo_mlp_level=levels,
@@ -85,7 +90,7 @@ def test_fused_forward_matches_oracle_large(layer_norm, levels, hidden):
     sdf_o = oc.decoder_sdf(params, z, cfg.sdf_scale)
     grad_o = oc.sdf_gradient(xo, sdf_o)
 
-    sdf, grad, nn_g, cert_g = fused.sdf_and_gradient(npm, dec, x.cuda())
+    sdf, grad, nn_g, cert_g = fused.sdf_and_gradient(npm, dec, x.cuda(), use_bricks=bricks)
     assert torch.equal(nn_g.cpu().long(), nn)
     gio.assert_close(sdf, sdf_o, hp.SDF_RTOL, hp.SDF_ATOL, "sdf")
     gio.assert_close(grad, grad_o, hp.GRAD_RTOL, hp.GRAD_ATOL, "grad")
