@@ -64,7 +64,7 @@ static int check_map(const ClidMap* m, uint32_t flags) {
     if (!m->bricks) return set_error(CLID_EINVAL, "CLID_USE_BRICKS without ClidMap.bricks");
     const ClidBricks* b = m->bricks;
     if (!b->headers || !b->records || !b->stencil) return set_error(CLID_EINVAL, "brick index arrays are NULL");
-    if (b->span < 1 || b->span > 3) return set_error(CLID_EUNSUPPORTED, "brick span %d outside 1..3", b->span);
+    if (b->span < 1 || b->span > 2) return set_error(CLID_EUNSUPPORTED, "brick span %d outside 1..2", b->span);
     if (!aligned16(b->headers) || !aligned16(b->records)) return set_error(CLID_EINVAL, "brick arrays must be 16-byte aligned");
   } else {
     if (m->kc < 1 || m->kc > CLID_MAX_KC) return set_error(CLID_EINVAL, "kc %d outside 1..%d", m->kc, CLID_MAX_KC);
@@ -82,9 +82,10 @@ template <int H, int L, int K, bool kBricks>
 static int launch_query(const QueryParams& p, cudaStream_t stream) {
   DeviceInfo info;
   if (int rc = device_info(&info)) return rc;
-  constexpr int kThreads = 128;
+  constexpr int kThreads = kQueryThreads;
   constexpr int kDecFloats = H > 0 ? MlpLayout<(H > 0 ? H : 4), (H > 0 ? L : 1)>::kFloats : 0;
-  size_t smem = kDecFloats * sizeof(float) + (kBricks ? 64 * 27 * sizeof(uint64_t) : CLID_MAX_KC * sizeof(int64_t));
+  size_t smem = kDecFloats * sizeof(float) +
+                (kBricks ? 64 * kBrickSlots * sizeof(uint64_t) + sizeof(BrickScratch) : CLID_MAX_KC * sizeof(int64_t));
   auto kern = query_forward_kernel<H, L, K, kBricks>;
   static thread_local int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {

@@ -1,4 +1,4 @@
-// Fused forward: voxel-hash kNN search -> IDW feature blend -> decoder MLP -> closed-form
+// Fused forward: voxel kNN search -> IDW feature blend -> decoder MLP -> closed-form
 // d sdf / d x.  One thread per query; everything between the probe and the outputs lives
 // in registers.  Replaces (reference, CPU/GPU eager torch):
 //   model/neural_points.py:971-1030 radius_neighborhood_search
@@ -9,6 +9,9 @@
 #include "common.cuh"
 
 namespace clid {
+
+constexpr int kQueryThreads = 128;
+constexpr int kBrickSlots = 8;  // span 2: a neighbourhood touches at most 2x2x2 bricks
 
 struct QueryParams {
   ClidMap map;
@@ -21,43 +24,43 @@ struct QueryParams {
   uint32_t flags;
 };
 
-// ascending top-K by squared distance, ties keep the earlier candidate
+// Ascending top-K by squared distance with an integer payload; ties keep the earlier candidate.
 template <int K>
 struct TopK {
   float d[K];
   int id[K];
-  float vx[K], vy[K], vz[K];
   __device__ __forceinline__ void init() {
 #pragma unroll
-    for (int k = 0; k < K; ++k) { d[k] = __int_as_float(0x7f800000); id[k] = -1; vx[k] = vy[k] = vz[k] = 0.f; }
+    for (int k = 0; k < K; ++k) { d[k] = __int_as_float(0x7f800000); id[k] = -1; }
   }
-  __device__ __forceinline__ void insert(float dc, int ic, float x, float y, float z) {
+  __device__ __forceinline__ void insert(float dc, int ic) {
     if (!(dc < d[K - 1])) return;
+    // one pass of compare-exchange from the front: the carried element is always the larger one
 #pragma unroll
-    for (int k = K - 1; k >= 1; --k) {
-      bool shift = dc < d[k - 1];  // candidate lands before slot k: slot k takes slot k-1
-      bool here = !shift && dc < d[k];
-      d[k] = shift ? d[k - 1] : (here ? dc : d[k]);
-      id[k] = shift ? id[k - 1] : (here ? ic : id[k]);
-      vx[k] = shift ? vx[k - 1] : (here ? x : vx[k]);
-      vy[k] = shift ? vy[k - 1] : (here ? y : vy[k]);
-      vz[k] = shift ? vz[k - 1] : (here ? z : vz[k]);
+    for (int k = 0; k < K; ++k) {
+      const bool lt = dc < d[k];
+      const float dk = d[k];
+      const int ik = id[k];
+      d[k] = lt ? dc : dk;
+      id[k] = lt ? ic : ik;
+      dc = lt ? dk : dc;
+      ic = lt ? ik : ic;
     }
-    if (dc < d[0]) { d[0] = dc; id[0] = ic; vx[0] = x; vy[0] = y; vz[0] = z; }
   }
 };
 
 // ---- candidate enumeration through the reference's hash table ----------------------------
+// Payload of the top-K: gather row (local row with CLID_QUERY_LOCALLY, else global id).
 template <int K>
 __device__ __forceinline__ int search_hashed(const ClidMap& m, const int64_t* __restrict__ cell_mod, float px,
-                                             float py, float pz, const bool kLocal, const bool kTimeFilter,
+                                             float py, float pz, const bool local, const bool time_filter,
                                              TopK<K>& top) {
   constexpr int U = 9;
   const int gx = cell_of(px, m.resolution), gy = cell_of(py, m.resolution), gz = cell_of(pz, m.resolution);
   const int64_t B = m.buffer_size;
   const int64_t m0 = floor_mod((int64_t)gx * m.primes[0] + (int64_t)gy * m.primes[1] + (int64_t)gz * m.primes[2], B);
   float td_cur = 0.f;
-  if (kTimeFilter) td_cur = m.travel_dist[m.cur_ts];
+  if (time_filter) td_cur = m.travel_dist[m.cur_ts];
   int count = 0;
   for (int c0 = 0; c0 < m.kc; c0 += U) {
     int gi[U];
@@ -80,22 +83,21 @@ __device__ __forceinline__ int search_hashed(const ClidMap& m, const int64_t* __
       int g = gi[u] < 0 ? 0 : gi[u];  // invalid lanes read row 0 (always mapped); result discarded
       const float* p = m.neural_points + 3 * (int64_t)g;
       cx[u] = __ldg(p); cy[u] = __ldg(p + 1); cz[u] = __ldg(p + 2);
-      li[u] = kLocal ? (int)__ldg(m.global2local + g) : g;
-      tsc[u] = kTimeFilter ? __ldg(m.point_ts_create + g) : 0;
+      li[u] = local ? (int)__ldg(m.global2local + g) : g;
+      tsc[u] = time_filter ? __ldg(m.point_ts_create + g) : 0;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       bool ok = gi[u] >= 0;
-      if (kTimeFilter) {
+      if (time_filter) {
         float gap = fabsf(td_cur - __ldg(m.travel_dist + tsc[u]));
         ok = ok && (gap < m.diff_travel_dist_local);
       }
-      float ex = cx[u] - px, ey = cy[u] - py, ez = cz[u] - pz;  // neighbour - query, as the reference
-      float d2 = dist2_torch(ex, ey, ez);
+      float d2 = dist2_torch(cx[u] - px, cy[u] - py, cz[u] - pz);  // neighbour - query, as the reference
       ok = ok && !(d2 > m.max_valid_dist2) && li[u] >= 0;
       if (ok) {
         ++count;
-        top.insert(d2, li[u], -ex, -ey, -ez);
+        top.insert(d2, li[u]);
       }
     }
   }
@@ -103,47 +105,68 @@ __device__ __forceinline__ int search_hashed(const ClidMap& m, const int64_t* __
 }
 
 // ---- candidate enumeration through the brick index ---------------------------------------
-// Visits only occupied cells: span^3 header loads (16 B each), then one 16-byte record per
-// occupied neighbourhood cell.  `stencil` is this block's shared-memory copy of the table.
+// Payload of the top-K: record index.  Phase 1 (warp-converged) loads the <= 8 brick headers
+// and compacts the non-empty (want, occupancy, base) triples into this thread's column of
+// shared memory.  Phase 2 walks them with one candidate per lane per iteration, so a warp
+// iterates max-over-lanes(candidates) times instead of diverging inside nested loops.
+struct BrickScratch {
+  uint64_t want[kBrickSlots][kQueryThreads];
+  uint64_t occ[kBrickSlots][kQueryThreads];
+  int base[kBrickSlots][kQueryThreads];
+};
+
 template <int K>
 __device__ __forceinline__ int search_bricks(const ClidMap& m, const ClidBricks& b,
-                                             const uint64_t* __restrict__ stencil, float px, float py, float pz,
-                                             TopK<K>& top) {
+                                             const uint64_t* __restrict__ stencil, BrickScratch& sc, bool live,
+                                             float px, float py, float pz, TopK<K>& top) {
+  const int tid = threadIdx.x;
   // lower corner of the neighbourhood, in cells relative to the brick grid origin
   const int rx = cell_of(px, m.resolution) - b.origin[0] - b.reach;
   const int ry = cell_of(py, m.resolution) - b.origin[1] - b.reach;
   const int rz = cell_of(pz, m.resolution) - b.origin[2] - b.reach;
   const int bx0 = rx >> 2, by0 = ry >> 2, bz0 = rz >> 2;  // arithmetic shifts: floor for negatives
   const int span = b.span;
-  const uint64_t* st = stencil + (((rz & 3) * 4 + (ry & 3)) * 4 + (rx & 3)) * (span * span * span);
+  const int nslots = span * span * span;
+  const uint64_t* st = stencil + (((rz & 3) * 4 + (ry & 3)) * 4 + (rx & 3)) * nslots;
   const uint4* headers = reinterpret_cast<const uint4*>(b.headers);
   const float4* records = reinterpret_cast<const float4*>(b.records);
-  int count = 0;
-  for (int dz = 0; dz < span; ++dz) {
-    const int bz = bz0 + dz;
-    if ((unsigned)bz >= (unsigned)b.dims[2]) continue;
-    for (int dy = 0; dy < span; ++dy) {
-      const int by = by0 + dy;
-      if ((unsigned)by >= (unsigned)b.dims[1]) continue;
-      const int64_t row = ((int64_t)bz * b.dims[1] + by) * b.dims[0];
-      for (int dx = 0; dx < span; ++dx) {
-        const int bx = bx0 + dx;
-        if ((unsigned)bx >= (unsigned)b.dims[0]) continue;
-        const uint4 h = __ldg(headers + row + bx);
-        const uint64_t occ = ((uint64_t)h.y << 32) | h.x;
-        uint64_t want = occ & st[(dz * span + dy) * span + dx];
-        while (want) {
-          const int bit = __ffsll((long long)want) - 1;
-          want &= want - 1;
-          const int rec = (int)h.z + __popcll(occ & ((1ull << bit) - 1ull));
-          const float4 r = __ldg(records + rec);
-          const float ex = r.x - px, ey = r.y - py, ez = r.z - pz;
-          const float d2 = dist2_torch(ex, ey, ez);
-          if (!(d2 > m.max_valid_dist2)) {
-            ++count;
-            top.insert(d2, __float_as_int(r.w), -ex, -ey, -ez);
-          }
-        }
+
+  int nfill = 0;
+#pragma unroll
+  for (int s = 0; s < kBrickSlots; ++s) {
+    if (s < nslots) {
+      const int dx = s % span, dy = (s / span) % span, dz = s / (span * span);
+      const int bx = bx0 + dx, by = by0 + dy, bz = bz0 + dz;
+      const bool in = live && (unsigned)bx < (unsigned)b.dims[0] && (unsigned)by < (unsigned)b.dims[1] &&
+                      (unsigned)bz < (unsigned)b.dims[2];
+      uint4 h = make_uint4(0, 0, 0, 0);
+      if (in) h = __ldg(headers + ((int64_t)bz * b.dims[1] + by) * b.dims[0] + bx);
+      const uint64_t occ = ((uint64_t)h.y << 32) | h.x;
+      const uint64_t want = occ & st[s];
+      if (want) {
+        sc.want[nfill][tid] = want;
+        sc.occ[nfill][tid] = occ;
+        sc.base[nfill][tid] = (int)h.z;
+        ++nfill;
+      }
+    }
+  }
+
+  int count = 0, cur = 0;
+  uint64_t w = 0, occ = 0;
+  int base = 0;
+  if (nfill > 0) { w = sc.want[0][tid]; occ = sc.occ[0][tid]; base = sc.base[0][tid]; }
+  while (__any_sync(0xffffffffu, w != 0)) {
+    if (w) {
+      const int bit = __ffsll((long long)w) - 1;
+      w &= w - 1;
+      const int rec = base + __popcll(occ & ((1ull << bit) - 1ull));
+      const float4 r = __ldg(records + rec);
+      if (w == 0 && ++cur < nfill) { w = sc.want[cur][tid]; occ = sc.occ[cur][tid]; base = sc.base[cur][tid]; }
+      const float d2 = dist2_torch(r.x - px, r.y - py, r.z - pz);
+      if (!(d2 > m.max_valid_dist2)) {
+        ++count;
+        top.insert(d2, rec);
       }
     }
   }
@@ -151,12 +174,13 @@ __device__ __forceinline__ int search_bricks(const ClidMap& m, const ClidBricks&
 }
 
 template <int H, int L, int K, bool kBricks>
-__global__ void __launch_bounds__(128) query_forward_kernel(const __grid_constant__ QueryParams p) {
+__global__ void __launch_bounds__(kQueryThreads) query_forward_kernel(const __grid_constant__ QueryParams p) {
   extern __shared__ __align__(16) float smem[];
   float* sm_dec = smem;
   constexpr int kDecFloats = H > 0 ? MlpLayout<(H > 0 ? H : 4), (H > 0 ? L : 1)>::kFloats : 0;
   int64_t* cell_mod = reinterpret_cast<int64_t*>(smem + kDecFloats);  // hashed: per-cell hash residues
-  uint64_t* stencil = reinterpret_cast<uint64_t*>(smem + kDecFloats);  // bricks: neighbourhood stencils
+  uint64_t* stencil = reinterpret_cast<uint64_t*>(smem + kDecFloats);  // bricks: 64 x 8 neighbourhood stencils
+  BrickScratch& scratch = *reinterpret_cast<BrickScratch*>(smem + kDecFloats + 2 * 64 * kBrickSlots);
   const ClidMap& m = p.map;
 
   if constexpr (H > 0) stage_decoder<H, L>(sm_dec, p.dec);
@@ -179,26 +203,47 @@ __global__ void __launch_bounds__(128) query_forward_kernel(const __grid_constan
   const float slope = (p.flags & CLID_LEAKY_RELU) ? kLeakySlope : 0.f;
   const int knn = m.knn;
 
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < p.n; q += (int64_t)gridDim.x * blockDim.x) {
-    const float px = p.x[3 * q], py = p.x[3 * q + 1], pz = p.x[3 * q + 2];
+  // block-uniform trip count: every lane stays in the loop so warp votes see full warps
+  for (int64_t q0 = (int64_t)blockIdx.x * blockDim.x; q0 < p.n; q0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = q0 + threadIdx.x;
+    const bool live = q < p.n;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (live) { px = p.x[3 * q]; py = p.x[3 * q + 1]; pz = p.x[3 * q + 2]; }
     TopK<K> top;
     top.init();
-    int count;
-    if constexpr (kBricks) count = search_bricks<K>(m, p.bricks, stencil, px, py, pz, top);
-    else count = search_hashed<K>(m, cell_mod, px, py, pz, local, time_filter, top);
+    int count = 0;
+    if constexpr (kBricks) count = search_bricks<K>(m, p.bricks, stencil, scratch, live, px, py, pz, top);
+    else if (live) count = search_hashed<K>(m, cell_mod, px, py, pz, local, time_filter, top);
+    if (!live) continue;
 
-    // ---- inverse-distance weights (neural_points.py:688-706)
-    float w[K], u[K];
+    // ---- neighbour rows, offsets and inverse-distance weights (neural_points.py:653-706)
+    int row[K];
+    float vx[K], vy[K], vz[K], w[K], u[K];
     float S = 0.f;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      bool valid = k < knn && top.id[k] >= 0;
-      if (!valid) top.id[k] = -1;
-      u[k] = valid ? 1.0f / (top.d[k] + kIdwEps) : 0.f;
-      S += u[k];
+      const bool valid = k < knn && top.id[k] >= 0;
+      row[k] = -1;
+      vx[k] = vy[k] = vz[k] = 0.f;
+      u[k] = 0.f;
+      if (valid) {
+        float qx, qy, qz;
+        if constexpr (kBricks) {
+          const float4 r = __ldg(reinterpret_cast<const float4*>(p.bricks.records) + top.id[k]);
+          qx = r.x; qy = r.y; qz = r.z;
+          row[k] = __float_as_int(r.w);
+        } else {
+          row[k] = top.id[k];
+          const float* g = m.gather_points + 3 * (int64_t)row[k];
+          qx = __ldg(g); qy = __ldg(g + 1); qz = __ldg(g + 2);
+        }
+        vx[k] = px - qx; vy[k] = py - qy; vz[k] = pz - qz;
+        u[k] = 1.0f / (top.d[k] + kIdwEps);
+        S += u[k];
+      }
     }
 #pragma unroll
-    for (int k = 0; k < K; ++k) w[k] = top.id[k] >= 0 ? u[k] / S : 0.f;
+    for (int k = 0; k < K; ++k) w[k] = row[k] >= 0 ? u[k] / S : 0.f;
 
     // ---- gather + blend
     float z[kIn];
@@ -208,18 +253,18 @@ __global__ void __launch_bounds__(128) query_forward_kernel(const __grid_constan
     float f[K][kFeat];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      if (top.id[k] >= 0) {
-        const float4* row = reinterpret_cast<const float4*>(m.gather_features + (int64_t)top.id[k] * kFeat);
-        float4 f0 = __ldg(row), f1 = __ldg(row + 1);
+      if (row[k] >= 0) {
+        const float4* fr = reinterpret_cast<const float4*>(m.gather_features + (int64_t)row[k] * kFeat);
+        float4 f0 = __ldg(fr), f1 = __ldg(fr + 1);
         f[k][0] = f0.x; f[k][1] = f0.y; f[k][2] = f0.z; f[k][3] = f0.w;
         f[k][4] = f1.x; f[k][5] = f1.y; f[k][6] = f1.z; f[k][7] = f1.w;
         if (layer_norm) { float mu, rs; layer_norm8(f[k], mu, rs); }
-        if (p.out.certainty) cert = fmaf(__ldg(m.gather_certainties + top.id[k]), w[k], cert);
+        if (p.out.certainty) cert = fmaf(__ldg(m.gather_certainties + row[k]), w[k], cert);
 #pragma unroll
         for (int i = 0; i < kFeat; ++i) z[i] = fmaf(w[k], f[k][i], z[i]);
-        z[8] = fmaf(w[k], top.vx[k], z[8]);
-        z[9] = fmaf(w[k], top.vy[k], z[9]);
-        z[10] = fmaf(w[k], top.vz[k], z[10]);
+        z[8] = fmaf(w[k], vx[k], z[8]);
+        z[9] = fmaf(w[k], vy[k], z[9]);
+        z[10] = fmaf(w[k], vz[k], z[10]);
       } else {
 #pragma unroll
         for (int i = 0; i < kFeat; ++i) f[k][i] = 0.f;
@@ -230,9 +275,9 @@ __global__ void __launch_bounds__(128) query_forward_kernel(const __grid_constan
     if (training) {
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        if (top.id[k] >= 0) {
-          atomicAdd(m.certainty_accum + top.id[k], w[k]);
-          if (p.ts && m.gather_ts_update) atomicMax(m.gather_ts_update + top.id[k], p.ts[q]);
+        if (row[k] >= 0) {
+          atomicAdd(m.certainty_accum + row[k], w[k]);
+          if (p.ts && m.gather_ts_update) atomicMax(m.gather_ts_update + row[k], p.ts[q]);
         }
       }
     }
@@ -245,20 +290,14 @@ __global__ void __launch_bounds__(128) query_forward_kernel(const __grid_constan
       for (int i = 0; i < kIn; ++i) p.out.z[q * kIn + i] = z[i];
     }
     if (p.out.weights) {
-      for (int k = 0; k < knn; ++k) {
-        float wk = 0.f;
 #pragma unroll
-        for (int kk = 0; kk < K; ++kk) wk = kk == k ? w[kk] : wk;
-        p.out.weights[q * knn + k] = wk;
-      }
+      for (int k = 0; k < K; ++k)
+        if (k < knn) p.out.weights[q * knn + k] = w[k];
     }
     if (p.out.knn_idx) {
-      for (int k = 0; k < knn; ++k) {
-        int ik = -1;
 #pragma unroll
-        for (int kk = 0; kk < K; ++kk) ik = kk == k ? top.id[kk] : ik;
-        p.out.knn_idx[q * knn + k] = ik;
-      }
+      for (int k = 0; k < K; ++k)
+        if (k < knn) p.out.knn_idx[q * knn + k] = row[k];
     }
 
     // ---- decoder + closed-form spatial gradient
@@ -276,15 +315,15 @@ __global__ void __launch_bounds__(128) query_forward_kernel(const __grid_constan
           const float invS = 1.0f / S;
 #pragma unroll
           for (int k = 0; k < K; ++k) {
-            if (top.id[k] >= 0) {
-              float ck = a[8] * top.vx[k] + a[9] * top.vy[k] + a[10] * top.vz[k];
+            if (row[k] >= 0) {
+              float ck = a[8] * vx[k] + a[9] * vy[k] + a[10] * vz[k];
 #pragma unroll
               for (int i = 0; i < kFeat; ++i) ck = fmaf(f[k][i], a[i], ck);
               // d u_k / d x = -2 u_k^2 v_k ; sum_k c_k d w_k / d x = (1/S) sum_k (c_k - cbar) d u_k / d x
-              float coef = (ck - cbar) * (-2.f * u[k] * u[k]) * invS;
-              gx = fmaf(coef, top.vx[k], gx);
-              gy = fmaf(coef, top.vy[k], gy);
-              gz = fmaf(coef, top.vz[k], gz);
+              const float coef = (ck - cbar) * (-2.f * u[k] * u[k]) * invS;
+              gx = fmaf(coef, vx[k], gx);
+              gy = fmaf(coef, vy[k], gy);
+              gz = fmaf(coef, vz[k], gz);
             }
           }
           gx += a[8]; gy += a[9]; gz += a[10];  // sum_k w_k == 1
