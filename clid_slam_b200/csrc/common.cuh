@@ -31,6 +31,10 @@ __device__ __forceinline__ float dist2_torch(float dx, float dy, float dz) {
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // ---- decoder weights staged in shared memory --------------------------------------
 // layout (floats): W0[H][kInPad] | b0[H] | {Wl[H][H] | bl[H]} (levels-1) | wout[H] | bout | pad
 template <int H, int L>
@@ -142,6 +146,12 @@ __device__ __forceinline__ void mlp_value_and_input_grad(const float* __restrict
       a[8] = fmaf(c, r2.x, a[8]); a[9] = fmaf(c, r2.y, a[9]); a[10] = fmaf(c, r2.z, a[10]);
     }
   }
+}
+
+__device__ __forceinline__ void load_feature_row(const float* __restrict__ feats, int id, float (&f)[kFeat]) {
+  const float4* row = reinterpret_cast<const float4*>(feats + (int64_t)id * kFeat);
+  float4 a = __ldg(row), b = __ldg(row + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
 // LayerNorm over the 8 feature channels, no affine (F.layer_norm(x, [8])).

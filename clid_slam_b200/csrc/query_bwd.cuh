@@ -46,12 +46,6 @@ __device__ __forceinline__ void load_neighbors(const ClidMap& m, const int32_t* 
   for (int k = 0; k < K; ++k) nb.w[k] = nb.id[k] >= 0 ? nb.u[k] / nb.S : 0.f;
 }
 
-__device__ __forceinline__ void load_feature_row(const float* __restrict__ feats, int id, float (&f)[kFeat]) {
-  const float4* row = reinterpret_cast<const float4*>(feats + (int64_t)id * kFeat);
-  float4 a = __ldg(row), b = __ldg(row + 1);
-  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-}
-
 // vector-Jacobian product of y = LN(raw) (no affine): t -> rstd * (t - mean(t) - y * mean(t * y))
 __device__ __forceinline__ void layer_norm8_vjp(const float (&y)[kFeat], float rstd, float (&t)[kFeat]) {
   float mt = 0.f, mty = 0.f;

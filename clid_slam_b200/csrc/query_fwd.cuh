@@ -148,6 +148,11 @@ __device__ __forceinline__ int search_bricks(const ClidMap& m, const ClidBricks&
         sc.occ[nfill][tid] = occ;
         sc.base[nfill][tid] = (int)h.z;
         ++nfill;
+        // pull the 128-byte lines that hold this brick's wanted records towards L2 now, so the
+        // serial walk below finds them there instead of paying one DRAM round trip per step
+        const int first = (int)h.z + __popcll(occ & ((want & (0 - want)) - 1ull));
+        const int last = (int)h.z + __popcll(occ & ((1ull << (63 - __clzll((long long)want))) - 1ull));
+        for (int line = first >> 3; line <= (last >> 3); ++line) prefetch_l2(records + 8 * line);
       }
     }
   }
@@ -166,7 +171,10 @@ __device__ __forceinline__ int search_bricks(const ClidMap& m, const ClidBricks&
       const float d2 = dist2_torch(r.x - px, r.y - py, r.z - pz);
       if (!(d2 > m.max_valid_dist2)) {
         ++count;
-        top.insert(d2, rec);
+        if (d2 < top.d[K - 1]) {
+          prefetch_l2(m.gather_features + (int64_t)__float_as_int(r.w) * kFeat);  // likely neighbour
+          top.insert(d2, rec);
+        }
       }
     }
   }
@@ -174,7 +182,7 @@ __device__ __forceinline__ int search_bricks(const ClidMap& m, const ClidBricks&
 }
 
 template <int H, int L, int K, bool kBricks>
-__global__ void __launch_bounds__(kQueryThreads) query_forward_kernel(const __grid_constant__ QueryParams p) {
+__global__ void __launch_bounds__(kQueryThreads, 4) query_forward_kernel(const __grid_constant__ QueryParams p) {
   extern __shared__ __align__(16) float smem[];
   float* sm_dec = smem;
   constexpr int kDecFloats = H > 0 ? MlpLayout<(H > 0 ? H : 4), (H > 0 ? L : 1)>::kFloats : 0;
@@ -250,24 +258,18 @@ __global__ void __launch_bounds__(kQueryThreads) query_forward_kernel(const __gr
 #pragma unroll
     for (int i = 0; i < kIn; ++i) z[i] = 0.f;
     float cert = 0.f;
-    float f[K][kFeat];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       if (row[k] >= 0) {
-        const float4* fr = reinterpret_cast<const float4*>(m.gather_features + (int64_t)row[k] * kFeat);
-        float4 f0 = __ldg(fr), f1 = __ldg(fr + 1);
-        f[k][0] = f0.x; f[k][1] = f0.y; f[k][2] = f0.z; f[k][3] = f0.w;
-        f[k][4] = f1.x; f[k][5] = f1.y; f[k][6] = f1.z; f[k][7] = f1.w;
-        if (layer_norm) { float mu, rs; layer_norm8(f[k], mu, rs); }
+        float f[kFeat];
+        load_feature_row(m.gather_features, row[k], f);
+        if (layer_norm) { float mu, rs; layer_norm8(f, mu, rs); }
         if (p.out.certainty) cert = fmaf(__ldg(m.gather_certainties + row[k]), w[k], cert);
 #pragma unroll
-        for (int i = 0; i < kFeat; ++i) z[i] = fmaf(w[k], f[k][i], z[i]);
+        for (int i = 0; i < kFeat; ++i) z[i] = fmaf(w[k], f[i], z[i]);
         z[8] = fmaf(w[k], vx[k], z[8]);
         z[9] = fmaf(w[k], vy[k], z[9]);
         z[10] = fmaf(w[k], vz[k], z[10]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < kFeat; ++i) f[k][i] = 0.f;
       }
     }
 
@@ -316,9 +318,14 @@ __global__ void __launch_bounds__(kQueryThreads) query_forward_kernel(const __gr
 #pragma unroll
           for (int k = 0; k < K; ++k) {
             if (row[k] >= 0) {
+              // the feature row is re-read (L1/L2-resident) instead of being held in 48 registers
+              // across the MLP
+              float f[kFeat];
+              load_feature_row(m.gather_features, row[k], f);
+              if (layer_norm) { float mu, rs; layer_norm8(f, mu, rs); }
               float ck = a[8] * vx[k] + a[9] * vy[k] + a[10] * vz[k];
 #pragma unroll
-              for (int i = 0; i < kFeat; ++i) ck = fmaf(f[k][i], a[i], ck);
+              for (int i = 0; i < kFeat; ++i) ck = fmaf(f[i], a[i], ck);
               // d u_k / d x = -2 u_k^2 v_k ; sum_k c_k d w_k / d x = (1/S) sum_k (c_k - cbar) d u_k / d x
               const float coef = (ck - cbar) * (-2.f * u[k] * u[k]) * invS;
               gx = fmaf(coef, vx[k], gx);
