@@ -65,6 +65,30 @@ class ClidQueryOut(C.Structure):
     ]
 
 
+class ClidLossArgs(C.Structure):
+    _fields_ = [
+        ("sdf", C.c_void_p), ("grad", C.c_void_p), ("label", C.c_void_p), ("weight", C.c_void_p),
+        ("dlogit", C.c_void_p), ("dgrad", C.c_void_p), ("loss", C.c_void_p),
+        ("n", C.c_int64), ("nd", C.c_int64),
+        ("sdf_scale", C.c_float), ("weight_e", C.c_float), ("num_eps", C.c_float), ("weighted", C.c_int32),
+    ]
+
+
+MAX_DEC_TENSORS = 2 * MAX_LEVELS + 2
+
+
+class ClidAdamArgs(C.Structure):
+    _fields_ = [
+        ("feat", C.c_void_p), ("feat_grad", C.c_void_p), ("feat_m", C.c_void_p), ("feat_v", C.c_void_p),
+        ("touched", C.c_void_p), ("rows", C.c_int64),
+        ("dec_param", C.c_void_p * MAX_DEC_TENSORS), ("dec_numel", C.c_int32 * MAX_DEC_TENSORS),
+        ("dec_tensors", C.c_int32),
+        ("dec_grad", C.c_void_p), ("dec_m", C.c_void_p), ("dec_v", C.c_void_p),
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+        ("weight_decay", C.c_float), ("step", C.c_int32),
+    ]
+
+
 _lib: Optional[C.CDLL] = None
 
 # every symbol include/clid_sdf.h declares: (name, restype, argtypes)
@@ -80,6 +104,11 @@ _SIGNATURES = [
     ("clid_query_backward_backward", C.c_int,
      [C.POINTER(ClidMap), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p,
       C.c_void_p, C.c_void_p]),
+    ("clid_sdf_loss", C.c_int, [C.POINTER(ClidLossArgs), C.c_void_p]),
+    ("clid_train_backward", C.c_int,
+     [C.POINTER(ClidMap), C.POINTER(ClidDecoder), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+      C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("clid_adam_step", C.c_int, [C.POINTER(ClidAdamArgs), C.c_void_p]),
     ("clid_radius_search", C.c_int,
      [C.POINTER(ClidMap), C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("clid_query_certainty", C.c_int,

@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "query_bwd.cuh"
 #include "query_fwd.cuh"
+#include "train.cuh"
 
 namespace clid {
 
@@ -164,6 +165,51 @@ static int elementwise_grid(int64_t work, int threads) {
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
+template <int H, int K>
+static int launch_train_backward(const TrainBwdParams& p, cudaStream_t stream) {
+  DeviceInfo info;
+  if (int rc = device_info(&info)) return rc;
+  constexpr int kWarps = kBwdThreads / 32;
+  size_t smem = (MlpLayout<H, 1>::kFloats + kWarps * 32 * kInPad + kWarps * 32 * (H / 32) + kWarps * H * kInPad) * sizeof(float);
+  auto kern = train_backward_l1_kernel<H, K>;
+  static thread_local int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+    }
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBwdThreads, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+  }
+  int64_t want = (p.n + kBwdThreads - 1) / kBwdThreads;
+  int64_t cap = (int64_t)info.sm_count * blocks_per_sm;
+  int grid = (int)(want < cap ? want : cap);
+  kern<<<grid, kBwdThreads, smem, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "train_backward_l1_kernel launch");
+  return CLID_OK;
+}
+
+static int dispatch_train_backward(const ClidMap* map, const ClidDecoder* dec, const float* x, const int32_t* knn_idx,
+                                   const float* dlogit, const float* dgrad, int64_t n, int64_t n_r, uint32_t flags,
+                                   float* gfeat, uint8_t* touched, float* dec_grad, cudaStream_t stream) {
+  TrainBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.map = *map; p.dec = *dec;
+  p.x = x; p.knn_idx = knn_idx; p.dlogit = dlogit; p.dgrad = dgrad;
+  p.gfeat = gfeat; p.touched = touched; p.dec_grad = dec_grad;
+  p.n = n; p.n_r = n_r; p.flags = flags;
+  const int H = dec->hidden_dim;
+  if (dec->levels != 1 || (H != 32 && H != 64 && H != 128))
+    return set_error(CLID_EUNSUPPORTED, "fused backward is compiled for one hidden level with H in {32,64,128}; got %d x %d",
+                     H, dec->levels);
+  const bool k6 = map->knn <= 6;
+  if (H == 64) return k6 ? launch_train_backward<64, 6>(p, stream) : launch_train_backward<64, 8>(p, stream);
+  if (H == 32) return k6 ? launch_train_backward<32, 6>(p, stream) : launch_train_backward<32, 8>(p, stream);
+  return k6 ? launch_train_backward<128, 6>(p, stream) : launch_train_backward<128, 8>(p, stream);
+}
+
 }  // namespace clid
 
 using namespace clid;
@@ -210,6 +256,74 @@ int clid_query_backward_backward(const ClidMap* map, const float* x, const int32
                                  clid_stream_t stream) {
   return launch_query_backward<true>(map, x, knn_idx, gz, ggx, n, flags, nullptr, g_gz, gfeat,
                                      static_cast<cudaStream_t>(stream), "clid_query_backward_backward");
+}
+
+int clid_sdf_loss(const ClidLossArgs* a, clid_stream_t stream) {
+  if (!a) return set_error(CLID_EINVAL, "args is NULL");
+  if (a->n < 0 || a->nd < 0) return set_error(CLID_EINVAL, "n = %lld, nd = %lld", (long long)a->n, (long long)a->nd);
+  if (a->n == 0) return CLID_OK;
+  if (!a->sdf || !a->label || !a->dlogit || !a->loss) return set_error(CLID_EINVAL, "sdf/label/dlogit/loss is NULL");
+  if (a->grad && a->nd > 0) return set_error(CLID_EINVAL, "analytic grad and numerical nd are mutually exclusive");
+  if (a->grad && a->weight_e > 0.f && !a->dgrad) return set_error(CLID_EINVAL, "analytic eikonal needs dgrad");
+  if (!(a->sdf_scale > 0.f)) return set_error(CLID_EINVAL, "sdf_scale must be positive");
+  if (a->nd > 0 && !(a->num_eps > 0.f)) return set_error(CLID_EINVAL, "num_eps must be positive");
+  LossParams p;
+  p.sdf = a->sdf; p.grad = a->grad; p.label = a->label; p.weight = a->weight;
+  p.dlogit = a->dlogit; p.dgrad = a->dgrad; p.loss = a->loss;
+  p.n = a->n; p.nd = a->nd; p.sdf_scale = a->sdf_scale; p.weight_e = a->weight_e; p.num_eps = a->num_eps;
+  p.weighted = a->weighted;
+  sdf_loss_kernel<<<elementwise_grid(a->n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "sdf_loss_kernel launch");
+  return CLID_OK;
+}
+
+int clid_train_backward(const ClidMap* map, const ClidDecoder* dec, const float* x, const int32_t* knn_idx,
+                        const float* dlogit, const float* dgrad, int64_t n, int64_t n_r, uint32_t flags, float* gfeat,
+                        uint8_t* touched, float* dec_grad, clid_stream_t stream) {
+  if (!map || !dec) return set_error(CLID_EINVAL, "map/dec is NULL");
+  if (n < 0 || n_r < 0 || n_r > n) return set_error(CLID_EINVAL, "n = %lld, n_r = %lld", (long long)n, (long long)n_r);
+  if (n == 0) return CLID_OK;
+  if (!x || !knn_idx || !dlogit) return set_error(CLID_EINVAL, "x/knn_idx/dlogit is NULL");
+  if (int rc = check_decoder(dec)) return rc;
+  if (map->feature_dim != kFeat) return set_error(CLID_EUNSUPPORTED, "feature_dim %d (only %d)", map->feature_dim, kFeat);
+  if (map->knn < 1 || map->knn > CLID_MAX_KNN) return set_error(CLID_EINVAL, "knn %d outside 1..%d", map->knn, CLID_MAX_KNN);
+  if (!map->gather_points || !map->gather_features || !aligned16(map->gather_features))
+    return set_error(CLID_EINVAL, "gather arrays are NULL or misaligned");
+  if (gfeat && !aligned16(gfeat)) return set_error(CLID_EINVAL, "gfeat must be 16-byte aligned");
+  return dispatch_train_backward(map, dec, x, knn_idx, dlogit, dgrad, n, n_r, flags, gfeat, touched, dec_grad,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int clid_adam_step(const ClidAdamArgs* a, clid_stream_t stream) {
+  if (!a) return set_error(CLID_EINVAL, "args is NULL");
+  if (a->rows < 0 || a->step < 1) return set_error(CLID_EINVAL, "rows = %lld, step = %d", (long long)a->rows, a->step);
+  if (a->rows > 0 && (!a->feat || !a->feat_grad || !a->feat_m || !a->feat_v))
+    return set_error(CLID_EINVAL, "feature buffers are NULL");
+  if (a->rows > 0 && (!aligned16(a->feat) || !aligned16(a->feat_grad) || !aligned16(a->feat_m) || !aligned16(a->feat_v)))
+    return set_error(CLID_EINVAL, "feature buffers must be 16-byte aligned");
+  if (a->weight_decay != 0.f && a->touched) return set_error(CLID_EINVAL, "weight_decay needs the dense step (touched == NULL)");
+  if (a->dec_grad && (!a->dec_m || !a->dec_v)) return set_error(CLID_EINVAL, "decoder moment buffers are NULL");
+  if (a->dec_tensors < 0 || a->dec_tensors > 2 * CLID_MAX_LEVELS + 2) return set_error(CLID_EINVAL, "dec_tensors %d", a->dec_tensors);
+  if (a->rows == 0 && !a->dec_grad) return CLID_OK;
+  AdamParams p;
+  memset(&p, 0, sizeof(p));
+  p.feat = a->feat; p.feat_grad = a->feat_grad; p.feat_m = a->feat_m; p.feat_v = a->feat_v;
+  p.touched = a->touched; p.rows = a->rows;
+  for (int t = 0; t < a->dec_tensors; ++t) { p.dec_param[t] = a->dec_param[t]; p.dec_numel[t] = a->dec_numel[t]; }
+  p.dec_tensors = a->dec_tensors;
+  p.dec_grad = a->dec_grad; p.dec_m = a->dec_m; p.dec_v = a->dec_v;
+  p.beta1 = a->beta1; p.beta2 = a->beta2; p.eps = a->eps; p.weight_decay = a->weight_decay;
+  // torch evaluates the bias corrections in double on the host (torch/optim/adam.py)
+  const double bc1 = 1.0 - pow((double)a->beta1, (double)a->step);
+  const double bc2 = 1.0 - pow((double)a->beta2, (double)a->step);
+  p.step_size = (float)((double)a->lr / bc1);
+  p.bc2_sqrt = (float)sqrt(bc2);
+  int grid = elementwise_grid(a->rows * 2 > 0 ? a->rows * 2 : 1, 256);
+  adam_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "adam_kernel launch");
+  return CLID_OK;
 }
 
 int clid_radius_search(const ClidMap* map, const float* x, int64_t n, uint32_t flags, float* dist2_out,

@@ -1,0 +1,394 @@
+// Training-side kernels of one mapping iteration (utils/mapper.py:642-836 of the reference):
+//   sdf_loss_kernel      sdf_bce_loss (utils/loss.py:44-62) + eikonal term (mapper.py:780-798,
+//                        with get_numerical_gradient's central differences, mapper.py:985-1034)
+//                        -> per-sample d L / d logit, d L / d grad, and the three loss scalars
+//   train_backward_kernel closed-form backward: decoder gradients reduced in
+//                        the block, neural-point feature gradients scattered with vector atomics
+//   adam_kernel          torch.optim.Adam(betas .9/.99, eps adam_eps) step (utils/tools.py:205-255)
+//                        on the touched feature rows and the decoder tensors
+#pragma once
+#include "common.cuh"
+#include "query_bwd.cuh"
+
+namespace clid {
+
+// ------------------------------------------------------------------------------------------
+// loss
+// ------------------------------------------------------------------------------------------
+struct LossParams {
+  const float* sdf;      // [n + 6 nd]  predictions: batch, then x+ex, x-ex, x+ey, x-ey, x+ez, x-ez blocks of nd
+  const float* grad;     // [n,3] analytic d sdf / d x or NULL
+  const float* label;    // [n]
+  const float* weight;   // [n] signed sample weight (|.| is used) or NULL
+  float* dlogit;         // [n + 6 nd]  d L / d (mlp output)
+  float* dgrad;          // [n,3] d L / d grad (analytic mode) or NULL
+  float* loss;           // [3] += total, bce, eikonal (un-weighted eikonal mean, like the reference logs)
+  int64_t n;
+  int64_t nd;            // decimated count for numerical mode, 0 otherwise
+  float sdf_scale;       // sigma of the BCE (= decoder sdf_scale)
+  float weight_e;        // eikonal weight, 0 disables
+  float num_eps;         // central-difference step
+  int weighted;          // loss_weight_on
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) sdf_loss_kernel(const LossParams p) {
+  __shared__ float red[2][8];
+  float bce_sum = 0.f, eik_sum = 0.f;
+  const float inv_n = 1.0f / (float)p.n;
+  const float s = p.sdf_scale;
+  const bool analytic = p.grad != nullptr && p.weight_e > 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x) {
+    // BCEWithLogits(pred / sigma, sigmoid(label / sigma), weight=|w|), mean reduction
+    const float l = p.sdf[i] / s;
+    const float t = 1.0f / (1.0f + expf(-(p.label[i] / s)));
+    const float wgt = (p.weighted && p.weight) ? fabsf(p.weight[i]) : 1.0f;
+    const float softplus_neg = fmaxf(-l, 0.f) + log1pf(expf(-fabsf(l)));  // log(1 + exp(-l))
+    bce_sum += wgt * ((1.0f - t) * l + softplus_neg);
+    const float sig = 1.0f / (1.0f + expf(-l));
+    p.dlogit[i] = wgt * (sig - t) * inv_n;
+    if (analytic) {
+      const float gx = p.grad[3 * i], gy = p.grad[3 * i + 1], gz = p.grad[3 * i + 2];
+      const float gn = sqrtf(gx * gx + gy * gy + gz * gz);
+      const float dev = gn - 1.0f;
+      eik_sum += dev * dev;
+      const float k = gn > 0.f ? p.weight_e * 2.0f * dev * inv_n / gn : 0.f;
+      p.dgrad[3 * i] = k * gx; p.dgrad[3 * i + 1] = k * gy; p.dgrad[3 * i + 2] = k * gz;
+    }
+  }
+  if (p.nd > 0 && p.weight_e > 0.f) {
+    const float inv_nd = 1.0f / (float)p.nd;
+    const float two_eps = 2.0f * p.num_eps;
+    const float* sh = p.sdf + p.n;
+    float* dsh = p.dlogit + p.n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.nd; i += (int64_t)gridDim.x * blockDim.x) {
+      const float gx = (sh[i] - sh[p.nd + i]) / two_eps;
+      const float gy = (sh[2 * p.nd + i] - sh[3 * p.nd + i]) / two_eps;
+      const float gz = (sh[4 * p.nd + i] - sh[5 * p.nd + i]) / two_eps;
+      const float gn = sqrtf(gx * gx + gy * gy + gz * gz);
+      const float dev = gn - 1.0f;
+      eik_sum += dev * dev;
+      // d L / d sdf(x +- eps e_a) = +- r_a / (2 eps);  d L / d logit = s * that
+      const float k = gn > 0.f ? p.weight_e * 2.0f * dev * inv_nd / gn * s / two_eps : 0.f;
+      dsh[i] = k * gx; dsh[p.nd + i] = -k * gx;
+      dsh[2 * p.nd + i] = k * gy; dsh[3 * p.nd + i] = -k * gy;
+      dsh[4 * p.nd + i] = k * gz; dsh[5 * p.nd + i] = -k * gz;
+    }
+  }
+  bce_sum = warp_sum(bce_sum);
+  eik_sum = warp_sum(eik_sum);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = bce_sum; red[1][warp] = eik_sum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = 0.f, e = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { b += red[0][w]; e += red[1][w]; }
+    const int64_t n_e = analytic ? p.n : p.nd;
+    const float bce = b * inv_n;
+    const float eik = n_e > 0 ? e / (float)n_e : 0.f;
+    atomicAdd(p.loss + 1, bce);
+    atomicAdd(p.loss + 2, eik);
+    atomicAdd(p.loss + 0, bce + p.weight_e * eik);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward (one hidden level): thread per sample, decoder gradients through the masked sums
+//   Gd[j][i'] = sum_n d_nj c'_ni',  c' = [delta z + tau0 ; delta],  d_nj = act'(pre_nj)
+//   dW0[j][i] = wout_j Gd[j][i],  db0[j] = wout_j Gd[j][11],
+//   dwout[j]  = sum_i' [W0 | b0][j][i'] Gd[j][i'],  dbout = sum_n delta_n
+// ------------------------------------------------------------------------------------------
+struct TrainBwdParams {
+  ClidMap map;
+  ClidDecoder dec;
+  const float* x;          // [n,3]
+  const int32_t* knn_idx;  // [n,knn] from the forward
+  const float* dlogit;     // [n]
+  const float* dgrad;      // [n_r,3] or NULL: samples >= n_r have no gradient term
+  float* gfeat;            // [n_gather+1,8] += (caller zero-fills once; Adam re-zeroes touched rows)
+  uint8_t* touched;        // [n_gather+1] set to 1 for rows that received a gradient, or NULL
+  float* dec_grad;         // flat [W0 (H x 11), b0 (H), wout (H), bout (1)] +=, or NULL (frozen decoder)
+  int64_t n;
+  int64_t n_r;
+  uint32_t flags;
+};
+
+constexpr int kBwdThreads = 128;
+
+template <int H, int K>
+__global__ void __launch_bounds__(kBwdThreads) train_backward_l1_kernel(const __grid_constant__ TrainBwdParams p) {
+  using Lay = MlpLayout<H, 1>;
+  constexpr int kRows = H / 32;       // hidden rows owned by a lane
+  constexpr int kMaskWords = H / 32;
+  constexpr int kWarps = kBwdThreads / 32;
+  extern __shared__ __align__(16) float smem[];
+  float* sm_dec = smem;
+  float* sm_c = smem + Lay::kFloats;                                   // [warps][32][12]
+  uint32_t* sm_m = reinterpret_cast<uint32_t*>(sm_c + kWarps * 32 * kInPad);  // [warps][32][kMaskWords]
+  float* sm_red = reinterpret_cast<float*>(sm_m + kWarps * 32 * kMaskWords);   // [warps][H][12] epilogue
+
+  const ClidMap& m = p.map;
+  stage_decoder<H, 1>(sm_dec, p.dec);
+  __syncthreads();
+
+  const bool layer_norm = p.flags & CLID_LAYER_NORM;
+  const float slope = (p.flags & CLID_LEAKY_RELU) ? kLeakySlope : 0.f;
+  const float s = p.dec.sdf_scale;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* my_c = sm_c + (warp * 32) * kInPad;
+  uint32_t* my_m = sm_m + (warp * 32) * kMaskWords;
+  const float4* w0 = reinterpret_cast<const float4*>(sm_dec + Lay::kW0);
+
+  float Gd[kRows][kInPad];
+#pragma unroll
+  for (int r = 0; r < kRows; ++r)
+#pragma unroll
+    for (int i = 0; i < kInPad; ++i) Gd[r][i] = 0.f;
+  float delta_sum = 0.f;
+
+  for (int64_t q0 = (int64_t)blockIdx.x * blockDim.x; q0 < p.n; q0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = q0 + threadIdx.x;
+    const bool live = q < p.n;
+    float c[kInPad];
+#pragma unroll
+    for (int i = 0; i < kInPad; ++i) c[i] = 0.f;
+    uint32_t mask[kMaskWords];
+#pragma unroll
+    for (int w = 0; w < kMaskWords; ++w) mask[w] = 0u;
+
+    if (live) {
+      const float px = p.x[3 * q], py = p.x[3 * q + 1], pz = p.x[3 * q + 2];
+      const float delta = p.dlogit[q];
+      const bool has_r = p.dgrad != nullptr && q < p.n_r;
+      float rx = 0.f, ry = 0.f, rz = 0.f;
+      if (has_r) { rx = p.dgrad[3 * q]; ry = p.dgrad[3 * q + 1]; rz = p.dgrad[3 * q + 2]; }
+      Neighbors<K> nb;
+      load_neighbors<K>(m, p.knn_idx, q, px, py, pz, nb);
+
+      // e_k = d w_k / d x . r  (zero without a gradient term)
+      float e[K];
+      if (has_r && nb.any) {
+        float du[K], dusum = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          du[k] = nb.id[k] >= 0 ? -2.f * nb.u[k] * nb.u[k] * (nb.vx[k] * rx + nb.vy[k] * ry + nb.vz[k] * rz) : 0.f;
+          dusum += du[k];
+        }
+        const float invS = 1.0f / nb.S;
+#pragma unroll
+        for (int k = 0; k < K; ++k) e[k] = nb.id[k] >= 0 ? (du[k] - nb.w[k] * dusum) * invS : 0.f;
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) e[k] = 0.f;
+      }
+
+      // z and the tangent input tau0 = s (sum_k e_k q_k + [0; r] sum_k w_k)
+      float z[kIn], tau[kIn];
+#pragma unroll
+      for (int i = 0; i < kIn; ++i) { z[i] = 0.f; tau[i] = 0.f; }
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (nb.id[k] >= 0) {
+          float f[kFeat];
+          load_feature_row(m.gather_features, nb.id[k], f);
+          if (layer_norm) { float mu, rs; layer_norm8(f, mu, rs); }
+#pragma unroll
+          for (int i = 0; i < kFeat; ++i) { z[i] = fmaf(nb.w[k], f[i], z[i]); tau[i] = fmaf(e[k], f[i], tau[i]); }
+          z[8] = fmaf(nb.w[k], nb.vx[k], z[8]); z[9] = fmaf(nb.w[k], nb.vy[k], z[9]); z[10] = fmaf(nb.w[k], nb.vz[k], z[10]);
+          tau[8] = fmaf(e[k], nb.vx[k], tau[8]); tau[9] = fmaf(e[k], nb.vy[k], tau[9]); tau[10] = fmaf(e[k], nb.vz[k], tau[10]);
+        }
+      }
+      if (has_r && nb.any) { tau[8] += rx; tau[9] += ry; tau[10] += rz; }
+
+      // decoder forward for the activation pattern and a = d logit / d z
+      float a[kIn];
+#pragma unroll
+      for (int i = 0; i < kIn; ++i) a[i] = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < H; ++j) {
+        const float4 r0 = w0[j * 3 + 0], r1 = w0[j * 3 + 1], r2 = w0[j * 3 + 2];
+        float pre = sm_dec[Lay::kB0 + j];
+        pre = fmaf(r0.x, z[0], pre); pre = fmaf(r0.y, z[1], pre); pre = fmaf(r0.z, z[2], pre); pre = fmaf(r0.w, z[3], pre);
+        pre = fmaf(r1.x, z[4], pre); pre = fmaf(r1.y, z[5], pre); pre = fmaf(r1.z, z[6], pre); pre = fmaf(r1.w, z[7], pre);
+        pre = fmaf(r2.x, z[8], pre); pre = fmaf(r2.y, z[9], pre); pre = fmaf(r2.z, z[10], pre);
+        const bool on = pre > 0.f;
+        if (on) mask[j >> 5] |= 1u << (j & 31);
+        const float cj = sm_dec[Lay::kWout + j] * (on ? 1.f : slope);
+        a[0] = fmaf(cj, r0.x, a[0]); a[1] = fmaf(cj, r0.y, a[1]); a[2] = fmaf(cj, r0.z, a[2]); a[3] = fmaf(cj, r0.w, a[3]);
+        a[4] = fmaf(cj, r1.x, a[4]); a[5] = fmaf(cj, r1.y, a[5]); a[6] = fmaf(cj, r1.z, a[6]); a[7] = fmaf(cj, r1.w, a[7]);
+        a[8] = fmaf(cj, r2.x, a[8]); a[9] = fmaf(cj, r2.y, a[9]); a[10] = fmaf(cj, r2.z, a[10]);
+      }
+
+      // c' = [delta z + s tau ; delta]
+#pragma unroll
+      for (int i = 0; i < kIn; ++i) c[i] = fmaf(delta, z[i], s * tau[i]);
+      c[kIn] = delta;
+      delta_sum += delta;
+
+      // neural-point feature gradients: dL/df_k = a_f (delta w_k + s e_k), through LN if on
+      if (p.gfeat) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (nb.id[k] >= 0) {
+            const float coef = fmaf(s, e[k], delta * nb.w[k]);
+            float t[kFeat];
+#pragma unroll
+            for (int i = 0; i < kFeat; ++i) t[i] = coef * a[i];
+            if (layer_norm) {
+              float f[kFeat], mu, rs;
+              load_feature_row(m.gather_features, nb.id[k], f);
+              layer_norm8(f, mu, rs);
+              layer_norm8_vjp(f, rs, t);
+            }
+            red_add_row(p.gfeat, nb.id[k], t);
+            if (p.touched) p.touched[nb.id[k]] = 1;
+          }
+        }
+      }
+    }
+
+    if (p.dec_grad) {
+      // stage this warp's 32 samples, then every lane folds them into the hidden rows it owns
+      float4* dst = reinterpret_cast<float4*>(my_c + lane * kInPad);
+      dst[0] = make_float4(c[0], c[1], c[2], c[3]);
+      dst[1] = make_float4(c[4], c[5], c[6], c[7]);
+      dst[2] = make_float4(c[8], c[9], c[10], c[11]);
+#pragma unroll
+      for (int w = 0; w < kMaskWords; ++w) my_m[lane * kMaskWords + w] = mask[w];
+      __syncwarp();
+#pragma unroll 4
+      for (int nn = 0; nn < 32; ++nn) {
+        const float4* src = reinterpret_cast<const float4*>(my_c + nn * kInPad);
+        const float4 c0 = src[0], c1 = src[1], c2 = src[2];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          // row j = lane + 32 r lives in mask word r, bit `lane`
+          const float d = ((my_m[nn * kMaskWords + r] >> lane) & 1u) ? 1.f : slope;
+          Gd[r][0] = fmaf(d, c0.x, Gd[r][0]); Gd[r][1] = fmaf(d, c0.y, Gd[r][1]);
+          Gd[r][2] = fmaf(d, c0.z, Gd[r][2]); Gd[r][3] = fmaf(d, c0.w, Gd[r][3]);
+          Gd[r][4] = fmaf(d, c1.x, Gd[r][4]); Gd[r][5] = fmaf(d, c1.y, Gd[r][5]);
+          Gd[r][6] = fmaf(d, c1.z, Gd[r][6]); Gd[r][7] = fmaf(d, c1.w, Gd[r][7]);
+          Gd[r][8] = fmaf(d, c2.x, Gd[r][8]); Gd[r][9] = fmaf(d, c2.y, Gd[r][9]);
+          Gd[r][10] = fmaf(d, c2.z, Gd[r][10]); Gd[r][11] = fmaf(d, c2.w, Gd[r][11]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  if (!p.dec_grad) return;
+  // ---- block epilogue: sum the warps' partial Gd, turn them into parameter gradients
+#pragma unroll
+  for (int r = 0; r < kRows; ++r)
+#pragma unroll
+    for (int i = 0; i < kInPad; ++i) sm_red[(warp * H + lane + 32 * r) * kInPad + i] = Gd[r][i];
+  delta_sum = warp_sum(delta_sum);
+  __shared__ float sm_delta[kWarps];
+  if (lane == 0) sm_delta[warp] = delta_sum;
+  __syncthreads();
+  float* gW0 = p.dec_grad;
+  float* gb0 = gW0 + H * kIn;
+  float* gwout = gb0 + H;
+  float* gbout = gwout + H;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    float g[kInPad];
+#pragma unroll
+    for (int i = 0; i < kInPad; ++i) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) v += sm_red[(w * H + j) * kInPad + i];
+      g[i] = v;
+    }
+    const float wout = sm_dec[Lay::kWout + j];
+    float dw = sm_dec[Lay::kB0 + j] * g[kIn];
+#pragma unroll
+    for (int i = 0; i < kIn; ++i) {
+      atomicAdd(gW0 + j * kIn + i, wout * g[i]);
+      dw = fmaf(sm_dec[Lay::kW0 + j * kInPad + i], g[i], dw);
+    }
+    if (p.dec.bias[0]) atomicAdd(gb0 + j, wout * g[kIn]);
+    atomicAdd(gwout + j, dw);
+  }
+  if (threadIdx.x == 0 && p.dec.out_bias) {
+    float d = 0.f;
+    for (int w = 0; w < kWarps; ++w) d += sm_delta[w];
+    atomicAdd(gbout, d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Adam
+// ------------------------------------------------------------------------------------------
+struct AdamParams {
+  // neural-point features
+  float* feat;            // [rows,8] parameters (local_geo_features)
+  float* feat_grad;       // [rows,8] gradient, re-zeroed for the rows it was applied to
+  float* feat_m;          // [rows,8]
+  float* feat_v;          // [rows,8]
+  const uint8_t* touched; // [rows] or NULL = every row
+  int64_t rows;
+  // decoder tensors, in flat order [W0, b0, (W1, b1, ...), wout, bout]
+  float* dec_param[2 * CLID_MAX_LEVELS + 2];
+  int32_t dec_numel[2 * CLID_MAX_LEVELS + 2];
+  int32_t dec_tensors;
+  float* dec_grad;        // flat, re-zeroed
+  float* dec_m;           // flat
+  float* dec_v;           // flat
+  // hyper-parameters; the bias corrections are evaluated on the host in double like torch does
+  float beta1, beta2, eps, weight_decay;
+  float step_size;        // lr / (1 - beta1^t)
+  float bc2_sqrt;         // sqrt(1 - beta2^t)
+};
+
+__device__ __forceinline__ float adam_update(float p, float g, float& mm, float& vv, const AdamParams& a) {
+  mm = mm + (g - mm) * (1.0f - a.beta1);                     // exp_avg.lerp_(grad, 1 - beta1)
+  vv = fmaf(1.0f - a.beta2, g * g, vv * a.beta2);            // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+  const float denom = sqrtf(vv) / a.bc2_sqrt + a.eps;
+  return p - a.step_size * (mm / denom);
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(const AdamParams a) {
+  // feature rows: one thread per float4 half-row
+  const int64_t halves = a.rows * 2;
+  for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h < halves; h += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = h >> 1;
+    if (a.touched && !a.touched[row]) continue;
+    float4* pg = reinterpret_cast<float4*>(a.feat_grad) + h;
+    float4 g = *pg;
+    float4* pp = reinterpret_cast<float4*>(a.feat) + h;
+    float4* pm = reinterpret_cast<float4*>(a.feat_m) + h;
+    float4* pv = reinterpret_cast<float4*>(a.feat_v) + h;
+    float4 p = *pp, mm = *pm, vv = *pv;
+    if (a.weight_decay != 0.f) { g.x = fmaf(a.weight_decay, p.x, g.x); g.y = fmaf(a.weight_decay, p.y, g.y); g.z = fmaf(a.weight_decay, p.z, g.z); g.w = fmaf(a.weight_decay, p.w, g.w); }
+    p.x = adam_update(p.x, g.x, mm.x, vv.x, a);
+    p.y = adam_update(p.y, g.y, mm.y, vv.y, a);
+    p.z = adam_update(p.z, g.z, mm.z, vv.z, a);
+    p.w = adam_update(p.w, g.w, mm.w, vv.w, a);
+    *pp = p; *pm = mm; *pv = vv;
+    *pg = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // decoder: block 0 walks the small tensors
+  if (blockIdx.x == 0 && a.dec_grad) {
+    int base = 0;
+    for (int t = 0; t < a.dec_tensors; ++t) {
+      float* prm = a.dec_param[t];
+      const int numel = a.dec_numel[t];
+      if (prm) {
+        for (int i = threadIdx.x; i < numel; i += blockDim.x) {
+          float mm = a.dec_m[base + i], vv = a.dec_v[base + i];
+          prm[i] = adam_update(prm[i], a.dec_grad[base + i], mm, vv, a);
+          a.dec_m[base + i] = mm; a.dec_v[base + i] = vv;
+          a.dec_grad[base + i] = 0.f;
+        }
+      }
+      base += numel;
+    }
+  }
+}
+
+}  // namespace clid

@@ -1,0 +1,182 @@
+"""Fused training iteration of the neural-SDF map (the loop body of Mapper.mapping,
+utils/mapper.py:642-836 of the reference) on top of the C ABI:
+
+    clid_query_forward   gather + IDW + decoder (+ closed-form d sdf / d x), side effects
+    clid_sdf_loss        bce + eikonal -> per-point d L / d logit (and d L / d grad)
+    clid_train_backward  decoder gradients + scattered neural-point feature gradients
+    clid_adam_step       Adam on the touched feature rows and the decoder tensors
+
+Four launches per iteration, no host synchronisation, no intermediate [N, 81, .] tensors.
+One `FusedTrainer` lives for one `mapping()` call, exactly like the reference's per-call Adam
+(fresh moments, step counter from 1).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+
+from .. import _lib
+from . import query as _q
+
+INT32_MIN = -(2**31)
+
+
+def supported(config, decoder) -> Optional[str]:
+    """None when the fused path covers this configuration, else the reason it does not."""
+    if not config.weighted_first:
+        return "weighted_first=False"
+    if config.main_loss_type != "bce":
+        return f"main_loss_type={config.main_loss_type}"
+    if getattr(config, "proj_correction_on", False) or getattr(config, "consistency_loss_on", False):
+        return "projective correction / consistency loss"
+    if getattr(config, "semantic_on", False) or getattr(config, "color_on", False):
+        return "semantic / colour heads"
+    if not config.opt_adam:
+        return "SGD optimiser"
+    if getattr(config, "ekional_add_to", "all") != "all" and config.ekional_loss_on and config.weight_e > 0:
+        return f"ekional_add_to={config.ekional_add_to}"
+    if len(decoder.layers) != 1 or decoder.layers[0].out_features not in (32, 64, 128):
+        return f"decoder {decoder.layers[0].out_features} x {len(decoder.layers)}"
+    if decoder.layers[0].in_features != config.feature_dim + 3 or config.feature_dim != 8:
+        return "feature_dim != 8 or positional encoding"
+    return None
+
+
+class FusedTrainer:
+    def __init__(self, config, neural_points, decoder):
+        why = supported(config, decoder)
+        if why is not None:
+            raise NotImplementedError(f"fused training does not cover {why}")
+        self.cfg, self.npm, self.dec = config, neural_points, decoder
+        self.lib = _lib.load()
+        feats = neural_points.local_geo_features
+        _q._require_cuda(feats, "local_geo_features")
+        dev = feats.device
+        self.device = dev
+        rows = feats.shape[0]
+        self.rows = rows
+        self.feat_grad = torch.zeros_like(feats.data)
+        self.feat_m = torch.zeros_like(feats.data)
+        self.feat_v = torch.zeros_like(feats.data)
+        self.dense = float(config.weight_decay) != 0.0
+        self.touched = None if self.dense else torch.zeros(rows, dtype=torch.uint8, device=dev)
+        self.train_features = bool(feats.requires_grad)
+
+        self.dec_tensors = decoder.flat_parameters()
+        self.train_decoder = any(p is not None and p.requires_grad for p in self.dec_tensors)
+        self.dec_numel = [0 if p is None else p.numel() for p in self.dec_tensors]
+        # absent biases still own a slot in the flat layout the kernels use
+        h = decoder.layers[0].out_features
+        expect = [h * decoder.layers[0].in_features, h, h, 1]
+        self.dec_numel = [max(a, b) for a, b in zip(self.dec_numel, expect)]
+        total = sum(self.dec_numel)
+        if self.train_decoder:
+            self.dec_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+            self.dec_m = torch.zeros_like(self.dec_grad)
+            self.dec_v = torch.zeros_like(self.dec_grad)
+        else:
+            self.dec_grad = self.dec_m = self.dec_v = None
+        self.step = 0
+        self.analytic = bool(config.ekional_loss_on and not config.numerical_grad)
+        self.numerical = bool(config.ekional_loss_on and config.numerical_grad)
+        self.weight_e = float(config.weight_e) if config.ekional_loss_on else 0.0
+        self.losses: List[torch.Tensor] = []  # [3] per iteration: total, bce, eikonal (device tensors)
+
+    # ------------------------------------------------------------------
+    def _shifted(self, x: torch.Tensor) -> torch.Tensor:
+        """The six central-difference copies of the decimated batch (mapper.py:985-1003)."""
+        eps = self.cfg.voxel_size_m * self.cfg.num_grad_step_ratio
+        xd = x[:: self.cfg.gradient_decimation]
+        out = xd.repeat(6, 1)
+        nd = xd.shape[0]
+        for axis in range(3):
+            out[(2 * axis) * nd:(2 * axis + 1) * nd, axis] += eps
+            out[(2 * axis + 1) * nd:(2 * axis + 2) * nd, axis] -= eps
+        return out
+
+    def iteration(self, x: torch.Tensor, label: torch.Tensor, ts: Optional[torch.Tensor], weight: torch.Tensor,
+                  apply_step: bool = True):
+        """One mapping iteration on the batch.  With apply_step=False the optimiser step is left to
+        a later `adam_step()` call, so the accumulated gradients can be inspected (tests)."""
+        cfg, npm, dec, lib, dev = self.cfg, self.npm, self.dec, self.lib, self.device
+        x = _q._prep_points(x, "coord")
+        n = x.shape[0]
+        if n == 0:
+            return
+        nd = 0
+        x_all, ts_all = x, ts
+        if self.numerical and self.weight_e > 0:
+            shifted = self._shifted(x)
+            nd = shifted.shape[0] // 6
+            x_all = torch.cat((x, shifted), 0)
+            if ts is not None:  # INT32_MIN makes the ts_update amax a no-op for the shifted copies
+                pad = torch.full((shifted.shape[0],), INT32_MIN, dtype=torch.int32, device=dev)
+                ts_all = torch.cat((ts.to(torch.int32), pad), 0)
+        want_grad = self.analytic and self.weight_e > 0
+        res = _q.forward(npm, dec, x_all, ts_all, training_mode=True, query_locally=True,
+                         want_sdf=True, want_grad=want_grad, want_idx=True)
+        n_all = x_all.shape[0]
+
+        loss = torch.zeros(3, dtype=torch.float32, device=dev)
+        dlogit = torch.empty(n_all, dtype=torch.float32, device=dev)
+        dgrad = torch.empty(n, 3, dtype=torch.float32, device=dev) if want_grad else None
+        la = _lib.ClidLossArgs()
+        la.sdf = res["sdf"].data_ptr()
+        la.grad = res["grad"].data_ptr() if want_grad else None
+        # conversions are bound to names so their storage outlives the (asynchronous) launches
+        label_f = label.contiguous().float()
+        w = weight.contiguous().float() if weight is not None else None
+        la.label = _lib.ptr(label_f, torch.float32, "sdf_label")
+        la.weight = _lib.ptr(w, torch.float32, "weight")
+        la.dlogit, la.dgrad, la.loss = dlogit.data_ptr(), (dgrad.data_ptr() if want_grad else None), loss.data_ptr()
+        la.n, la.nd = n, nd
+        la.sdf_scale = float(dec.sdf_scale)
+        la.weight_e = self.weight_e
+        la.num_eps = float(cfg.voxel_size_m * cfg.num_grad_step_ratio)
+        la.weighted = int(bool(cfg.loss_weight_on))
+        stream = _lib.current_stream(dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.clid_sdf_loss(C.byref(la), stream), "clid_sdf_loss")
+
+            m, flags = _q.map_struct(npm, True)
+            if dec.use_leaky_relu:
+                flags |= _lib.LEAKY_RELU
+            ds = dec.abi_struct()
+            rc = lib.clid_train_backward(
+                C.byref(m), C.byref(ds), x_all.data_ptr(), res["knn_idx"].data_ptr(), dlogit.data_ptr(),
+                dgrad.data_ptr() if want_grad else None, n_all, n if want_grad else 0, flags,
+                self.feat_grad.data_ptr() if self.train_features else None,
+                None if self.touched is None else self.touched.data_ptr(),
+                None if self.dec_grad is None else self.dec_grad.data_ptr(), stream)
+            _lib.check(rc, "clid_train_backward")
+
+        self.losses.append(loss)
+        if apply_step:
+            self.adam_step()
+        return loss
+
+    def adam_step(self) -> None:
+        cfg, npm, lib, dev = self.cfg, self.npm, self.lib, self.device
+        stream = _lib.current_stream(dev)
+        with torch.cuda.device(dev):
+            self.step += 1
+            aa = _lib.ClidAdamArgs()
+            if self.train_features:
+                aa.feat = npm.local_geo_features.data.data_ptr()
+                aa.feat_grad, aa.feat_m, aa.feat_v = (self.feat_grad.data_ptr(), self.feat_m.data_ptr(),
+                                                      self.feat_v.data_ptr())
+                aa.touched = None if self.touched is None else self.touched.data_ptr()
+                aa.rows = self.rows
+            else:
+                aa.rows = 0
+            aa.dec_tensors = len(self.dec_tensors)
+            for i, p in enumerate(self.dec_tensors):
+                aa.dec_param[i] = None if p is None else p.data.data_ptr()
+                aa.dec_numel[i] = self.dec_numel[i]
+            if self.dec_grad is not None:
+                aa.dec_grad, aa.dec_m, aa.dec_v = self.dec_grad.data_ptr(), self.dec_m.data_ptr(), self.dec_v.data_ptr()
+            aa.lr, aa.beta1, aa.beta2 = float(cfg.lr), 0.9, 0.99
+            aa.eps, aa.weight_decay, aa.step = float(cfg.adam_eps), float(cfg.weight_decay), self.step
+            _lib.check(lib.clid_adam_step(C.byref(aa), stream), "clid_adam_step")

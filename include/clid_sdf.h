@@ -169,6 +169,69 @@ CLID_API int clid_query_backward_backward(const ClidMap* map, const float* x,
                                           const float* ggx, int64_t n, uint32_t flags,
                                           float* g_gz, float* gfeat, clid_stream_t stream);
 
+/* ---- training step (utils/mapper.py:642-836) ------------------------------------------------ */
+
+/* sdf_bce_loss (utils/loss.py:44-62) + eikonal term (utils/mapper.py:780-798).
+ * sdf holds the n batch predictions followed, in numerical-gradient mode, by the 6 nd
+ * central-difference predictions in get_numerical_gradient's order (utils/mapper.py:985-1034:
+ * x+ex, x-ex, x+ey, x-ey, x+ez, x-ez, nd rows each).  Exactly one of {grad != NULL, nd > 0}
+ * selects the eikonal input; weight_e == 0 disables the term.
+ *   dlogit [n + 6 nd]  d L / d (Decoder.mlp output) per evaluated point
+ *   dgrad  [n,3]       d L / d (d sdf / d x), analytic mode only
+ *   loss   [3] +=      total, bce, eikonal (caller zero-fills) */
+typedef struct ClidLossArgs {
+  const float* sdf;
+  const float* grad;
+  const float* label;
+  const float* weight;   /* signed sample weights, |.| is applied (mapper.py:747-749); NULL = 1 */
+  float* dlogit;
+  float* dgrad;
+  float* loss;
+  int64_t n;
+  int64_t nd;
+  float sdf_scale;
+  float weight_e;
+  float num_eps;
+  int32_t weighted;      /* loss_weight_on */
+} ClidLossArgs;
+CLID_API int clid_sdf_loss(const ClidLossArgs* args, clid_stream_t stream);
+
+/* Closed-form backward of loss -> decoder -> interpolation (what cur_loss.backward() computes,
+ * utils/mapper.py:834-835, including the double backward through get_gradient in analytic
+ * mode).  x / knn_idx / dlogit cover n points; dgrad covers the first n_r of them (0 in
+ * numerical mode).  Only the gather_* arrays, knn, feature_dim of `map` are read.
+ *   gfeat    [n_gather+1,F] +=  d L / d local_geo_features
+ *   touched  [n_gather+1]   = 1 for rows that received a contribution (may be NULL)
+ *   dec_grad flat [W0 (HxD), b0 (H), wout (H), bout (1)] +=, NULL when the decoder is frozen
+ * Compiled for one hidden level with H in {32, 64, 128}; other decoders return
+ * CLID_EUNSUPPORTED (the host then differentiates through clid_query_backward instead). */
+CLID_API int clid_train_backward(const ClidMap* map, const ClidDecoder* dec, const float* x,
+                                 const int32_t* knn_idx, const float* dlogit, const float* dgrad,
+                                 int64_t n, int64_t n_r, uint32_t flags, float* gfeat,
+                                 uint8_t* touched, float* dec_grad, clid_stream_t stream);
+
+/* torch.optim.Adam step (utils/tools.py:205-255: betas (0.9, 0.99), eps adam_eps) on the touched
+ * neural-point feature rows and on the decoder tensors; applied gradients are re-zeroed.
+ * Rows never touched since the optimiser was created have m = v = g = 0, for which dense Adam
+ * is the identity, so skipping them is exact (weight_decay != 0 needs touched == NULL). */
+typedef struct ClidAdamArgs {
+  float* feat;             /* [rows,F] */
+  float* feat_grad;
+  float* feat_m;
+  float* feat_v;
+  const uint8_t* touched;  /* [rows] or NULL = all rows */
+  int64_t rows;
+  float* dec_param[2 * CLID_MAX_LEVELS + 2]; /* W0,b0,(W1,b1,..),wout,bout; NULL entries skipped */
+  int32_t dec_numel[2 * CLID_MAX_LEVELS + 2];
+  int32_t dec_tensors;
+  float* dec_grad;         /* flat in the same order, or NULL (decoder frozen) */
+  float* dec_m;
+  float* dec_v;
+  float lr, beta1, beta2, eps, weight_decay;
+  int32_t step;            /* 1-based, shared by every parameter like torch's per-call optimiser */
+} ClidAdamArgs;
+CLID_API int clid_adam_step(const ClidAdamArgs* args, clid_stream_t stream);
+
 /* NeuralPoints.radius_neighborhood_search (model/neural_points.py:971-1030): the raw candidate
  * table.  dist2_out [n,kc] f32, idx_out [n,kc] int64 global ids (-1 invalid).  Only
  * CLID_TIME_FILTER is read from flags. */

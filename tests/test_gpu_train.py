@@ -1,0 +1,122 @@
+"""GPU parity of the training step (loss, gradients, Adam, side effects) against fixtures that
+were produced by driving the reference's own Mapper.mapping() (oracle/gen_golden.py)."""
+import pytest
+import torch
+
+import golden_io as gio
+import helpers as hp
+
+pytestmark = pytest.mark.gpu
+
+L1_CASES = [n for n in gio.names("train") if "l2h32" not in n]
+ALL_CASES = gio.names("train")
+
+
+class _Dataset:
+    lose_track = False
+    stop_status = False
+    processed_frame = 0
+    gt_pose_provided = True
+    pgo_poses = None
+    static_mask = None
+
+
+def _setup(name):
+    fx = gio.load("train", name)
+    m = gio.oracle_map(fx)
+    cfg = hp.product_config(m.cfg)
+    npm = hp.product_map(m)
+    frozen = bool(fx["freeze_decoder"])
+    dec = hp.product_decoder(m.cfg, gio.decoder_params(fx))
+    if frozen:
+        from clid_slam_b200.utils.tools import freeze_model
+
+        freeze_model(dec)
+    return fx, m, cfg, npm, dec, frozen
+
+
+def _batch(fx, it):
+    return (gio.t(fx["batch_x"][it]).cuda(), gio.t(fx["batch_label"][it]).cuda(),
+            gio.t(fx["batch_ts"][it]).cuda(), gio.t(fx["batch_weight"][it]).cuda())
+
+
+def _check_final_state(fx, npm, dec):
+    gio.assert_close(npm.local_geo_features, fx["after_local_features"], 1e-3, 1e-5, "features after Adam", 2e-3)
+    gio.assert_close(npm.local_point_certainties, fx["after_local_certainties"], 1e-5, 1e-5, "certainties")
+    assert torch.equal(npm.local_point_ts_update.cpu(), gio.t(fx["after_local_ts_update"]))
+    after = gio.decoder_params(fx, prefix="after_dec_", requires_grad=False)
+    for a, b in zip(dec.flat_parameters(), after):
+        gio.assert_close(a, b, 1e-3, 1e-5, "decoder after Adam", 2e-3)
+
+
+@pytest.mark.parametrize("name", L1_CASES)
+def test_fused_training_matches_reference(name):
+    from clid_slam_b200.ops.train import FusedTrainer
+
+    fx, m, cfg, npm, dec, frozen = _setup(name)
+    trainer = FusedTrainer(cfg, npm, dec)
+    for it in range(int(fx["n_iters"])):
+        x, label, ts, weight = _batch(fx, it)
+        loss = trainer.iteration(x, label, ts, weight, apply_step=False)
+        gio.assert_close(loss[0], fx["loss_total"][it], hp.LOSS_RTOL, 0, f"total loss it{it}")
+        gio.assert_close(loss[1], fx["loss_bce"][it], 1e-4, 0, f"bce loss it{it}")
+        gio.assert_close(loss[2], fx["loss_eikonal"][it], 1e-4, 0, f"eikonal loss it{it}")
+        gio.assert_close(trainer.feat_grad, fx["feat_grads"][it], 1e-3, 2e-9, f"dL/dfeatures it{it}", 1e-3)
+        if not frozen:
+            flat = torch.cat([gio.t(fx[f"dec_grad_it{it}_{j}"]).flatten() for j in range(4)])
+            gio.assert_close(trainer.dec_grad, flat, 1e-3, 1e-7, f"dL/ddecoder it{it}")
+        trainer.adam_step()
+    _check_final_state(fx, npm, dec)
+
+
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "unfused"])
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_mapper_mapping_matches_reference(name, fused):
+    """Mapper.mapping() end to end on the recorded batches: fused kernels, and the unfused path
+    (query_feature autograd incl. double backward + torch decoder + torch Adam)."""
+    from clid_slam_b200.ops import train as tr
+    from clid_slam_b200.utils.mapper import Mapper
+
+    fx, m, cfg, npm, dec, frozen = _setup(name)
+    if fused and tr.supported(cfg, dec) is not None:
+        pytest.skip("configuration not covered by the fused path: " + tr.supported(cfg, dec))
+    n_iters = int(fx["n_iters"])
+    cfg.bs = fx["batch_x"].shape[1]
+    mapper = Mapper(cfg, _Dataset(), npm, None, dec)
+    mapper.use_fused = fused
+    mapper.adaptive_iter_offset = 0
+    feed = iter(range(n_iters))
+
+    def replay(global_coord=False):
+        x, label, ts, weight = _batch(fx, next(feed))
+        return x, label, ts, None, None, None, weight
+
+    mapper.get_batch = replay
+    mapper.mapping(n_iters)
+    assert mapper.total_iter == n_iters
+    losses = mapper.last_losses.cpu()
+    gio.assert_close(losses[:, 0], fx["loss_total"], hp.LOSS_RTOL, 0, "total loss")
+    gio.assert_close(losses[:, 1], fx["loss_bce"], 1e-4, 0, "bce loss")
+    gio.assert_close(losses[:, 2], fx["loss_eikonal"], 1e-4, 0, "eikonal loss")
+    _check_final_state(fx, npm, dec)
+    gio.assert_close(npm.geo_features, fx["after_features"], 1e-3, 1e-5, "global features after write-back", 2e-3)
+
+
+def test_unfused_gradients_match_reference():
+    """Analytic mode through torch autograd: first- and second-order kernels of query_feature."""
+    from clid_slam_b200.utils.loss import sdf_bce_loss
+    from clid_slam_b200.utils.tools import get_gradient
+
+    fx, m, cfg, npm, dec, _ = _setup("analytic_l1h64")
+    x, label, ts, weight = _batch(fx, 0)
+    x.requires_grad_(True)
+    z, _, _, _, _ = npm.query_feature(x, ts)
+    sdf = dec.sdf(z)
+    g = get_gradient(x, sdf)
+    loss = sdf_bce_loss(sdf, label, dec.sdf_scale, weight.abs(), cfg.loss_weight_on)
+    loss = loss + cfg.weight_e * ((g.norm(2, dim=-1) - 1.0) ** 2).mean()
+    loss.backward()
+    gio.assert_close(loss, fx["loss_total"][0], 1e-4, 0, "loss")
+    gio.assert_close(npm.local_geo_features.grad, fx["feat_grads"][0], 1e-3, 2e-9, "dL/dfeatures", 1e-3)
+    for j, p in enumerate(dec.flat_parameters()):
+        gio.assert_close(p.grad, fx[f"dec_grad_it0_{j}"], 1e-3, 1e-7, f"dL/ddecoder[{j}]")
