@@ -1,0 +1,367 @@
+#!/usr/bin/env python3
+"""Benchmark of the neural-SDF hot path (BASELINE.json metric: sampled-points/sec through the SDF
+decoder + gradient + loss, with % of the HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one mapping iteration (utils/mapper.py:642-836 of the reference) on one batch:
+fused gather + decoder + d sdf/dx forward, bce + eikonal loss, backward into decoder weights and
+neural-point features, Adam.  Workload = BASELINE.json configs[2] (the configuration the
+north_star target is quoted on): 131072 samples per batch per GPU, ~1.08 M neural points
+(4 wavy sheets, 0.4 m voxels, ncd128 decoder 11->64->1, Kc = 81, K = 6), analytic gradient.
+Data are synthetic (no dataset is shipped); see clid_slam_b200/synth.py.
+
+For N > 1 launch with torchrun (one rank per GPU); the map is replicated, every rank takes its
+own 131072-sample shard of an N x 131072 global batch (weak scaling), decoder gradients + loss
+go through one flat NCCL all-reduce and the replicated feature gradients through a second.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 131072
+SIDE, SHEETS = 520, 4
+L2_FLUSH_BYTES = 256 << 20
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--mode", default="analytic", choices=["analytic", "numerical"],
+                    help="eikonal gradient mode of the training step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ native arm
+def build_world(device, mode):
+    import torch
+
+    from clid_slam_b200.config import ncd128
+    from clid_slam_b200.model.decoder import Decoder
+    from clid_slam_b200.model.neural_points import NeuralPoints
+    from clid_slam_b200.synth import wavy_sheets
+
+    torch.manual_seed(42)
+    cfg = ncd128()
+    cfg.device = device
+    cfg.feature_std = 0.05          # the default 0.0 makes every feature exactly zero (SURVEY 8c gotchas)
+    cfg.local_map_radius = 1.0e4    # the whole ~1 M-point map is the local window (configs[2])
+    cfg.numerical_grad = mode == "numerical"
+    cfg.gradient_decimation = 10 if cfg.numerical_grad else 1
+    dec = Decoder(cfg, cfg.geo_mlp_hidden_dim, cfg.geo_mlp_level, 1)
+    npm = NeuralPoints(cfg)
+    npm.travel_dist = torch.zeros(1, device=device)
+    gen = torch.Generator(device=device).manual_seed(1)
+    pts = wavy_sheets(SIDE, SHEETS, cfg.voxel_size_m, gen, device=device)
+    npm.update(pts, torch.zeros(3, device=device), torch.eye(3, device=device), 0)
+    return cfg, dec, npm
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    from clid_slam_b200 import _lib, fused
+    from clid_slam_b200 import build as _build
+    from clid_slam_b200.ops.train import FusedTrainer
+    from clid_slam_b200.synth import sample_batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    if rank == 0:
+        _build.build()
+    if world > 1:
+        dist.barrier()
+    _lib.load()
+
+    cfg, dec, npm = build_world(device, args.mode)
+    gen = torch.Generator(device=device).manual_seed(1000 + rank)
+    n_batches = 4  # rotate a few batches so no step sees the previous step's exact access pattern
+    batches = [sample_batch(npm.neural_points, BATCH, gen) for _ in range(n_batches)]
+    host_batches = [tuple(t.cpu().pin_memory() for t in b) for b in batches]
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
+
+    trainer = FusedTrainer(cfg, npm, dec)
+    n_global = BATCH * world
+    nd_global = 0
+    if cfg.numerical_grad:
+        nd_global = world * ((BATCH + cfg.gradient_decimation - 1) // cfg.gradient_decimation)
+
+    def step(i, from_host=False):
+        if from_host:
+            x, label, weight, ts = (t.to(device, non_blocking=True) for t in host_batches[i % n_batches])
+        else:
+            x, label, weight, ts = batches[i % n_batches]
+        loss = trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global, sync=world > 1)
+        return loss
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        flush.zero_()
+        step(i)
+    sync_all()
+
+    # ---- timed region: K steps, device-resident inputs, L2 flushed (untimed) before every step
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    trainer.forward_events, trainer.backward_events = [], []
+    launches0 = trainer.launches
+    events = []
+    sync_all()
+    for i in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(i)
+        e1.record()
+        events.append((e0, e1))
+    sync_all()
+    total_ms = sum(a.elapsed_time(b) for a, b in events)
+    fwd_ms = [a.elapsed_time(b) for a, b in trainer.forward_events]
+    bwd_ms = [a.elapsed_time(b) for a, b in trainer.backward_events]
+    launches = trainer.launches - launches0
+    trainer.forward_events = trainer.backward_events = None
+
+    # ---- end to end: host (pinned) batch -> device, step, loss back to the host, every step
+    e2e_events = []
+    sync_all()
+    for i in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = step(i, from_host=True)
+        loss_host = loss.cpu()  # device -> host read of the step's result (synchronises)
+        e1.record()
+        e2e_events.append((e0, e1))
+    sync_all()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_events)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- inference-only forward (what the 40 % roofline target is stated on), same L2 hygiene
+    inf_events = []
+    x0 = batches[0][0]
+    for i in range(3):
+        fused.sdf_and_gradient(npm, dec, x0)
+    for i in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _, _, nn_count, _ = fused.sdf_and_gradient(npm, dec, batches[i % n_batches][0])
+        e1.record()
+        inf_events.append((e0, e1))
+    torch.cuda.synchronize()
+    inf_ms = statistics.median(a.elapsed_time(b) for a, b in inf_events)
+    mean_nn = float(nn_count.float().mean().item())
+
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        samples_per_step = BATCH * world
+        value = samples_per_step * args.steps / (total_ms * 1e-3)
+        e2e_value = samples_per_step * args.steps / (e2e_ms * 1e-3)
+        # algorithmic bytes of the fused forward kernel per sample (SURVEY.md 8d / DESIGN.md section 5)
+        b_fwd = 576.0 + 16.0 * mean_nn
+        evals = BATCH + (6 * ((BATCH + 9) // 10) if cfg.numerical_grad else 0)
+        fwd_avg_ms = statistics.mean(fwd_ms)
+        achieved = b_fwd * evals / (fwd_avg_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get("query_forward_kernel_dram_bytes_per_launch")
+        h2d = sum(tt.numel() * tt.element_size() for tt in host_batches[0])
+        line = {
+            "metric": "sampled-points/sec through SDF decoder+grad+loss (train step: fused gather+MLP+grad forward, "
+                      "bce+eikonal loss, backward, Adam)",
+            "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": "BASELINE configs[2]: 131072 samples/batch/GPU, 1.08M neural points (4 wavy sheets, "
+                            "0.4 m voxels), ncd128 decoder 11->64->1, Kc=81, K=6, brick index, "
+                            f"{args.mode} eikonal gradient",
+                "samples_per_step": samples_per_step, "neural_points": int(npm.count()),
+                "mean_valid_candidates": mean_nn, "l2": "flushed (256 MiB write) before every timed step",
+                "parallelism": f"batch-sharded x{world}, replicated map" if world > 1 else "single GPU",
+            },
+            "roofline": {
+                "kernel": "query_forward_kernel<64,1,6,bricks> (training forward)",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_sample": b_fwd, "samples_per_launch": evals,
+                "kernel_ms_avg": fwd_avg_ms, "backward_kernel_ms_avg": statistics.mean(bwd_ms),
+                "inference_forward": {
+                    "ms_median": inf_ms, "samples_per_s": BATCH / (inf_ms * 1e-3),
+                    "achieved_gbs": b_fwd * BATCH / (inf_ms * 1e-3) / 1e9,
+                    "frac": b_fwd * BATCH / (inf_ms * 1e-3) / 1e9 / peak,
+                },
+            },
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "final_loss": [float(v) for v in loss_host.tolist()],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference(args.mode, steps=3, warmup=1, n=BATCH)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_reference(mode, steps, warmup, n):
+    """The reference's algorithm for the same step on the host cores: the oracle port (torch CPU
+    ops, oracle/sdf_oracle.py -- the reference itself is pure PyTorch and is not on this box)."""
+    import torch
+
+    from oracle import sdf_oracle as oc
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = oc.OracleConfig(local_map_radius=1.0e4, numerical_grad=(mode == "numerical"),
+                          gradient_decimation=10 if mode == "numerical" else 1)
+    gen = torch.Generator().manual_seed(1)
+    m = oc.empty_map(cfg)
+    pts = oc.wavy_sheets(SIDE, SHEETS, cfg.voxel_size_m, gen)
+    oc.map_insert(m, pts, torch.zeros(3), 0, generator=gen)
+    params = oc.init_decoder(cfg, gen)
+    opt = oc.make_adam(cfg, [m.local_features], params)
+    batches = [oc.sample_batch(m.points, n, gen) for _ in range(2)]
+    times = []
+    for i in range(warmup + steps):
+        x, label, weight, ts = batches[i % 2]
+        t0 = time.perf_counter()
+        oc.train_iteration(m, params, opt, x.clone(), label, ts, weight)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return {"value": n * steps / total, "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": f"{steps} steps of {n} samples on the same 1.08M-point world ({mode} gradient), after {warmup} warm-up",
+            "ms_per_step": total / steps * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warmup = max(1, min(args.warmup, 2))
+    base = cpu_reference(args.mode, steps=steps, warmup=warmup, n=BATCH)
+    line = {
+        "impl": "reference",
+        "metric": "sampled-points/sec through SDF decoder+grad+loss (train step: fused gather+MLP+grad forward, "
+                  "bce+eikonal loss, backward, Adam)",
+        "value": base["value"], "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[2]: 131072 samples/batch, 1.08M neural points, ncd128 decoder, "
+                               f"{args.mode} eikonal gradient; reference algorithm (oracle port, torch CPU) on host cores"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

@@ -69,7 +69,7 @@ class ClidLossArgs(C.Structure):
     _fields_ = [
         ("sdf", C.c_void_p), ("grad", C.c_void_p), ("label", C.c_void_p), ("weight", C.c_void_p),
         ("dlogit", C.c_void_p), ("dgrad", C.c_void_p), ("loss", C.c_void_p),
-        ("n", C.c_int64), ("nd", C.c_int64),
+        ("n", C.c_int64), ("nd", C.c_int64), ("n_norm", C.c_int64), ("nd_norm", C.c_int64),
         ("sdf_scale", C.c_float), ("weight_e", C.c_float), ("num_eps", C.c_float), ("weighted", C.c_int32),
     ]
 

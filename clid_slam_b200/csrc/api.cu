@@ -270,7 +270,10 @@ int clid_sdf_loss(const ClidLossArgs* a, clid_stream_t stream) {
   LossParams p;
   p.sdf = a->sdf; p.grad = a->grad; p.label = a->label; p.weight = a->weight;
   p.dlogit = a->dlogit; p.dgrad = a->dgrad; p.loss = a->loss;
-  p.n = a->n; p.nd = a->nd; p.sdf_scale = a->sdf_scale; p.weight_e = a->weight_e; p.num_eps = a->num_eps;
+  p.n = a->n; p.nd = a->nd;
+  p.n_norm = a->n_norm > 0 ? a->n_norm : a->n;
+  p.nd_norm = a->nd_norm > 0 ? a->nd_norm : a->nd;
+  p.sdf_scale = a->sdf_scale; p.weight_e = a->weight_e; p.num_eps = a->num_eps;
   p.weighted = a->weighted;
   sdf_loss_kernel<<<elementwise_grid(a->n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();

@@ -25,6 +25,8 @@ struct LossParams {
   float* loss;           // [3] += total, bce, eikonal (un-weighted eikonal mean, like the reference logs)
   int64_t n;
   int64_t nd;            // decimated count for numerical mode, 0 otherwise
+  int64_t n_norm;        // mean denominators: the GLOBAL batch / decimated sizes when the batch is
+  int64_t nd_norm;       // sharded over ranks (== n / nd on one GPU)
   float sdf_scale;       // sigma of the BCE (= decoder sdf_scale)
   float weight_e;        // eikonal weight, 0 disables
   float num_eps;         // central-difference step
@@ -40,7 +42,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void __launch_bounds__(256) sdf_loss_kernel(const LossParams p) {
   __shared__ float red[2][8];
   float bce_sum = 0.f, eik_sum = 0.f;
-  const float inv_n = 1.0f / (float)p.n;
+  const float inv_n = 1.0f / (float)p.n_norm;
   const float s = p.sdf_scale;
   const bool analytic = p.grad != nullptr && p.weight_e > 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(256) sdf_loss_kernel(const LossParams p) {
     }
   }
   if (p.nd > 0 && p.weight_e > 0.f) {
-    const float inv_nd = 1.0f / (float)p.nd;
+    const float inv_nd = 1.0f / (float)p.nd_norm;
     const float two_eps = 2.0f * p.num_eps;
     const float* sh = p.sdf + p.n;
     float* dsh = p.dlogit + p.n;
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(256) sdf_loss_kernel(const LossParams p) {
   if (threadIdx.x == 0) {
     float b = 0.f, e = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { b += red[0][w]; e += red[1][w]; }
-    const int64_t n_e = analytic ? p.n : p.nd;
+    const int64_t n_e = analytic ? p.n_norm : p.nd_norm;
     const float bce = b * inv_n;
     const float eik = n_e > 0 ? e / (float)n_e : 0.f;
     atomicAdd(p.loss + 1, bce);

@@ -83,6 +83,9 @@ class FusedTrainer:
         self.numerical = bool(config.ekional_loss_on and config.numerical_grad)
         self.weight_e = float(config.weight_e) if config.ekional_loss_on else 0.0
         self.losses: List[torch.Tensor] = []  # [3] per iteration: total, bce, eikonal (device tensors)
+        self.forward_events = None  # bench hook: list that receives (start, end) CUDA events of the forward
+        self.backward_events = None
+        self.launches = 0           # kernels of libclid_sdf.so launched so far
 
     # ------------------------------------------------------------------
     def _shifted(self, x: torch.Tensor) -> torch.Tensor:
@@ -97,13 +100,17 @@ class FusedTrainer:
         return out
 
     def iteration(self, x: torch.Tensor, label: torch.Tensor, ts: Optional[torch.Tensor], weight: torch.Tensor,
-                  apply_step: bool = True):
+                  apply_step: bool = True, n_global: int = 0, nd_global: int = 0, sync: bool = False):
         """One mapping iteration on the batch.  With apply_step=False the optimiser step is left to
-        a later `adam_step()` call, so the accumulated gradients can be inspected (tests)."""
+        a later `adam_step()` call, so the accumulated gradients can be inspected (tests).
+
+        Sharded use (one process per GPU): every rank passes its slice of the batch, the GLOBAL
+        batch size `n_global` (and decimated count `nd_global` in numerical mode) as the loss
+        normalisers, and sync=True so gradients and losses are all-reduced before the step."""
         cfg, npm, dec, lib, dev = self.cfg, self.npm, self.dec, self.lib, self.device
         x = _q._prep_points(x, "coord")
         n = x.shape[0]
-        if n == 0:
+        if n == 0 and not sync:
             return
         nd = 0
         x_all, ts_all = x, ts
@@ -115,9 +122,17 @@ class FusedTrainer:
                 pad = torch.full((shifted.shape[0],), INT32_MIN, dtype=torch.int32, device=dev)
                 ts_all = torch.cat((ts.to(torch.int32), pad), 0)
         want_grad = self.analytic and self.weight_e > 0
+        if self.forward_events is not None:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
         res = _q.forward(npm, dec, x_all, ts_all, training_mode=True, query_locally=True,
                          want_sdf=True, want_grad=want_grad, want_idx=True)
+        if self.forward_events is not None:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            self.forward_events.append((ev0, ev1))
         n_all = x_all.shape[0]
+        self.launches += 3 if n_all > 0 else 0
 
         loss = torch.zeros(3, dtype=torch.float32, device=dev)
         dlogit = torch.empty(n_all, dtype=torch.float32, device=dev)
@@ -132,6 +147,7 @@ class FusedTrainer:
         la.weight = _lib.ptr(w, torch.float32, "weight")
         la.dlogit, la.dgrad, la.loss = dlogit.data_ptr(), (dgrad.data_ptr() if want_grad else None), loss.data_ptr()
         la.n, la.nd = n, nd
+        la.n_norm, la.nd_norm = int(n_global), int(nd_global)
         la.sdf_scale = float(dec.sdf_scale)
         la.weight_e = self.weight_e
         la.num_eps = float(cfg.voxel_size_m * cfg.num_grad_step_ratio)
@@ -144,6 +160,9 @@ class FusedTrainer:
             if dec.use_leaky_relu:
                 flags |= _lib.LEAKY_RELU
             ds = dec.abi_struct()
+            if self.backward_events is not None:
+                bv0 = torch.cuda.Event(enable_timing=True)
+                bv0.record()
             rc = lib.clid_train_backward(
                 C.byref(m), C.byref(ds), x_all.data_ptr(), res["knn_idx"].data_ptr(), dlogit.data_ptr(),
                 dgrad.data_ptr() if want_grad else None, n_all, n if want_grad else 0, flags,
@@ -151,7 +170,20 @@ class FusedTrainer:
                 None if self.touched is None else self.touched.data_ptr(),
                 None if self.dec_grad is None else self.dec_grad.data_ptr(), stream)
             _lib.check(rc, "clid_train_backward")
+            if self.backward_events is not None:
+                bv1 = torch.cuda.Event(enable_timing=True)
+                bv1.record()
+                self.backward_events.append((bv0, bv1))
 
+        if sync:
+            # one flat all-reduce for [decoder grads | loss scalars]; the replicated feature table
+            # needs its gradient (and which rows were touched) summed as well
+            from .. import dist as _dist
+
+            _dist.FlatAllReduce([self.dec_grad, loss])()
+            if self.train_features:
+                _dist.all_reduce_sum(self.feat_grad)
+                _dist.all_reduce_max(self.touched)
         self.losses.append(loss)
         if apply_step:
             self.adam_step()
@@ -180,3 +212,4 @@ class FusedTrainer:
             aa.lr, aa.beta1, aa.beta2 = float(cfg.lr), 0.9, 0.99
             aa.eps, aa.weight_decay, aa.step = float(cfg.adam_eps), float(cfg.weight_decay), self.step
             _lib.check(lib.clid_adam_step(C.byref(aa), stream), "clid_adam_step")
+            self.launches += 1

@@ -189,6 +189,8 @@ typedef struct ClidLossArgs {
   float* loss;
   int64_t n;
   int64_t nd;
+  int64_t n_norm;        /* denominators of the two means; 0 = n / nd.  A rank that holds a shard of the */
+  int64_t nd_norm;       /* batch passes the global sizes so that summing over ranks gives the global loss */
   float sdf_scale;
   float weight_e;
   float num_eps;
