@@ -38,7 +38,7 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--mode", default="analytic", choices=["analytic", "numerical"],
@@ -198,6 +198,7 @@ def run_native(args):
     launches0 = trainer.launches
     events = []
     sync_all()
+    torch.cuda.nvtx.range_push("timed")
     for i in range(args.steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -206,6 +207,7 @@ def run_native(args):
         e1.record()
         events.append((e0, e1))
     sync_all()
+    torch.cuda.nvtx.range_pop()
     total_ms = sum(a.elapsed_time(b) for a, b in events)
     fwd_ms = [a.elapsed_time(b) for a, b in trainer.forward_events]
     bwd_ms = [a.elapsed_time(b) for a, b in trainer.backward_events]

@@ -15,7 +15,7 @@ from .ops import query as _q
 
 def sdf_and_gradient(neural_points, decoder, query_points: torch.Tensor, query_ts: Optional[torch.Tensor] = None,
                      training_mode: bool = False, query_locally: bool = True, with_gradient: bool = True,
-                     with_certainty: bool = True, use_bricks: bool = False):
+                     with_certainty: bool = True, use_bricks: Optional[bool] = None):
     """SDF, its spatial gradient, the candidate count and the queried certainty of every point.
 
     Returns (sdf [N], grad [N,3] | None, nn_counts [N] int32, certainty [N] | None).  Values equal

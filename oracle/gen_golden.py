@@ -375,7 +375,26 @@ def map_case(ref, name, cfg, frames, travel, seed):
     print(f"  wrote {path}: frames={len(frames)} M={npm.count()} local={npm.local_count()}")
 
 
+def sampler_case(ref, name, cfg, seed):
+    """DataSampler.sample_pin of the reference under a fixed torch seed (CPU generator)."""
+    from utils.data_sampler import DataSampler
+
+    gen = torch.Generator().manual_seed(seed)
+    scan = torch.randn(300, 3, generator=gen) * torch.tensor([15.0, 15.0, 2.0]) + torch.tensor([0.0, 0.0, 1.0])
+    torch.manual_seed(seed)
+    coord, label, _, _, _, weight = DataSampler(cfg).sample_pin(scan, None, None, None)
+    path = os.path.join(GOLDEN_DIR, f"sampler_{name}.npz")
+    np.savez_compressed(path, cfg_sampler=np.array(json.dumps({
+        k: getattr(cfg, k) for k in ("surface_sample_range_m", "surface_sample_n", "free_front_n", "free_behind_n",
+                                      "free_sample_begin_ratio", "free_sample_end_dist_m", "dist_weight_on",
+                                      "dist_weight_scale", "max_range", "behind_dropoff_on")})),
+        seed=np.int64(seed), scan=scan.numpy(), coord=coord.numpy(), label=label.numpy(), weight=weight.numpy())
+    print(f"  wrote {path}: {scan.shape[0]} rays -> {coord.shape[0]} samples")
+
+
 def main():
+    """python -m oracle.gen_golden [query|train|map|sampler]   (no argument = everything)"""
+    only = sys.argv[1] if len(sys.argv) > 1 else None
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     ref = ref_loader.load()
     torch.set_num_threads(8)
@@ -388,7 +407,22 @@ def main():
     right = world[world[:, 0] > -2.0] + torch.tensor([0.07, -0.05, 0.03])
     two_frames = [(left, origin, 0), (right, torch.tensor([1.0, 0.0, 0.0]), 2)]
 
-    print("query fixtures")
+    if only in (None, "query"):
+        print("query fixtures")
+        _query_cases(ref, gen, one_frame, two_frames, origin)
+    if only in (None, "train"):
+        print("train fixtures")
+        _train_cases(ref, one_frame, two_frames)
+    if only in (None, "map"):
+        print("map fixtures")
+        _map_cases(ref, two_frames)
+    if only in (None, "sampler"):
+        print("sampler fixtures")
+        sampler_case(ref, "ncd128", make_ref_config(ref), 41)
+    print("done")
+
+
+def _query_cases(ref, gen, one_frame, two_frames, origin):
     query_case(ref, "ncd128_train", make_ref_config(ref), one_frame, [0.0], 2048, True, True, 1)
     query_case(ref, "ncd128_infer", make_ref_config(ref), one_frame, [0.0], 2048, False, True, 2, with_ts=False)
     query_case(ref, "smallbuf_collisions", make_ref_config(ref, buffer_size=4001), one_frame, [0.0], 2048, True, True, 3)
@@ -403,7 +437,8 @@ def main():
     query_case(ref, "leaky", make_ref_config(ref, mlp_leaky_relu=True), one_frame, [0.0], 1024, False, True, 12, with_ts=False)
     query_case(ref, "res02", make_ref_config(ref, voxel_size_m=0.2, sigma_sigmoid_m=0.05), [(sheet_world(gen, 96, 1, 0.2), origin, 0)], [0.0], 1024, True, True, 13)
 
-    print("train fixtures")
+
+def _train_cases(ref, one_frame, two_frames):
     train_case(ref, "analytic_l1h64", make_ref_config(ref, numerical_grad=False), one_frame, [0.0], 2048, 3, 21)
     train_case(ref, "numerical_l1h64", make_ref_config(ref), one_frame, [0.0], 2048, 3, 22)
     train_case(ref, "analytic_l2h32", make_ref_config(ref, numerical_grad=False, geo_mlp_level=2, geo_mlp_hidden_dim=32), one_frame, [0.0], 2048, 2, 23)
@@ -413,11 +448,11 @@ def main():
     train_case(ref, "numerical_frozen", make_ref_config(ref), one_frame, [0.0], 2048, 2, 27, freeze_decoder=True)
     train_case(ref, "analytic_unweighted", make_ref_config(ref, numerical_grad=False, loss_weight_on=False), one_frame, [0.0], 1024, 2, 28)
 
-    print("map fixtures")
+
+def _map_cases(ref, two_frames):
     map_case(ref, "two_frames", make_ref_config(ref), two_frames, [0.0, 1.0, 2.0], 31)
     map_case(ref, "two_frames_far", make_ref_config(ref), two_frames, [0.0, 100.0, 400.0], 32)
     map_case(ref, "smallbuf", make_ref_config(ref, buffer_size=4001), two_frames, [0.0, 1.0, 2.0], 33)
-    print("done")
 
 
 if __name__ == "__main__":

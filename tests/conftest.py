@@ -10,6 +10,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+    # make sure libclid_sdf.so matches the sources that are about to be tested (no-op when fresh)
+    from clid_slam_b200 import build as _build
+
+    _build.build()
 
 
 def pytest_collection_modifyitems(config, items):

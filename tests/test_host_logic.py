@@ -1,0 +1,184 @@
+"""CPU tests of the host-side logic: per-frame map maintenance of the product NeuralPoints (torch ops,
+device-agnostic) against reference-generated fixtures, the sampler, config loading, and the
+batch-sharding / all-reduce plumbing with a 2-process gloo group."""
+import json
+import os
+import tempfile
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import golden_io as gio
+from clid_slam_b200 import dist as cdist
+from clid_slam_b200.config import Config, ncd128
+from clid_slam_b200.model.neural_points import NeuralPoints
+from clid_slam_b200.utils.data_sampler import DataSampler
+from clid_slam_b200.utils.tools import voxel_down_sample_torch
+from oracle import sdf_oracle as oc
+
+
+def _cpu_config(ocfg) -> Config:
+    cfg = Config()
+    for name in ocfg.__dataclass_fields__:
+        setattr(cfg, name, getattr(ocfg, name))
+    cfg.device = "cpu"
+    return cfg
+
+
+@pytest.mark.parametrize("name", gio.names("map"))
+def test_map_insert_and_local_window_match_reference(name):
+    fx = gio.load("map", name)
+    cfg = _cpu_config(gio.config_of(fx))
+    npm = NeuralPoints(cfg)
+    npm.travel_dist = gio.t(fx["travel_dist"])
+    for i in range(int(fx["n_frames"])):
+        pre = f"frame{i}_map_"
+        ratio = npm.update(gio.t(fx[f"frame{i}_points"]), gio.t(fx[f"frame{i}_sensor"]), torch.eye(3),
+                           int(fx[f"frame{i}_ts"]))
+        assert ratio == float(fx[f"frame{i}_ratio"])
+        assert torch.equal(npm.buffer_pt_index, gio.dense_table(fx, pre))
+        assert torch.equal(npm.neural_points, gio.t(fx[pre + "points"]))
+        assert torch.equal(npm.point_ts_create, gio.t(fx[pre + "ts_create"]))
+        assert torch.equal(npm.point_ts_update, gio.t(fx[pre + "ts_update"]))
+        assert torch.equal(npm.local_mask, gio.t(fx[pre + "local_mask"]))
+        assert torch.equal(npm.global2local, gio.t(fx[pre + "global2local"]))
+        assert torch.equal(npm.local_neural_points, gio.t(fx[pre + "local_points"]))
+        assert npm.geo_features.shape == (npm.count() + 1, cfg.feature_dim)
+        assert isinstance(npm.local_geo_features, torch.nn.Parameter)
+        assert npm.local_geo_features.shape[0] == npm.local_count() + 1
+    # write-back is the identity when nothing was trained
+    before = npm.geo_features.clone()
+    npm.assign_local_to_global()
+    assert torch.equal(before, npm.geo_features)
+
+
+def test_prune_and_recreate_hash_keep_the_table_consistent():
+    cfg = ncd128()
+    cfg.device, cfg.buffer_size = "cpu", 200_003
+    npm = NeuralPoints(cfg)
+    npm.travel_dist = torch.zeros(4)
+    gen = torch.Generator().manual_seed(0)
+    pts = oc.wavy_sheets(40, 1, cfg.voxel_size_m, gen)
+    npm.update(pts, torch.zeros(3), torch.eye(3), 0)
+    n0 = npm.count()
+    npm.point_certainties = torch.rand(n0, generator=gen) * 4
+    assert npm.prune_map(2.0, min_prune_count=10, global_prune=True)
+    assert npm.count() < n0 and npm.geo_features.shape[0] == npm.count() + 1
+    npm.recreate_hash(torch.zeros(3), torch.eye(3), kept_points=True, with_ts=True, cur_ts=0)
+    # every slot points at a point whose voxel hashes to that slot
+    slots = torch.nonzero(npm.buffer_pt_index >= 0).flatten()
+    owners = npm.buffer_pt_index[slots]
+    cells = (npm.neural_points[owners] / npm.resolution).floor().long()
+    assert torch.equal(oc.voxel_hash(cells, cfg.buffer_size) % cfg.buffer_size, slots)
+    assert owners.unique().numel() == owners.numel()
+
+
+def test_pickle_round_trip_drops_the_cuda_cache():
+    import pickle
+
+    cfg = ncd128()
+    cfg.device, cfg.buffer_size = "cpu", 50_021
+    npm = NeuralPoints(cfg)
+    npm.travel_dist = torch.zeros(1)
+    npm.update(torch.rand(2000, 3) * 20, torch.zeros(3), torch.eye(3), 0)
+    npm._brick_cache = {True: ("key", object())}
+    npm.clear_temp()
+    clone = pickle.loads(pickle.dumps(npm))
+    assert clone.count() == npm.count() and clone._brick_cache == {}
+    assert clone.buffer_pt_index is None  # like the reference, rebuilt by recreate_hash on load
+
+
+def test_voxel_downsample_matches_oracle():
+    gen = torch.Generator().manual_seed(3)
+    pts = torch.rand(20000, 3, generator=gen) * torch.tensor([30.0, 25.0, 4.0]) - 10.0
+    assert torch.equal(voxel_down_sample_torch(pts, 0.4), oc.voxel_downsample_indices(pts, 0.4))
+
+
+def test_sample_pin_matches_reference_fixture():
+    fx = gio.load("sampler", "ncd128")
+    cfg = ncd128()
+    cfg.device = "cpu"
+    for k, v in json.loads(str(fx["cfg_sampler"])).items():
+        setattr(cfg, k, v)
+    torch.manual_seed(int(fx["seed"]))
+    coord, label, normal, sem, color, weight = DataSampler(cfg).sample_pin(gio.t(fx["scan"]), None, None, None)
+    assert normal is None and sem is None and color is None
+    assert torch.equal(coord, gio.t(fx["coord"]))
+    assert torch.equal(label, gio.t(fx["label"]))
+    assert torch.equal(weight, gio.t(fx["weight"]))
+
+
+def test_config_load_reads_hot_path_sections():
+    text = """
+process: {min_range_m: 1.0, max_range_m: 60.0, vox_down_m: 0.1}
+sampler: {surface_sample_range_m: 0.25, surface_sample_n: 4, free_sample_begin_ratio: 0.5,
+          free_sample_end_dist_m: 1.2, free_front_sample_n: 2}
+neuralpoints: {voxel_size_m: 0.4, num_nei_cells: 2, search_alpha: 0.5, weighted_first: True}
+loss: {sigma_sigmoid_m: 0.1, loss_weight_on: True, dist_weight_scale: 0.8}
+continual: {batch_size_new_sample: 1000, pool_capacity: 1e7}
+optimizer: {iters: 10, batch_size: 16384, learning_rate: 0.01, adaptive_iters: True}
+"""
+    with tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False) as fh:
+        fh.write(text)
+    try:
+        cfg = Config()
+        cfg.load(fh.name)
+    finally:
+        os.unlink(fh.name)
+    ref = ncd128()
+    for key in ("voxel_size_m", "num_nei_cells", "search_alpha", "surface_sample_n", "free_front_n", "bs", "iters",
+                "loss_weight_on", "bs_new_sample", "pool_capacity", "local_map_radius", "infer_bs", "sigma_sigmoid_m"):
+        assert getattr(cfg, key) == getattr(ref, key), key
+    assert cfg.numerical_grad and cfg.gradient_decimation == 10
+
+
+def test_shard_bounds_tile_the_batch():
+    for n in (0, 1, 7, 16384, 131072, 131075):
+        for world in (1, 2, 3, 8):
+            edges = [cdist.shard_bounds(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+            sizes = [e - b for b, e in edges]
+            assert max(sizes) - min(sizes) <= 1
+            for dec in (1, 10):
+                assert sum(cdist.decimated_count(b, e, dec) for b, e in edges) == len(range(0, n, dec))
+
+
+def _gloo_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dec_grad = torch.full((833,), float(rank + 1))
+        loss = torch.tensor([1.0, 2.0, 3.0]) * (rank + 1)
+        cdist.FlatAllReduce([dec_grad, None, loss])()
+        feat = torch.zeros(10, 8)
+        feat[rank] = 1.0
+        cdist.all_reduce_sum(feat)
+        touched = torch.zeros(10, dtype=torch.uint8)
+        touched[rank] = 1
+        cdist.all_reduce_max(touched)
+        before = torch.arange(6, dtype=torch.float32)
+        cert = before + (rank + 1) * 0.5
+        ts = torch.tensor([rank, 5 - rank, 2], dtype=torch.int32)
+        cdist.reduce_side_effects(cert, before, ts)
+        torch.save({"dec": dec_grad, "loss": loss, "feat": feat, "touched": touched, "cert": cert, "ts": ts},
+                   os.path.join(out_dir, f"r{rank}.pt"))
+    finally:
+        torch.distributed.destroy_process_group()
+
+
+def test_gradient_sync_with_two_gloo_ranks():
+    world = 2
+    port = 29500 + os.getpid() % 2000
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_gloo_worker, args=(world, port, tmp), nprocs=world, join=True)
+        outs = [torch.load(os.path.join(tmp, f"r{r}.pt")) for r in range(world)]
+    for o in outs:
+        assert torch.equal(o["dec"], torch.full((833,), 3.0))
+        assert torch.equal(o["loss"], torch.tensor([3.0, 6.0, 9.0]))
+        assert o["feat"].sum().item() == 16.0 and o["feat"][0].sum() == 8 and o["feat"][1].sum() == 8
+        assert o["touched"].tolist()[:3] == [1, 1, 0]
+        assert torch.allclose(o["cert"], torch.arange(6, dtype=torch.float32) + 1.5)
+        assert o["ts"].tolist() == [1, 5, 2]
+    assert torch.equal(outs[0]["dec"], outs[1]["dec"])
