@@ -82,3 +82,24 @@ def test_product_refuses_cpu_tensors():
     assert npm.count() > 0
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         npm.query_feature(pts[:4])
+
+
+def test_install_aliases_reference_module_names():
+    """clid_slam_b200.install() makes the names slam.py imports resolve to this package."""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import clid_slam_b200; clid_slam_b200.install()\n"
+        "from model.neural_points import NeuralPoints\n"
+        "from model.decoder import Decoder\n"
+        "from utils.mapper import Mapper\n"
+        "from utils.loss import sdf_bce_loss\n"
+        "assert NeuralPoints.__module__ == 'clid_slam_b200.model.neural_points'\n"
+        "assert Mapper.__module__ == 'clid_slam_b200.utils.mapper' and Decoder.__module__.startswith('clid_slam_b200')\n"
+        "assert 'utils.data_sampler' not in sys.modules or not sys.modules['utils.data_sampler'].__name__.startswith('clid')\n"
+        "print('ok')\n" % ROOT
+    )
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr

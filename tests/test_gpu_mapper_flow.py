@@ -1,0 +1,109 @@
+"""slam.py-shaped flow on the GPU: a few synthetic scans through Mapper.process_frame + mapping
+(sample_pin sampler), the way slam.py:135-208 drives the modules."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class FakeDataset:
+    lose_track = False
+    stop_status = False
+    processed_frame = 0
+    gt_pose_provided = True
+    pgo_poses = None
+    static_mask = None
+
+    def __init__(self, n):
+        self.gt_poses = self.odom_poses = np.tile(np.eye(4), (n, 1, 1))
+
+
+def _scan(gen, device, n=6000):
+    """Points of a wavy floor + a wall, in the sensor frame."""
+    xy = (torch.rand(n, 2, generator=gen, device=device) - 0.5) * 40
+    floor = torch.cat((xy, -1.5 + 0.3 * torch.sin(xy[:, :1] / 3)), dim=1)
+    yz = (torch.rand(n // 3, 2, generator=gen, device=device) - 0.5) * torch.tensor([30.0, 4.0], device=device)
+    wall = torch.cat((torch.full((n // 3, 1), 12.0, device=device), yz), dim=1)
+    pts = torch.cat((floor, wall), 0)
+    return pts[pts.norm(dim=1) > 1.0]
+
+
+@pytest.mark.parametrize("mode", ["numerical", "analytic"])
+def test_three_frames_train_and_write_back(mode):
+    from clid_slam_b200.config import ncd128
+    from clid_slam_b200.model.decoder import Decoder
+    from clid_slam_b200.model.neural_points import NeuralPoints
+    from clid_slam_b200.utils.mapper import Mapper
+    from clid_slam_b200.utils.tools import freeze_model
+
+    torch.manual_seed(42)
+    cfg = ncd128()
+    cfg.device = "cuda"
+    cfg.use_pin_mapper = True
+    cfg.buffer_size = 2_000_003
+    cfg.feature_std = 0.0  # reference default: features start at exactly zero
+    if mode == "analytic":
+        cfg.numerical_grad, cfg.gradient_decimation = False, 1
+    dec = Decoder(cfg, cfg.geo_mlp_hidden_dim, cfg.geo_mlp_level, 1)
+    npm = NeuralPoints(cfg)
+    frames = 3
+    ds = FakeDataset(frames)
+    mapper = Mapper(cfg, ds, npm, None, dec)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    first_loss = last_loss = None
+    for frame in range(frames):
+        ds.processed_frame = frame
+        pose = torch.eye(4, device="cuda", dtype=torch.float64)
+        pose[0, 3] = 0.5 * frame
+        ds.gt_poses[frame, 0, 3] = 0.5 * frame
+        npm.travel_dist = torch.arange(frame + 1, device="cuda", dtype=torch.float32) * 0.5
+        mapper.process_frame(_scan(gen, "cuda"), None, pose, frame)
+        assert npm.count() > 0 and npm.local_count() > 0
+        assert mapper.pool_sample_count == mapper.coord_pool.shape[0]
+        if frame == 2:
+            freeze_model(dec)  # slam.py:193-196 freezes the decoder after freeze_after_frame
+        before = npm.geo_features.clone()
+        dec_before = [p.detach().clone() for p in dec.parameters()]
+        mapper.mapping(12)
+        losses = mapper.last_losses.cpu()
+        assert torch.isfinite(losses).all()
+        first_loss = losses[0, 0] if first_loss is None else first_loss
+        last_loss = losses[-1, 0]
+        assert not torch.equal(before, npm.geo_features), "trained features must be written back to the global map"
+        changed = any(not torch.equal(a, b.detach()) for a, b in zip(dec_before, dec.parameters()))
+        assert changed == (frame < 2), "decoder trains until frozen"
+        assert float(npm.point_certainties.sum()) > 0
+        assert int(npm.point_ts_update.max()) == frame
+    assert last_loss < first_loss, (first_loss, last_loss)
+    # the map answers queries afterwards
+    from clid_slam_b200 import fused
+
+    probe = npm.neural_points[::50].contiguous()
+    sdf, grad, nn, cert = fused.sdf_and_gradient(npm, dec, probe)
+    assert torch.isfinite(sdf).all() and torch.isfinite(grad).all() and int(nn.min()) >= 1
+    assert float(sdf.abs().mean()) < 0.2  # neural points sit on the surface: |sdf| should already be small
+
+
+def test_dynamic_filter_and_certainty_queries_run():
+    from clid_slam_b200.config import ncd128
+    from clid_slam_b200.model.decoder import Decoder
+    from clid_slam_b200.model.neural_points import NeuralPoints
+    from clid_slam_b200.utils.mapper import Mapper
+
+    torch.manual_seed(1)
+    cfg = ncd128()
+    cfg.device, cfg.use_pin_mapper, cfg.buffer_size = "cuda", True, 500_009
+    dec = Decoder(cfg, 64, 1, 1)
+    npm = NeuralPoints(cfg)
+    ds = FakeDataset(2)
+    mapper = Mapper(cfg, ds, npm, None, dec)
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    npm.travel_dist = torch.zeros(2, device="cuda")
+    pose = torch.eye(4, device="cuda", dtype=torch.float64)
+    mapper.process_frame(_scan(gen, "cuda", 3000), None, pose, 0)
+    mapper.mapping(5)
+    ds.processed_frame = 1
+    mapper.process_frame(_scan(gen, "cuda", 3000), None, pose, 1, filter_dynamic=True)
+    assert mapper.static_mask.dtype == torch.bool and mapper.static_mask.numel() > 0
+    assert mapper.new_idx is not None
