@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--mode", default="analytic", choices=["analytic", "numerical"],
                     help="eikonal gradient mode of the training step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharding", default="spatial", choices=["spatial", "replicated"],
+                    help="N > 1: slab-partitioned samples with one flat all-reduce (default) or any-sample-anywhere "
+                         "with a dense feature-gradient all-reduce")
     return ap.parse_args()
 
 
@@ -161,7 +164,22 @@ def run_native(args):
     cfg, dec, npm = build_world(device, args.mode)
     gen = torch.Generator(device=device).manual_seed(1000 + rank)
     n_batches = 4  # rotate a few batches so no step sees the previous step's exact access pattern
-    batches = [sample_batch(npm.neural_points, BATCH, gen) for _ in range(n_batches)]
+    shards = None
+    if world > 1 and args.sharding == "spatial":
+        # slab partition along the longest map axis; a rank's samples are those whose voxel lies in
+        # its slab (what a per-rank replay pool would hand out), see clid_slam_b200/dist.py
+        from clid_slam_b200.dist import SpatialShards
+
+        shards = SpatialShards(npm.local_neural_points, cfg.voxel_size_m, reach=cfg.num_nei_cells, world_size=world)
+        own_points = npm.neural_points[shards.row_owner[:-1] == rank]
+        batches = []
+        for _ in range(n_batches):
+            cand = sample_batch(own_points, int(BATCH * 1.25), gen)
+            keep = torch.nonzero(shards.owner_of(cand[0]) == rank).flatten()[:BATCH]
+            assert keep.numel() == BATCH, "not enough samples inside the slab"
+            batches.append(tuple(t[keep].contiguous() for t in cand))
+    else:
+        batches = [sample_batch(npm.neural_points, BATCH, gen) for _ in range(n_batches)]
     host_batches = [tuple(t.cpu().pin_memory() for t in b) for b in batches]
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
 
@@ -176,7 +194,8 @@ def run_native(args):
             x, label, weight, ts = (t.to(device, non_blocking=True) for t in host_batches[i % n_batches])
         else:
             x, label, weight, ts = batches[i % n_batches]
-        loss = trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global, sync=world > 1)
+        loss = trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global,
+                                 sync=world > 1 and shards is None, shards=shards)
         return loss
 
     def sync_all():
@@ -278,7 +297,11 @@ def run_native(args):
                             f"{args.mode} eikonal gradient",
                 "samples_per_step": samples_per_step, "neural_points": int(npm.count()),
                 "mean_valid_candidates": mean_nn, "l2": "flushed (256 MiB write) before every timed step",
-                "parallelism": f"batch-sharded x{world}, replicated map" if world > 1 else "single GPU",
+                "parallelism": ("single GPU" if world == 1 else
+                                f"x{world}: samples sharded by map slab, one flat NCCL all-reduce "
+                                f"[decoder grads | loss | {int(shards.shared_rows.numel())} shared feature rows] per step"
+                                if shards is not None else
+                                f"x{world}: batch-sharded, replicated map, dense feature-gradient all-reduce"),
             },
             "roofline": {
                 "kernel": "query_forward_kernel<64,1,6,bricks> (training forward)",

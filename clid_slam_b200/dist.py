@@ -2,20 +2,29 @@
 NVLink 5 / NVSwitch on the box, gloo on CPU for the host-logic tests).
 
 The reference is single-process, so this is new functionality whose contract
-is "N ranks on one batch == 1 rank on the same batch": the sample batch is sharded across
-ranks (every sample's forward / loss / backward only reads the replicated map), and the
-reductions the reference does over the whole batch are completed with all-reduces:
+is "N ranks on one global batch == 1 rank on the same batch" (up to fp32 summation order).
+Every sample's forward / loss / backward only reads map state, so the batch is sharded across
+ranks; the reductions the reference does over the whole batch are completed with all-reduces.
 
-  * decoder gradients + the three loss scalars: ONE flat fp32 buffer (833 + 3 floats at ncd128
-    shapes), all-reduced right behind the backward kernel on the same stream;
-  * neural-point feature gradients (the features are replicated): all-reduced with their
-    `touched` flags so every rank applies the identical Adam step;
-  * certainty / ts_update side effects are only consumed between frames, so they are reduced
-    once per mapping() call (`reduce_side_effects`), not per iteration.
+Two sharding modes (FusedTrainer.iteration):
+
+* replicated (`sync=True`, no shards): any sample may sit on any rank.  Per iteration one flat
+  all-reduce of [decoder grads | loss] plus a dense all-reduce of the replicated feature gradient
+  (35 MB at 1 M points) -- correct but bandwidth-bound; kept as the simple reference mode.
+
+* spatial (`shards=SpatialShards(...)`): space is cut into slabs along one axis, a sample belongs
+  to the rank that owns the slab of its voxel.  A sample only touches neural points within
+  `reach` voxels, so feature rows are private to their slab's rank except for a thin band around
+  every slab boundary (`shared_rows`).  Per iteration ONE flat all-reduce carries
+  [decoder grads | loss | gradients of the shared rows]; every rank then applies the identical Adam
+  step to the shared rows and its own step to its private rows.  Other ranks' private rows go stale
+  locally but are never read; `SpatialShards.gather_features` re-replicates the table once per
+  mapping() call.  Certainty / ts_update side effects are likewise reduced once per call
+  (`reduce_side_effects`).
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -43,9 +52,9 @@ def decimated_count(begin: int, end: int, decimation: int) -> int:
 
 
 class FlatAllReduce:
-    """Sum-all-reduce several small tensors through one flat buffer (one collective launch)."""
+    """Sum-all-reduce several tensors through one flat buffer (one collective launch)."""
 
-    def __init__(self, tensors: Sequence[torch.Tensor], group=None):
+    def __init__(self, tensors: Sequence[Optional[torch.Tensor]], group=None):
         self.tensors = [t for t in tensors if t is not None]
         self.group = group
         total = sum(t.numel() for t in self.tensors)
@@ -86,3 +95,59 @@ def reduce_side_effects(certainty: torch.Tensor, certainty_before: torch.Tensor,
     dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=group)
     certainty.copy_(certainty_before + delta)
     dist.all_reduce(ts_update, op=dist.ReduceOp.MAX, group=group)
+
+
+class SpatialShards:
+    """Slab partition of the local map along one axis, in voxel units.
+
+    boundaries  [world-1] int64 cell coordinates b_1 < ... ; rank r owns cells in [b_r, b_{r+1})
+    shared_rows rows of the local feature table whose voxel lies within `reach + margin` cells of
+                a boundary: the only rows that can receive gradient from two ranks
+    row_owner   [rows] rank that owns each local row (shared rows included: they have one owner for
+                the final gather, although every rank keeps them up to date)
+    The margin (default 1 voxel) covers the numerical-gradient probes, which are shifted by a
+    fraction of a voxel and may fall into the next cell.
+    """
+
+    def __init__(self, points: torch.Tensor, resolution: float, reach: int, world_size: int, axis: Optional[int] = None,
+                 margin: int = 1, boundaries: Optional[torch.Tensor] = None, pad_rows: int = 1):
+        self.resolution = float(resolution)
+        self.world_size = int(world_size)
+        dev = points.device
+        if axis is None:  # cut across the longest extent of the map
+            ext = points.amax(0) - points.amin(0)
+            axis = int(torch.argmax(ext).item())
+        self.axis = axis
+        cell = torch.floor(points[:, axis] / self.resolution).to(torch.int64)
+        if boundaries is None:
+            if world_size > 1:
+                q = torch.arange(1, world_size, device=dev, dtype=torch.float32) / world_size
+                srt = torch.sort(cell).values
+                pick = (q * (srt.numel() - 1)).long()
+                boundaries = torch.unique(srt[pick])  # equal point counts per slab
+            else:
+                boundaries = torch.empty(0, dtype=torch.int64, device=dev)
+        self.boundaries = boundaries.to(device=dev, dtype=torch.int64).contiguous()
+        band = reach + margin
+        shared = torch.zeros(cell.shape[0], dtype=torch.bool, device=dev)
+        for b in self.boundaries.tolist():
+            shared |= (cell >= b - band) & (cell <= b + band - 1)
+        owner = torch.searchsorted(self.boundaries, cell, right=True)
+        pad = torch.zeros(pad_rows, dtype=torch.bool, device=dev)  # the feature table's padding row
+        self.shared_mask = torch.cat((shared, pad))
+        self.shared_rows = torch.nonzero(self.shared_mask).flatten()
+        self.row_owner = torch.cat((owner, torch.zeros(pad_rows, dtype=owner.dtype, device=dev)))
+
+    def owner_of(self, x: torch.Tensor) -> torch.Tensor:
+        """Rank that processes each sample of x [n,3]."""
+        cell = torch.floor(x[:, self.axis] / self.resolution).to(torch.int64)
+        return torch.searchsorted(self.boundaries, cell, right=True)
+
+    def gather_features(self, features: torch.Tensor, rank: int, group=None) -> None:
+        """Re-replicate the feature table after training: every row is taken from its owner."""
+        if world()[1] == 1:
+            return
+        mine = (self.row_owner == rank).unsqueeze(1)
+        contrib = torch.where(mine, features, torch.zeros_like(features))
+        dist.all_reduce(contrib, op=dist.ReduceOp.SUM, group=group)
+        features.copy_(contrib)

@@ -88,10 +88,10 @@ class FusedTrainer:
         self.launches = 0           # kernels of libclid_sdf.so launched so far
 
     # ------------------------------------------------------------------
-    def _shifted(self, x: torch.Tensor) -> torch.Tensor:
+    def _shifted(self, x: torch.Tensor, eik_index: Optional[torch.Tensor] = None) -> torch.Tensor:
         """The six central-difference copies of the decimated batch (mapper.py:985-1003)."""
         eps = self.cfg.voxel_size_m * self.cfg.num_grad_step_ratio
-        xd = x[:: self.cfg.gradient_decimation]
+        xd = x[:: self.cfg.gradient_decimation] if eik_index is None else x[eik_index]
         out = xd.repeat(6, 1)
         nd = xd.shape[0]
         for axis in range(3):
@@ -100,7 +100,8 @@ class FusedTrainer:
         return out
 
     def iteration(self, x: torch.Tensor, label: torch.Tensor, ts: Optional[torch.Tensor], weight: torch.Tensor,
-                  apply_step: bool = True, n_global: int = 0, nd_global: int = 0, sync: bool = False):
+                  apply_step: bool = True, n_global: int = 0, nd_global: int = 0, sync: bool = False,
+                  shards=None, eik_index: Optional[torch.Tensor] = None):
         """One mapping iteration on the batch.  With apply_step=False the optimiser step is left to
         a later `adam_step()` call, so the accumulated gradients can be inspected (tests).
 
@@ -115,7 +116,7 @@ class FusedTrainer:
         nd = 0
         x_all, ts_all = x, ts
         if self.numerical and self.weight_e > 0:
-            shifted = self._shifted(x)
+            shifted = self._shifted(x, eik_index)
             nd = shifted.shape[0] // 6
             x_all = torch.cat((x, shifted), 0)
             if ts is not None:  # INT32_MIN makes the ts_update amax a no-op for the shifted copies
@@ -175,9 +176,12 @@ class FusedTrainer:
                 bv1.record()
                 self.backward_events.append((bv0, bv1))
 
-        if sync:
-            # one flat all-reduce for [decoder grads | loss scalars]; the replicated feature table
-            # needs its gradient (and which rows were touched) summed as well
+        if shards is not None:
+            # spatial sharding: ONE flat all-reduce of [decoder grads | loss | shared-row gradients]
+            self.sync_spatial(loss, shards)
+        elif sync:
+            # replicated sharding: flat all-reduce for [decoder grads | loss scalars]; the replicated
+            # feature table needs its whole gradient (and which rows were touched) summed as well
             from .. import dist as _dist
 
             _dist.FlatAllReduce([self.dec_grad, loss])()
@@ -188,6 +192,38 @@ class FusedTrainer:
         if apply_step:
             self.adam_step()
         return loss
+
+    def pack_spatial(self, loss: torch.Tensor, shards) -> torch.Tensor:
+        """[decoder grads | loss | gradients of the shared feature rows] as one flat buffer."""
+        parts = []
+        if self.dec_grad is not None:
+            parts.append(self.dec_grad)
+        parts.append(loss)
+        if self.train_features:
+            parts.append(self.feat_grad[shards.shared_rows].reshape(-1))
+            if self.touched is not None and not getattr(self, "_shared_marked", False):
+                # shared rows step on every rank with identical state; untouched ones are no-ops
+                self.touched[shards.shared_rows] = 1
+                self._shared_marked = True
+        return torch.cat(parts)
+
+    def unpack_spatial(self, flat: torch.Tensor, loss: torch.Tensor, shards) -> None:
+        off = 0
+        if self.dec_grad is not None:
+            self.dec_grad.copy_(flat[: self.dec_grad.numel()])
+            off = self.dec_grad.numel()
+        loss.copy_(flat[off:off + 3])
+        off += 3
+        if self.train_features:
+            self.feat_grad[shards.shared_rows] = flat[off:].view(-1, self.feat_grad.shape[1])
+
+    def sync_spatial(self, loss: torch.Tensor, shards) -> None:
+        import torch.distributed as tdist
+
+        flat = self.pack_spatial(loss, shards)
+        if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
+            tdist.all_reduce(flat, op=tdist.ReduceOp.SUM)
+        self.unpack_spatial(flat, loss, shards)
 
     def adam_step(self) -> None:
         cfg, npm, lib, dev = self.cfg, self.npm, self.lib, self.device
