@@ -154,7 +154,19 @@ def run_native(args):
     torch.cuda.set_device(local_rank)
     device = f"cuda:{local_rank}"
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(device))
+        # library banners (e.g. "NCCL version ...") must not land on stdout: rank 0 prints ONE json line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(device))
+            warm = torch.zeros(1, device=device)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     if rank == 0:
         _build.build()
     if world > 1:

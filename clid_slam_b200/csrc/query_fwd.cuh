@@ -105,14 +105,21 @@ __device__ __forceinline__ int search_hashed(const ClidMap& m, const int64_t* __
 }
 
 // ---- candidate enumeration through the brick index ---------------------------------------
-// Payload of the top-K: record index.  Phase 1 (warp-converged) loads the <= 8 brick headers
-// and compacts the non-empty (want, occupancy, base) triples into this thread's column of
-// shared memory.  Phase 2 walks them with one candidate per lane per iteration, so a warp
-// iterates max-over-lanes(candidates) times instead of diverging inside nested loops.
+// Payload of the top-K: record index.  A 64-cell brick is walked as two 32-cell halves (z < 2,
+// z >= 2) so every bit operation is a single 32-bit instruction.
+// Phase 1 (warp-converged): load the <= 8 brick headers, AND with the stencil, compact the
+// non-empty (want, occupancy, first-record) half-brick triples into this thread's column of shared
+// memory and prefetch the 128-byte record lines they span towards L2.
+// Phase 2: every lane pops up to kWalkBatch candidates, issues their record loads together, then
+// ranks them; a warp iterates ceil(max-over-lanes(candidates) / kWalkBatch) times with all lanes
+// converged instead of diverging inside nested loops.
+constexpr int kHalfSlots = 2 * kBrickSlots;
+constexpr int kWalkBatch = 4;
+
 struct BrickScratch {
-  uint64_t want[kBrickSlots][kQueryThreads];
-  uint64_t occ[kBrickSlots][kQueryThreads];
-  int base[kBrickSlots][kQueryThreads];
+  uint32_t want[kHalfSlots][kQueryThreads];
+  uint32_t occ[kHalfSlots][kQueryThreads];
+  int base[kHalfSlots][kQueryThreads];
 };
 
 template <int K>
@@ -127,7 +134,7 @@ __device__ __forceinline__ int search_bricks(const ClidMap& m, const ClidBricks&
   const int bx0 = rx >> 2, by0 = ry >> 2, bz0 = rz >> 2;  // arithmetic shifts: floor for negatives
   const int span = b.span;
   const int nslots = span * span * span;
-  const uint64_t* st = stencil + (((rz & 3) * 4 + (ry & 3)) * 4 + (rx & 3)) * nslots;
+  const uint2* st = reinterpret_cast<const uint2*>(stencil) + (((rz & 3) * 4 + (ry & 3)) * 4 + (rx & 3)) * nslots;
   const uint4* headers = reinterpret_cast<const uint4*>(b.headers);
   const float4* records = reinterpret_cast<const float4*>(b.records);
 
@@ -141,39 +148,55 @@ __device__ __forceinline__ int search_bricks(const ClidMap& m, const ClidBricks&
                       (unsigned)bz < (unsigned)b.dims[2];
       uint4 h = make_uint4(0, 0, 0, 0);
       if (in) h = __ldg(headers + ((int64_t)bz * b.dims[1] + by) * b.dims[0] + bx);
-      const uint64_t occ = ((uint64_t)h.y << 32) | h.x;
-      const uint64_t want = occ & st[s];
-      if (want) {
-        sc.want[nfill][tid] = want;
-        sc.occ[nfill][tid] = occ;
-        sc.base[nfill][tid] = (int)h.z;
-        ++nfill;
-        // pull the 128-byte lines that hold this brick's wanted records towards L2 now, so the
-        // serial walk below finds them there instead of paying one DRAM round trip per step
-        const int first = (int)h.z + __popcll(occ & ((want & (0 - want)) - 1ull));
-        const int last = (int)h.z + __popcll(occ & ((1ull << (63 - __clzll((long long)want))) - 1ull));
-        for (int line = first >> 3; line <= (last >> 3); ++line) prefetch_l2(records + 8 * line);
+      const uint2 sten = st[s];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t occ = half ? h.y : h.x;
+        const uint32_t want = occ & (half ? sten.y : sten.x);
+        if (want) {
+          const int base = (int)h.z + (half ? __popc(h.x) : 0);
+          sc.want[nfill][tid] = want;
+          sc.occ[nfill][tid] = occ;
+          sc.base[nfill][tid] = base;
+          ++nfill;
+          // first and last wanted record of this half: pull their 128-byte lines towards L2 now,
+          // so the serial walk below does not pay a DRAM round trip per step
+          const int first = base + __popc(occ & ((want & (0u - want)) - 1u));
+          const int last = base + __popc(occ & ((0x80000000u >> __clz(want)) - 1u));
+          prefetch_l2(records + first);
+          if ((last >> 3) != (first >> 3)) prefetch_l2(records + last);
+        }
       }
     }
   }
 
   int count = 0, cur = 0;
-  uint64_t w = 0, occ = 0;
+  uint32_t w = 0, occ = 0;
   int base = 0;
   if (nfill > 0) { w = sc.want[0][tid]; occ = sc.occ[0][tid]; base = sc.base[0][tid]; }
   while (__any_sync(0xffffffffu, w != 0)) {
-    if (w) {
-      const int bit = __ffsll((long long)w) - 1;
-      w &= w - 1;
-      const int rec = base + __popcll(occ & ((1ull << bit) - 1ull));
-      const float4 r = __ldg(records + rec);
-      if (w == 0 && ++cur < nfill) { w = sc.want[cur][tid]; occ = sc.occ[cur][tid]; base = sc.base[cur][tid]; }
-      const float d2 = dist2_torch(r.x - px, r.y - py, r.z - pz);
-      if (!(d2 > m.max_valid_dist2)) {
+    int rec[kWalkBatch];
+#pragma unroll
+    for (int j = 0; j < kWalkBatch; ++j) {
+      rec[j] = -1;
+      if (w) {
+        const int bit = __ffs(w) - 1;
+        w &= w - 1;
+        rec[j] = base + __popc(occ & ((1u << bit) - 1u));
+        if (w == 0 && ++cur < nfill) { w = sc.want[cur][tid]; occ = sc.occ[cur][tid]; base = sc.base[cur][tid]; }
+      }
+    }
+    float4 r[kWalkBatch];
+#pragma unroll
+    for (int j = 0; j < kWalkBatch; ++j) r[j] = __ldg(records + (rec[j] < 0 ? 0 : rec[j]));
+#pragma unroll
+    for (int j = 0; j < kWalkBatch; ++j) {
+      const float d2 = dist2_torch(r[j].x - px, r[j].y - py, r[j].z - pz);
+      if (rec[j] >= 0 && !(d2 > m.max_valid_dist2)) {
         ++count;
         if (d2 < top.d[K - 1]) {
-          prefetch_l2(m.gather_features + (int64_t)__float_as_int(r.w) * kFeat);  // likely neighbour
-          top.insert(d2, rec);
+          prefetch_l2(m.gather_features + (int64_t)__float_as_int(r[j].w) * kFeat);  // likely neighbour
+          top.insert(d2, rec[j]);
         }
       }
     }
