@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libclid_sdf.so")
+LIB_PATH = os.environ.get("CLID_LIB_PATH", os.path.join(_PKG, "libclid_sdf.so"))  # override: kernel experiments
 
 MAX_LEVELS = 3
 MAX_KNN = 8
@@ -74,6 +74,15 @@ class ClidLossArgs(C.Structure):
     ]
 
 
+class ClidTrainFusedArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("ts", C.c_void_p), ("label", C.c_void_p), ("weight", C.c_void_p),
+        ("n", C.c_int64), ("n_norm", C.c_int64), ("weight_e", C.c_float), ("weighted", C.c_int32),
+        ("gfeat", C.c_void_p), ("touched", C.c_void_p), ("dec_grad", C.c_void_p), ("loss", C.c_void_p),
+        ("sdf_out", C.c_void_p),
+    ]
+
+
 MAX_DEC_TENSORS = 2 * MAX_LEVELS + 2
 
 
@@ -108,6 +117,8 @@ _SIGNATURES = [
     ("clid_train_backward", C.c_int,
      [C.POINTER(ClidMap), C.POINTER(ClidDecoder), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
       C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("clid_train_fused", C.c_int,
+     [C.POINTER(ClidMap), C.POINTER(ClidDecoder), C.POINTER(ClidTrainFusedArgs), C.c_uint32, C.c_void_p]),
     ("clid_adam_step", C.c_int, [C.POINTER(ClidAdamArgs), C.c_void_p]),
     ("clid_radius_search", C.c_int,
      [C.POINTER(ClidMap), C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),

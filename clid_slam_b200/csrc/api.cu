@@ -8,6 +8,7 @@
 #include "query_bwd.cuh"
 #include "query_fwd.cuh"
 #include "train.cuh"
+#include "train_fused.cuh"
 
 namespace clid {
 
@@ -191,6 +192,47 @@ static int launch_train_backward(const TrainBwdParams& p, cudaStream_t stream) {
   return CLID_OK;
 }
 
+template <int H, int K, bool kBricks>
+static int launch_train_fused(const TrainFusedParams& p, cudaStream_t stream) {
+  DeviceInfo info;
+  if (int rc = device_info(&info)) return rc;
+  constexpr int kWarps = kFusedThreads / 32;
+  constexpr int kSearchFloats = kBricks ? (2 * 64 * kBrickSlots + (int)(sizeof(BrickScratch) / sizeof(float)))
+                                        : 2 * CLID_MAX_KC;
+  size_t smem = (MlpLayout<H, 1>::kFloats + kSearchFloats + kWarps * 32 * kInPad + kWarps * 32 * (H / 32) +
+                 kWarps * H * kInPad) * sizeof(float);
+  auto kern = train_fused_l1_kernel<H, K, kBricks>;
+  static thread_local int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+    }
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kFusedThreads, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+  }
+  int64_t want = (p.n + kFusedThreads - 1) / kFusedThreads;
+  int64_t cap = (int64_t)info.sm_count * blocks_per_sm;
+  int grid = (int)(want < cap ? want : cap);
+  kern<<<grid, kFusedThreads, smem, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "train_fused_l1_kernel launch");
+  return CLID_OK;
+}
+
+static int dispatch_train_fused(const TrainFusedParams& p, cudaStream_t stream) {
+  const int H = p.dec.hidden_dim;
+  if (p.dec.levels != 1 || (H != 32 && H != 64 && H != 128))
+    return set_error(CLID_EUNSUPPORTED, "fused training is compiled for one hidden level with H in {32,64,128}; got %d x %d",
+                     H, p.dec.levels);
+  if (p.map.knn > 6) return set_error(CLID_EUNSUPPORTED, "fused training is compiled for query_nn_k <= 6");
+  const bool bricks = p.flags & CLID_USE_BRICKS;
+  if (H == 64) return bricks ? launch_train_fused<64, 6, true>(p, stream) : launch_train_fused<64, 6, false>(p, stream);
+  if (H == 32) return bricks ? launch_train_fused<32, 6, true>(p, stream) : launch_train_fused<32, 6, false>(p, stream);
+  return bricks ? launch_train_fused<128, 6, true>(p, stream) : launch_train_fused<128, 6, false>(p, stream);
+}
+
 static int dispatch_train_backward(const ClidMap* map, const ClidDecoder* dec, const float* x, const int32_t* knn_idx,
                                    const float* dlogit, const float* dgrad, int64_t n, int64_t n_r, uint32_t flags,
                                    float* gfeat, uint8_t* touched, float* dec_grad, cudaStream_t stream) {
@@ -296,6 +338,28 @@ int clid_train_backward(const ClidMap* map, const ClidDecoder* dec, const float*
   if (gfeat && !aligned16(gfeat)) return set_error(CLID_EINVAL, "gfeat must be 16-byte aligned");
   return dispatch_train_backward(map, dec, x, knn_idx, dlogit, dgrad, n, n_r, flags, gfeat, touched, dec_grad,
                                  static_cast<cudaStream_t>(stream));
+}
+
+int clid_train_fused(const ClidMap* map, const ClidDecoder* dec, const ClidTrainFusedArgs* a, uint32_t flags,
+                     clid_stream_t stream) {
+  if (!map || !dec || !a) return set_error(CLID_EINVAL, "map/dec/args is NULL");
+  if (a->n < 0) return set_error(CLID_EINVAL, "n = %lld", (long long)a->n);
+  if (a->n == 0) return CLID_OK;
+  if (!a->x || !a->label || !a->loss) return set_error(CLID_EINVAL, "x/label/loss is NULL");
+  flags |= CLID_TRAINING_MODE;
+  if (int rc = check_map(map, flags)) return rc;
+  if (int rc = check_decoder(dec)) return rc;
+  if (a->gfeat && !aligned16(a->gfeat)) return set_error(CLID_EINVAL, "gfeat must be 16-byte aligned");
+  if (!(dec->sdf_scale > 0.f)) return set_error(CLID_EINVAL, "sdf_scale must be positive");
+  TrainFusedParams p;
+  memset(&p, 0, sizeof(p));
+  p.map = *map; p.dec = *dec;
+  if (flags & CLID_USE_BRICKS) p.bricks = *map->bricks;
+  p.x = a->x; p.ts = a->ts; p.label = a->label; p.weight = a->weight;
+  p.gfeat = a->gfeat; p.touched = a->touched; p.dec_grad = a->dec_grad; p.loss = a->loss; p.sdf_out = a->sdf_out;
+  p.n = a->n; p.n_norm = a->n_norm > 0 ? a->n_norm : a->n;
+  p.weight_e = a->weight_e; p.weighted = a->weighted; p.flags = flags;
+  return dispatch_train_fused(p, static_cast<cudaStream_t>(stream));
 }
 
 int clid_adam_step(const ClidAdamArgs* a, clid_stream_t stream) {

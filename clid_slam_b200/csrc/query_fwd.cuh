@@ -10,6 +10,9 @@
 
 namespace clid {
 
+#ifndef CLID_QUERY_MIN_BLOCKS
+#define CLID_QUERY_MIN_BLOCKS 4  // resident CTAs per SM the forward kernel is register-budgeted for
+#endif
 constexpr int kQueryThreads = 128;
 constexpr int kBrickSlots = 8;  // span 2: a neighbourhood touches at most 2x2x2 bricks
 
@@ -205,7 +208,7 @@ __device__ __forceinline__ int search_bricks(const ClidMap& m, const ClidBricks&
 }
 
 template <int H, int L, int K, bool kBricks>
-__global__ void __launch_bounds__(kQueryThreads, 4) query_forward_kernel(const __grid_constant__ QueryParams p) {
+__global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_forward_kernel(const __grid_constant__ QueryParams p) {
   extern __shared__ __align__(16) float smem[];
   float* sm_dec = smem;
   constexpr int kDecFloats = H > 0 ? MlpLayout<(H > 0 ? H : 4), (H > 0 ? L : 1)>::kFloats : 0;

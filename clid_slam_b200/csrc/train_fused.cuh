@@ -1,0 +1,358 @@
+// One-kernel mapping iteration for the analytic-gradient mode (utils/mapper.py:642-835 with
+// numerical_grad_on: False): per sample, in one thread and without leaving registers,
+//   kNN search -> IDW blend -> decoder -> d sdf/dx            (as query_forward_kernel)
+//   bce + eikonal loss terms and their derivatives            (utils/loss.py:44-62, mapper.py:780-798)
+//   closed-form backward: feature-gradient scatter, decoder-gradient fold
+// Every quantity the backward needs (neighbour rows, weights, activation pattern, a = d out/d z)
+// is still live when the loss derivative is known, because in analytic mode d L / d logit and
+// d L / d grad of a sample depend on that sample alone.  Replaces three launches
+// (clid_query_forward + clid_sdf_loss + clid_train_backward) and the re-gather / MLP
+// re-evaluation of the split backward.
+#pragma once
+#include "common.cuh"
+#include "query_bwd.cuh"
+#include "query_fwd.cuh"
+#include "train.cuh"
+
+namespace clid {
+
+struct TrainFusedParams {
+  ClidMap map;
+  ClidDecoder dec;
+  ClidBricks bricks;
+  const float* x;        // [n,3]
+  const int32_t* ts;     // [n] or NULL
+  const float* label;    // [n]
+  const float* weight;   // [n] or NULL
+  float* gfeat;          // [n_gather+1,8] += or NULL
+  uint8_t* touched;      // [n_gather+1] or NULL
+  float* dec_grad;       // flat [W0,b0,wout,bout] += or NULL (frozen decoder)
+  float* loss;           // [3] += total, bce, eikonal
+  float* sdf_out;        // [n] or NULL (diagnostics)
+  int64_t n;
+  int64_t n_norm;        // mean denominator (global batch size when sharded)
+  float weight_e;
+  int weighted;
+  uint32_t flags;
+};
+
+constexpr int kFusedThreads = 128;
+
+template <int H, int K, bool kBricks>
+__global__ void __launch_bounds__(kFusedThreads, 3) train_fused_l1_kernel(const __grid_constant__ TrainFusedParams p) {
+  using Lay = MlpLayout<H, 1>;
+  constexpr int kRows = H / 32;
+  constexpr int kMaskWords = H / 32;
+  constexpr int kWarps = kFusedThreads / 32;
+  static_assert(kFusedThreads == kQueryThreads, "BrickScratch is sized for kQueryThreads");
+  extern __shared__ __align__(16) float smem[];
+  float* sm_dec = smem;
+  // search scratch (hash residues or stencil + brick cursor columns), then the fold staging
+  constexpr int kSearchFloats = kBricks ? (2 * 64 * kBrickSlots + (int)(sizeof(BrickScratch) / sizeof(float)))
+                                        : 2 * CLID_MAX_KC;
+  int64_t* cell_mod = reinterpret_cast<int64_t*>(smem + Lay::kFloats);
+  uint64_t* stencil = reinterpret_cast<uint64_t*>(smem + Lay::kFloats);
+  BrickScratch& scratch = *reinterpret_cast<BrickScratch*>(smem + Lay::kFloats + 2 * 64 * kBrickSlots);
+  float* sm_c = smem + Lay::kFloats + kSearchFloats;                            // [warps][32][12]
+  uint32_t* sm_m = reinterpret_cast<uint32_t*>(sm_c + kWarps * 32 * kInPad);     // [warps][32][words]
+  float* sm_red = reinterpret_cast<float*>(sm_m + kWarps * 32 * kMaskWords);     // [warps][H][12] epilogue
+  __shared__ float sm_scalar[3][kWarps];
+
+  const ClidMap& m = p.map;
+  stage_decoder<H, 1>(sm_dec, p.dec);
+  if constexpr (kBricks) {
+    const int n_st = 64 * p.bricks.span * p.bricks.span * p.bricks.span;
+    for (int i = threadIdx.x; i < n_st; i += blockDim.x) stencil[i] = p.bricks.stencil[i];
+  } else {
+    for (int c = threadIdx.x; c < m.kc; c += blockDim.x) {
+      int64_t h = m.neighbor_dx[3 * c] * m.primes[0] + m.neighbor_dx[3 * c + 1] * m.primes[1] +
+                  m.neighbor_dx[3 * c + 2] * m.primes[2];
+      cell_mod[c] = floor_mod(h, m.buffer_size);
+    }
+  }
+  __syncthreads();
+
+  const bool local = p.flags & CLID_QUERY_LOCALLY;
+  const bool time_filter = p.flags & CLID_TIME_FILTER;
+  const bool layer_norm = p.flags & CLID_LAYER_NORM;
+  const float slope = (p.flags & CLID_LEAKY_RELU) ? kLeakySlope : 0.f;
+  const float s = p.dec.sdf_scale;
+  const float inv_n = 1.0f / (float)p.n_norm;
+  const int knn = m.knn;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* my_c = sm_c + (warp * 32) * kInPad;
+  uint32_t* my_m = sm_m + (warp * 32) * kMaskWords;
+  const float4* w0 = reinterpret_cast<const float4*>(sm_dec + Lay::kW0);
+
+  float Gd[kRows][kInPad];
+#pragma unroll
+  for (int r = 0; r < kRows; ++r)
+#pragma unroll
+    for (int i = 0; i < kInPad; ++i) Gd[r][i] = 0.f;
+  float delta_sum = 0.f, bce_sum = 0.f, eik_sum = 0.f;
+
+  for (int64_t q0 = (int64_t)blockIdx.x * blockDim.x; q0 < p.n; q0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = q0 + threadIdx.x;
+    const bool live = q < p.n;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (live) { px = p.x[3 * q]; py = p.x[3 * q + 1]; pz = p.x[3 * q + 2]; }
+    TopK<K> top;
+    top.init();
+    int count = 0;
+    if constexpr (kBricks) count = search_bricks<K>(m, p.bricks, stencil, scratch, live, px, py, pz, top);
+    else if (live) count = search_hashed<K>(m, cell_mod, px, py, pz, local, time_filter, top);
+
+    float c[kInPad];
+#pragma unroll
+    for (int i = 0; i < kInPad; ++i) c[i] = 0.f;
+    uint32_t mask[kMaskWords];
+#pragma unroll
+    for (int w = 0; w < kMaskWords; ++w) mask[w] = 0u;
+
+    if (live) {
+      // ---- neighbour rows, offsets, inverse-distance weights
+      int row[K];
+      float vx[K], vy[K], vz[K], w[K], u[K];
+      float S = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const bool valid = k < knn && top.id[k] >= 0;
+        row[k] = -1;
+        vx[k] = vy[k] = vz[k] = 0.f;
+        u[k] = 0.f;
+        if (valid) {
+          float qx, qy, qz;
+          if constexpr (kBricks) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(p.bricks.records) + top.id[k]);
+            qx = r.x; qy = r.y; qz = r.z;
+            row[k] = __float_as_int(r.w);
+          } else {
+            row[k] = top.id[k];
+            const float* g = m.gather_points + 3 * (int64_t)row[k];
+            qx = __ldg(g); qy = __ldg(g + 1); qz = __ldg(g + 2);
+          }
+          vx[k] = px - qx; vy[k] = py - qy; vz[k] = pz - qz;
+          u[k] = 1.0f / (top.d[k] + kIdwEps);
+          S += u[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k) w[k] = row[k] >= 0 ? u[k] / S : 0.f;
+
+      // ---- blend
+      float z[kIn];
+#pragma unroll
+      for (int i = 0; i < kIn; ++i) z[i] = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (row[k] >= 0) {
+          float f[kFeat];
+          load_feature_row(m.gather_features, row[k], f);
+          if (layer_norm) { float mu, rs; layer_norm8(f, mu, rs); }
+#pragma unroll
+          for (int i = 0; i < kFeat; ++i) z[i] = fmaf(w[k], f[i], z[i]);
+          z[8] = fmaf(w[k], vx[k], z[8]); z[9] = fmaf(w[k], vy[k], z[9]); z[10] = fmaf(w[k], vz[k], z[10]);
+        }
+      }
+
+      // ---- side effects (neural_points.py:708-733)
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (row[k] >= 0) {
+          atomicAdd(m.certainty_accum + row[k], w[k]);
+          if (p.ts && m.gather_ts_update) atomicMax(m.gather_ts_update + row[k], p.ts[q]);
+        }
+      }
+
+      // ---- decoder: logit, activation pattern, a = d logit / d z
+      float out = sm_dec[Lay::kBout];
+      float a[kIn];
+#pragma unroll
+      for (int i = 0; i < kIn; ++i) a[i] = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < H; ++j) {
+        const float4 r0 = w0[j * 3 + 0], r1 = w0[j * 3 + 1], r2 = w0[j * 3 + 2];
+        float pre = sm_dec[Lay::kB0 + j];
+        pre = fmaf(r0.x, z[0], pre); pre = fmaf(r0.y, z[1], pre); pre = fmaf(r0.z, z[2], pre); pre = fmaf(r0.w, z[3], pre);
+        pre = fmaf(r1.x, z[4], pre); pre = fmaf(r1.y, z[5], pre); pre = fmaf(r1.z, z[6], pre); pre = fmaf(r1.w, z[7], pre);
+        pre = fmaf(r2.x, z[8], pre); pre = fmaf(r2.y, z[9], pre); pre = fmaf(r2.z, z[10], pre);
+        const bool on = pre > 0.f;
+        if (on) mask[j >> 5] |= 1u << (j & 31);
+        const float cj = sm_dec[Lay::kWout + j] * (on ? 1.f : slope);
+        out = fmaf(cj, pre, out);
+        a[0] = fmaf(cj, r0.x, a[0]); a[1] = fmaf(cj, r0.y, a[1]); a[2] = fmaf(cj, r0.z, a[2]); a[3] = fmaf(cj, r0.w, a[3]);
+        a[4] = fmaf(cj, r1.x, a[4]); a[5] = fmaf(cj, r1.y, a[5]); a[6] = fmaf(cj, r1.z, a[6]); a[7] = fmaf(cj, r1.w, a[7]);
+        a[8] = fmaf(cj, r2.x, a[8]); a[9] = fmaf(cj, r2.y, a[9]); a[10] = fmaf(cj, r2.z, a[10]);
+      }
+      const float sdf = out * s;
+      if (p.sdf_out) p.sdf_out[q] = sdf;
+
+      // ---- features once more (L1/L2 resident), kept for both passes over the neighbours
+      float f[K][kFeat];
+      float rstd[K];
+      float ck[K], cbar = 0.f;
+#pragma unroll
+      for (int i = 0; i < kIn; ++i) cbar = fmaf(z[i], a[i], cbar);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        rstd[k] = 1.f;
+        ck[k] = 0.f;
+        if (row[k] >= 0) {
+          load_feature_row(m.gather_features, row[k], f[k]);
+          if (layer_norm) { float mu; layer_norm8(f[k], mu, rstd[k]); }
+          float v = a[8] * vx[k] + a[9] * vy[k] + a[10] * vz[k];
+#pragma unroll
+          for (int i = 0; i < kFeat; ++i) v = fmaf(f[k][i], a[i], v);
+          ck[k] = v;
+        }
+      }
+
+      // ---- d sdf / d x (closed form) and the loss terms of this sample
+      float gx = 0.f, gy = 0.f, gz = 0.f;
+      const float invS = count > 0 ? 1.0f / S : 0.f;
+      if (count > 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (row[k] >= 0) {
+            const float coef = (ck[k] - cbar) * (-2.f * u[k] * u[k]) * invS;
+            gx = fmaf(coef, vx[k], gx); gy = fmaf(coef, vy[k], gy); gz = fmaf(coef, vz[k], gz);
+          }
+        }
+        gx += a[8]; gy += a[9]; gz += a[10];
+      }
+      gx *= s; gy *= s; gz *= s;
+
+      const float l = sdf / s;  // BCEWithLogits(pred / sigma, sigmoid(label / sigma))
+      const float t = 1.0f / (1.0f + expf(-(p.label[q] / s)));
+      const float wgt = (p.weighted && p.weight) ? fabsf(p.weight[q]) : 1.0f;
+      bce_sum += wgt * ((1.0f - t) * l + fmaxf(-l, 0.f) + log1pf(expf(-fabsf(l))));
+      const float delta = wgt * (1.0f / (1.0f + expf(-l)) - t) * inv_n;
+      float rx = 0.f, ry = 0.f, rz = 0.f;
+      if (p.weight_e > 0.f) {
+        const float gn = sqrtf(gx * gx + gy * gy + gz * gz);
+        const float dev = gn - 1.0f;
+        eik_sum += dev * dev;
+        const float kk = gn > 0.f ? p.weight_e * 2.0f * dev * inv_n / gn : 0.f;
+        rx = kk * gx; ry = kk * gy; rz = kk * gz;
+      }
+
+      // ---- tangent input tau0 = s J r, with e_k = d w_k / d x . r
+      float e[K], dusum = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        e[k] = row[k] >= 0 ? -2.f * u[k] * u[k] * (vx[k] * rx + vy[k] * ry + vz[k] * rz) : 0.f;
+        dusum += e[k];
+      }
+      float tau[kIn];
+#pragma unroll
+      for (int i = 0; i < kIn; ++i) tau[i] = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (row[k] >= 0) {
+          e[k] = (e[k] - w[k] * dusum) * invS;
+#pragma unroll
+          for (int i = 0; i < kFeat; ++i) tau[i] = fmaf(e[k], f[k][i], tau[i]);
+          tau[8] = fmaf(e[k], vx[k], tau[8]); tau[9] = fmaf(e[k], vy[k], tau[9]); tau[10] = fmaf(e[k], vz[k], tau[10]);
+        } else {
+          e[k] = 0.f;
+        }
+      }
+      if (count > 0) { tau[8] += rx; tau[9] += ry; tau[10] += rz; }
+#pragma unroll
+      for (int i = 0; i < kIn; ++i) c[i] = fmaf(delta, z[i], s * tau[i]);
+      c[kIn] = delta;
+      delta_sum += delta;
+
+      // ---- neural-point feature gradients
+      if (p.gfeat) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (row[k] >= 0) {
+            const float coef = fmaf(s, e[k], delta * w[k]);
+            float tt[kFeat];
+#pragma unroll
+            for (int i = 0; i < kFeat; ++i) tt[i] = coef * a[i];
+            if (layer_norm) layer_norm8_vjp(f[k], rstd[k], tt);
+            red_add_row(p.gfeat, row[k], tt);
+            if (p.touched) p.touched[row[k]] = 1;
+          }
+        }
+      }
+    }
+
+    // ---- decoder-gradient fold (see train_backward_l1_kernel)
+    if (p.dec_grad) {
+      float4* dst = reinterpret_cast<float4*>(my_c + lane * kInPad);
+      dst[0] = make_float4(c[0], c[1], c[2], c[3]);
+      dst[1] = make_float4(c[4], c[5], c[6], c[7]);
+      dst[2] = make_float4(c[8], c[9], c[10], c[11]);
+#pragma unroll
+      for (int w = 0; w < kMaskWords; ++w) my_m[lane * kMaskWords + w] = mask[w];
+      __syncwarp();
+#pragma unroll 4
+      for (int nn = 0; nn < 32; ++nn) {
+        const float4* src = reinterpret_cast<const float4*>(my_c + nn * kInPad);
+        const float4 c0 = src[0], c1 = src[1], c2 = src[2];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          const float d = ((my_m[nn * kMaskWords + r] >> lane) & 1u) ? 1.f : slope;
+          Gd[r][0] = fmaf(d, c0.x, Gd[r][0]); Gd[r][1] = fmaf(d, c0.y, Gd[r][1]);
+          Gd[r][2] = fmaf(d, c0.z, Gd[r][2]); Gd[r][3] = fmaf(d, c0.w, Gd[r][3]);
+          Gd[r][4] = fmaf(d, c1.x, Gd[r][4]); Gd[r][5] = fmaf(d, c1.y, Gd[r][5]);
+          Gd[r][6] = fmaf(d, c1.z, Gd[r][6]); Gd[r][7] = fmaf(d, c1.w, Gd[r][7]);
+          Gd[r][8] = fmaf(d, c2.x, Gd[r][8]); Gd[r][9] = fmaf(d, c2.y, Gd[r][9]);
+          Gd[r][10] = fmaf(d, c2.z, Gd[r][10]); Gd[r][11] = fmaf(d, c2.w, Gd[r][11]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- block epilogue: loss scalars, then decoder gradients
+  bce_sum = warp_sum(bce_sum);
+  eik_sum = warp_sum(eik_sum);
+  delta_sum = warp_sum(delta_sum);
+  if (lane == 0) { sm_scalar[0][warp] = bce_sum; sm_scalar[1][warp] = eik_sum; sm_scalar[2][warp] = delta_sum; }
+  if (p.dec_grad) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+#pragma unroll
+      for (int i = 0; i < kInPad; ++i) sm_red[(warp * H + lane + 32 * r) * kInPad + i] = Gd[r][i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = 0.f, e = 0.f, d = 0.f;
+    for (int w = 0; w < kWarps; ++w) { b += sm_scalar[0][w]; e += sm_scalar[1][w]; d += sm_scalar[2][w]; }
+    const float bce = b * inv_n;
+    const float eik = p.weight_e > 0.f ? e * inv_n : 0.f;
+    atomicAdd(p.loss + 1, bce);
+    atomicAdd(p.loss + 2, eik);
+    atomicAdd(p.loss + 0, bce + p.weight_e * eik);
+    if (p.dec_grad && p.dec.out_bias) atomicAdd(p.dec_grad + H * kIn + 2 * H, d);
+  }
+  if (!p.dec_grad) return;
+  float* gW0 = p.dec_grad;
+  float* gb0 = gW0 + H * kIn;
+  float* gwout = gb0 + H;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    float g[kInPad];
+#pragma unroll
+    for (int i = 0; i < kInPad; ++i) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) v += sm_red[(w * H + j) * kInPad + i];
+      g[i] = v;
+    }
+    const float wout = sm_dec[Lay::kWout + j];
+    float dw = sm_dec[Lay::kB0 + j] * g[kIn];
+#pragma unroll
+    for (int i = 0; i < kIn; ++i) {
+      atomicAdd(gW0 + j * kIn + i, wout * g[i]);
+      dw = fmaf(sm_dec[Lay::kW0 + j * kInPad + i], g[i], dw);
+    }
+    if (p.dec.bias[0]) atomicAdd(gb0 + j, wout * g[kIn]);
+    atomicAdd(gwout + j, dw);
+  }
+}
+
+}  // namespace clid

@@ -13,6 +13,7 @@ One `FusedTrainer` lives for one `mapping()` call, exactly like the reference's 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional
 
 import torch
@@ -86,6 +87,9 @@ class FusedTrainer:
         self.forward_events = None  # bench hook: list that receives (start, end) CUDA events of the forward
         self.backward_events = None
         self.launches = 0           # kernels of libclid_sdf.so launched so far
+        # analytic (or no) eikonal: forward + loss + backward run as ONE kernel (clid_train_fused);
+        # set False to use the three-launch path (always used by the numerical-gradient mode)
+        self.single_kernel = True
 
     # ------------------------------------------------------------------
     def _shifted(self, x: torch.Tensor, eik_index: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -111,8 +115,11 @@ class FusedTrainer:
         cfg, npm, dec, lib, dev = self.cfg, self.npm, self.dec, self.lib, self.device
         x = _q._prep_points(x, "coord")
         n = x.shape[0]
-        if n == 0 and not sync:
+        if n == 0 and not sync and shards is None:
             return
+        if self.single_kernel and not (self.numerical and self.weight_e > 0):
+            loss = self._iteration_single_kernel(x, label, ts, weight, n_global)
+            return self._finish_iteration(loss, apply_step, sync, shards)
         nd = 0
         x_all, ts_all = x, ts
         if self.numerical and self.weight_e > 0:
@@ -176,6 +183,49 @@ class FusedTrainer:
                 bv1.record()
                 self.backward_events.append((bv0, bv1))
 
+        return self._finish_iteration(loss, apply_step, sync, shards)
+
+    def _iteration_single_kernel(self, x, label, ts, weight, n_global):
+        """clid_train_fused: forward + loss + backward of the analytic mode in one launch."""
+        npm, dec, lib, dev = self.npm, self.dec, self.lib, self.device
+        n = x.shape[0]
+        loss = torch.zeros(3, dtype=torch.float32, device=dev)
+        label_f = label.contiguous().float()
+        w = weight.contiguous().float() if weight is not None else None
+        tsd = _q._prep_ts(ts, n)
+        m, flags = _q.map_struct(npm, True, npm.local_point_certainties)
+        bricks = npm.brick_index(True) if os.environ.get("CLID_DISABLE_BRICKS", "0") != "1" else None
+        if bricks is not None:
+            m.bricks = C.pointer(bricks.struct)
+            flags |= _lib.USE_BRICKS
+        if dec.use_leaky_relu:
+            flags |= _lib.LEAKY_RELU
+        ds = dec.abi_struct()
+        a = _lib.ClidTrainFusedArgs()
+        a.x, a.ts = x.data_ptr(), (None if tsd is None else tsd.data_ptr())
+        a.label = _lib.ptr(label_f, torch.float32, "sdf_label")
+        a.weight = _lib.ptr(w, torch.float32, "weight")
+        a.n, a.n_norm = n, int(n_global)
+        a.weight_e = self.weight_e
+        a.weighted = int(bool(self.cfg.loss_weight_on))
+        a.gfeat = self.feat_grad.data_ptr() if self.train_features else None
+        a.touched = None if self.touched is None else self.touched.data_ptr()
+        a.dec_grad = None if self.dec_grad is None else self.dec_grad.data_ptr()
+        a.loss = loss.data_ptr()
+        if self.forward_events is not None:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        with torch.cuda.device(dev):
+            rc = lib.clid_train_fused(C.byref(m), C.byref(ds), C.byref(a), flags, _lib.current_stream(dev))
+        _lib.check(rc, "clid_train_fused")
+        if self.forward_events is not None:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            self.forward_events.append((ev0, ev1))
+        self.launches += 1 if n > 0 else 0
+        return loss
+
+    def _finish_iteration(self, loss, apply_step, sync, shards):
         if shards is not None:
             # spatial sharding: ONE flat all-reduce of [decoder grads | loss | shared-row gradients]
             self.sync_spatial(loss, shards)

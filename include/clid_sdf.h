@@ -212,6 +212,30 @@ CLID_API int clid_train_backward(const ClidMap* map, const ClidDecoder* dec, con
                                  int64_t n, int64_t n_r, uint32_t flags, float* gfeat,
                                  uint8_t* touched, float* dec_grad, clid_stream_t stream);
 
+/* One-kernel mapping iteration for the analytic-gradient mode (loss.numerical_grad_on: False):
+ * clid_query_forward (training mode) + clid_sdf_loss + clid_train_backward fused per sample, i.e.
+ * utils/mapper.py:660-835 from query_feature to cur_loss.backward() in a single launch.  Possible
+ * because with the analytic gradient d L / d logit and d L / d grad of a sample depend on that
+ * sample alone.  Same outputs and accumulation rules as the three calls; sdf_out [n] is optional.
+ * `map` needs everything clid_query_forward needs (CLID_USE_BRICKS honoured) plus certainty_accum. */
+typedef struct ClidTrainFusedArgs {
+  const float* x;        /* [n,3] */
+  const int32_t* ts;     /* [n] or NULL */
+  const float* label;    /* [n] */
+  const float* weight;   /* [n] or NULL */
+  int64_t n;
+  int64_t n_norm;        /* mean denominator; 0 = n */
+  float weight_e;        /* 0 disables the eikonal term */
+  int32_t weighted;      /* loss_weight_on */
+  float* gfeat;          /* [n_gather+1,F] += or NULL */
+  uint8_t* touched;      /* [n_gather+1] or NULL */
+  float* dec_grad;       /* flat [W0,b0,wout,bout] += or NULL (frozen decoder) */
+  float* loss;           /* [3] += total, bce, eikonal */
+  float* sdf_out;        /* [n] or NULL */
+} ClidTrainFusedArgs;
+CLID_API int clid_train_fused(const ClidMap* map, const ClidDecoder* dec, const ClidTrainFusedArgs* args,
+                              uint32_t flags, clid_stream_t stream);
+
 /* torch.optim.Adam step (utils/tools.py:205-255: betas (0.9, 0.99), eps adam_eps) on the touched
  * neural-point feature rows and on the decoder tensors; applied gradients are re-zeroed.
  * Rows never touched since the optimiser was created have m = v = g = 0, for which dense Adam

@@ -45,3 +45,13 @@ for flush_l2 in (True, False):
     b_alg = 576 + 16 * nv
     print(f"flush_l2={flush_l2}: median {med*1e3:.1f} us  {args.n/med/1e3:.1f} M samples/s  mean nn {nv:.2f} "
           f"alg {b_alg:.0f} B/sample -> {args.n*b_alg/med/1e6:.1f} GB/s = {args.n*b_alg/med/1e6/6551.7*100:.1f}% of 6551.7")
+
+# back-to-back launches, no host sync in between (steady state of a mapping loop, map L2-resident)
+for reps in (20, 100):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fused.sdf_and_gradient(npm, dec, x, use_bricks=bool(args.bricks))
+    e1.record(); torch.cuda.synchronize()
+    print(f"back-to-back x{reps}: {e0.elapsed_time(e1)/reps*1e3:.1f} us per launch")

@@ -49,12 +49,16 @@ def _check_final_state(fx, npm, dec):
         gio.assert_close(a, b, 1e-3, 1e-5, "decoder after Adam", 2e-3)
 
 
+@pytest.mark.parametrize("single_kernel", [True, False], ids=["one-kernel", "three-kernels"])
 @pytest.mark.parametrize("name", L1_CASES)
-def test_fused_training_matches_reference(name):
+def test_fused_training_matches_reference(name, single_kernel):
     from clid_slam_b200.ops.train import FusedTrainer
 
     fx, m, cfg, npm, dec, frozen = _setup(name)
+    if single_kernel and cfg.numerical_grad and cfg.ekional_loss_on:
+        pytest.skip("the numerical-gradient mode always uses the three-launch path")
     trainer = FusedTrainer(cfg, npm, dec)
+    trainer.single_kernel = single_kernel
     for it in range(int(fx["n_iters"])):
         x, label, ts, weight = _batch(fx, it)
         loss = trainer.iteration(x, label, ts, weight, apply_step=False)
