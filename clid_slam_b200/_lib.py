@@ -47,6 +47,7 @@ class ClidMap(C.Structure):
         ("gather_points", C.c_void_p), ("gather_features", C.c_void_p), ("gather_certainties", C.c_void_p),
         ("certainty_accum", C.c_void_p), ("gather_ts_update", C.c_void_p), ("n_gather", C.c_int64),
         ("feature_dim", C.c_int32), ("knn", C.c_int32), ("bricks", C.POINTER(ClidBricks)),
+        ("work_counter", C.c_void_p),
     ]
 
 

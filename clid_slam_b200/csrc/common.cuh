@@ -31,6 +31,41 @@ __device__ __forceinline__ float dist2_torch(float dx, float dy, float dz) {
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// Work distribution of the thread-per-sample kernels: a tile is 32 consecutive samples, owned by
+// one warp.  With a counter, warps fetch tiles dynamically (an atomic per tile) so per-sample cost
+// differences and the 1.7-wave tail of a static grid-stride loop even out; the warp that draws the
+// last ticket (n_tiles + n_warps - 1) resets the counter for the next launch.  Without a counter
+// the tiles are dealt round-robin.
+struct TileScheduler {
+  int32_t* counter;
+  int64_t n_tiles;
+  int64_t next_static;
+  int64_t stride;
+  int lane;
+  __device__ __forceinline__ TileScheduler(int32_t* counter_, int64_t n) : counter(counter_) {
+    n_tiles = (n + 31) >> 5;
+    lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    next_static = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    stride = (int64_t)gridDim.x * warps_per_block;
+  }
+  // returns the tile index for this warp or -1 when the work is exhausted (warp-uniform)
+  __device__ __forceinline__ int64_t next() {
+    if (counter == nullptr) {
+      const int64_t t = next_static;
+      next_static += stride;
+      return t < n_tiles ? t : -1;
+    }
+    int t = 0;
+    if (lane == 0) {
+      t = atomicAdd(counter, 1);
+      if ((int64_t)t == n_tiles + stride - 1) atomicExch(counter, 0);  // last ticket of the launch
+    }
+    t = __shfl_sync(0xffffffffu, t, 0);
+    return t < n_tiles ? (int64_t)t : -1;
+  }
+};
+
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -68,6 +103,60 @@ __device__ __forceinline__ void stage_decoder(float* sm, const ClidDecoder& dec)
   if (threadIdx.x == 0) sm[Lay::kBout] = dec.out_bias ? dec.out_bias[0] : 0.f;
 }
 
+// One-hidden-level decoder with Blackwell's packed fp32 FMA (FFMA2, `fma.rn.f32x2`, sm_100+): the
+// 11-wide dot product and the 11-wide a += c_j W0[j] update are each 6 two-lane FMAs on register
+// pairs instead of 11 scalar ones, which halves the FMA-pipe instruction count of the decoder (the
+// largest block of issued instructions in the fused kernels).  Weights come from shared memory as
+// three broadcast LDS.128 per hidden unit.  Optionally records the activation pattern as bit
+// masks (unit j -> bit j % 32 of word j / 32) for the backward's decoder-gradient fold.
+template <int H, bool kMask>
+__device__ __forceinline__ void mlp_l1_ffma2(const float* __restrict__ sm, const float (&z)[kIn], float slope,
+                                             float& out, float (&a)[kIn], uint32_t* __restrict__ mask) {
+  using Lay = MlpLayout<H, 1>;
+  const float4* w0 = reinterpret_cast<const float4*>(sm + Lay::kW0);
+  float2 zp[6], ap[6];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) zp[i] = make_float2(z[2 * i], z[2 * i + 1]);
+  zp[5] = make_float2(z[10], 0.f);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) ap[i] = make_float2(0.f, 0.f);
+  out = sm[Lay::kBout];
+#pragma unroll
+  for (int jw = 0; jw < H / 32; ++jw) {
+    uint32_t bits = 0u;
+#pragma unroll 8
+    for (int jj = 0; jj < 32; ++jj) {
+      const int j = jw * 32 + jj;
+      const float4 r0 = w0[j * 3 + 0], r1 = w0[j * 3 + 1], r2 = w0[j * 3 + 2];
+      // two independent chains of three packed FMAs
+      float2 p0 = make_float2(sm[Lay::kB0 + j], 0.f);
+      float2 p1 = make_float2(0.f, 0.f);
+      p0 = __ffma2_rn(make_float2(r0.x, r0.y), zp[0], p0);
+      p1 = __ffma2_rn(make_float2(r0.z, r0.w), zp[1], p1);
+      p0 = __ffma2_rn(make_float2(r1.x, r1.y), zp[2], p0);
+      p1 = __ffma2_rn(make_float2(r1.z, r1.w), zp[3], p1);
+      p0 = __ffma2_rn(make_float2(r2.x, r2.y), zp[4], p0);
+      p1 = __ffma2_rn(make_float2(r2.z, r2.w), zp[5], p1);  // r2.w is the zero padding
+      const float pre = (p0.x + p0.y) + (p1.x + p1.y);
+      const bool on = pre > 0.f;
+      if (kMask) bits = (bits >> 1) | (on ? 0x80000000u : 0u);  // after 32 steps unit jj sits at bit jj
+      const float cj = sm[Lay::kWout + j] * (on ? 1.f : slope);
+      out = fmaf(cj, pre, out);
+      const float2 cc = make_float2(cj, cj);
+      ap[0] = __ffma2_rn(make_float2(r0.x, r0.y), cc, ap[0]);
+      ap[1] = __ffma2_rn(make_float2(r0.z, r0.w), cc, ap[1]);
+      ap[2] = __ffma2_rn(make_float2(r1.x, r1.y), cc, ap[2]);
+      ap[3] = __ffma2_rn(make_float2(r1.z, r1.w), cc, ap[3]);
+      ap[4] = __ffma2_rn(make_float2(r2.x, r2.y), cc, ap[4]);
+      ap[5] = __ffma2_rn(make_float2(r2.z, r2.w), cc, ap[5]);
+    }
+    if (kMask) mask[jw] = bits;
+  }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) { a[2 * i] = ap[i].x; a[2 * i + 1] = ap[i].y; }
+  a[10] = ap[5].x;
+}
+
 // Forward of the MLP plus a = d out / d z (back-propagated through the activation masks).
 // out is the un-scaled logit (Decoder.mlp); sdf = sdf_scale * out.
 template <int H, int L>
@@ -79,20 +168,7 @@ __device__ __forceinline__ void mlp_value_and_input_grad(const float* __restrict
 #pragma unroll
   for (int i = 0; i < kIn; ++i) a[i] = 0.f;
   if constexpr (L == 1) {
-#pragma unroll 8
-    for (int j = 0; j < H; ++j) {
-      float4 r0 = w0[j * 3 + 0], r1 = w0[j * 3 + 1], r2 = w0[j * 3 + 2];
-      float pre = sm[Lay::kB0 + j];
-      pre = fmaf(r0.x, z[0], pre); pre = fmaf(r0.y, z[1], pre); pre = fmaf(r0.z, z[2], pre); pre = fmaf(r0.w, z[3], pre);
-      pre = fmaf(r1.x, z[4], pre); pre = fmaf(r1.y, z[5], pre); pre = fmaf(r1.z, z[6], pre); pre = fmaf(r1.w, z[7], pre);
-      pre = fmaf(r2.x, z[8], pre); pre = fmaf(r2.y, z[9], pre); pre = fmaf(r2.z, z[10], pre);
-      float d = pre > 0.f ? 1.f : slope;
-      float c = sm[Lay::kWout + j] * d;
-      out = fmaf(c, pre, out);
-      a[0] = fmaf(c, r0.x, a[0]); a[1] = fmaf(c, r0.y, a[1]); a[2] = fmaf(c, r0.z, a[2]); a[3] = fmaf(c, r0.w, a[3]);
-      a[4] = fmaf(c, r1.x, a[4]); a[5] = fmaf(c, r1.y, a[5]); a[6] = fmaf(c, r1.z, a[6]); a[7] = fmaf(c, r1.w, a[7]);
-      a[8] = fmaf(c, r2.x, a[8]); a[9] = fmaf(c, r2.y, a[9]); a[10] = fmaf(c, r2.z, a[10]);
-    }
+    mlp_l1_ffma2<H, false>(sm, z, slope, out, a, nullptr);
   } else {
     // level 0
     float h[H], dact[H];
@@ -153,6 +229,49 @@ __device__ __forceinline__ void load_feature_row(const float* __restrict__ feats
   float4 a = __ldg(row), b = __ldg(row + 1);
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
+
+// Second moments of a query's neighbourhood.  With t_k = -2 u_k^2 (d u_k / d x = t_k v_k):
+//   M_j = sum_k t_k v_kj f_k   (3 x 8),   P_jl = sum_k t_k v_kj v_kl   (symmetric 3 x 3),   qv_j = sum_k t_k v_kj
+// The spatial gradient and the tangent input of the analytic eikonal term are linear in them:
+//   sum_k c_k d w_k/d x = (1/S) (a_f . M_j + a_p . P_j - cbar qv_j)_j,   c_k = [f_k; v_k] . a,  cbar = z . a
+// so they are accumulated while the feature rows pass through registers for the blend, and no
+// row has to be read a second time (the gathers are L1-wavefront bound).
+struct Moments {
+  float M[3][kFeat];
+  float P[6];  // xx xy xz yy yz zz
+  float qv[3];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      qv[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < kFeat; ++i) M[j][i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) P[i] = 0.f;
+  }
+  __device__ __forceinline__ void add(const float (&f)[kFeat], float u, float vx, float vy, float vz) {
+    const float t2 = -2.f * u * u;
+    const float tx = t2 * vx, ty = t2 * vy, tz = t2 * vz;
+#pragma unroll
+    for (int i = 0; i < kFeat; ++i) {
+      M[0][i] = fmaf(tx, f[i], M[0][i]); M[1][i] = fmaf(ty, f[i], M[1][i]); M[2][i] = fmaf(tz, f[i], M[2][i]);
+    }
+    P[0] = fmaf(tx, vx, P[0]); P[1] = fmaf(tx, vy, P[1]); P[2] = fmaf(tx, vz, P[2]);
+    P[3] = fmaf(ty, vy, P[3]); P[4] = fmaf(ty, vz, P[4]); P[5] = fmaf(tz, vz, P[5]);
+    qv[0] += tx; qv[1] += ty; qv[2] += tz;
+  }
+  // (1/S) sum_k (c_k - cbar) d u_k/d x + a_p  (un-scaled d logit / d x for a query with neighbours)
+  __device__ __forceinline__ void logit_gradient(const float (&a)[kIn], float cbar, float invS, float& gx, float& gy,
+                                                 float& gz) const {
+    float sx = a[8] * P[0] + a[9] * P[1] + a[10] * P[2] - cbar * qv[0];
+    float sy = a[8] * P[1] + a[9] * P[3] + a[10] * P[4] - cbar * qv[1];
+    float sz = a[8] * P[2] + a[9] * P[4] + a[10] * P[5] - cbar * qv[2];
+#pragma unroll
+    for (int i = 0; i < kFeat; ++i) { sx = fmaf(a[i], M[0][i], sx); sy = fmaf(a[i], M[1][i], sy); sz = fmaf(a[i], M[2][i], sz); }
+    gx = fmaf(invS, sx, a[8]); gy = fmaf(invS, sy, a[9]); gz = fmaf(invS, sz, a[10]);
+  }
+};
 
 // LayerNorm over the 8 feature channels, no affine (F.layer_norm(x, [8])).
 __device__ __forceinline__ void layer_norm8(float (&f)[kFeat], float& mean, float& rstd) {

@@ -117,7 +117,10 @@ __device__ __forceinline__ int search_hashed(const ClidMap& m, const int64_t* __
 // ranks them; a warp iterates ceil(max-over-lanes(candidates) / kWalkBatch) times with all lanes
 // converged instead of diverging inside nested loops.
 constexpr int kHalfSlots = 2 * kBrickSlots;
-constexpr int kWalkBatch = 4;
+#ifndef CLID_WALK_BATCH
+#define CLID_WALK_BATCH 4
+#endif
+constexpr int kWalkBatch = CLID_WALK_BATCH;
 
 struct BrickScratch {
   uint32_t want[kHalfSlots][kQueryThreads];
@@ -237,9 +240,10 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
   const float slope = (p.flags & CLID_LEAKY_RELU) ? kLeakySlope : 0.f;
   const int knn = m.knn;
 
-  // block-uniform trip count: every lane stays in the loop so warp votes see full warps
-  for (int64_t q0 = (int64_t)blockIdx.x * blockDim.x; q0 < p.n; q0 += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t q = q0 + threadIdx.x;
+  // warp-uniform trip count: every lane stays in the loop so warp votes see full warps
+  TileScheduler sched(p.map.work_counter, p.n);
+  for (int64_t tile = sched.next(); tile >= 0; tile = sched.next()) {
+    const int64_t q = tile * 32 + (threadIdx.x & 31);
     const bool live = q < p.n;
     float px = 0.f, py = 0.f, pz = 0.f;
     if (live) { px = p.x[3 * q]; py = p.x[3 * q + 1]; pz = p.x[3 * q + 2]; }
@@ -284,6 +288,9 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
 #pragma unroll
     for (int i = 0; i < kIn; ++i) z[i] = 0.f;
     float cert = 0.f;
+    const bool want_grad = H > 0 && p.out.grad != nullptr;
+    Moments mom;
+    mom.clear();
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       if (row[k] >= 0) {
@@ -296,6 +303,7 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
         z[8] = fmaf(w[k], vx[k], z[8]);
         z[9] = fmaf(w[k], vy[k], z[9]);
         z[10] = fmaf(w[k], vz[k], z[10]);
+        if (want_grad) mom.add(f, u[k], vx[k], vy[k], vz[k]);  // the only pass over the feature rows
       }
     }
 
@@ -340,26 +348,9 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
           float cbar = 0.f;
 #pragma unroll
           for (int i = 0; i < kIn; ++i) cbar = fmaf(z[i], a[i], cbar);
-          const float invS = 1.0f / S;
-#pragma unroll
-          for (int k = 0; k < K; ++k) {
-            if (row[k] >= 0) {
-              // the feature row is re-read (L1/L2-resident) instead of being held in 48 registers
-              // across the MLP
-              float f[kFeat];
-              load_feature_row(m.gather_features, row[k], f);
-              if (layer_norm) { float mu, rs; layer_norm8(f, mu, rs); }
-              float ck = a[8] * vx[k] + a[9] * vy[k] + a[10] * vz[k];
-#pragma unroll
-              for (int i = 0; i < kFeat; ++i) ck = fmaf(f[i], a[i], ck);
-              // d u_k / d x = -2 u_k^2 v_k ; sum_k c_k d w_k / d x = (1/S) sum_k (c_k - cbar) d u_k / d x
-              const float coef = (ck - cbar) * (-2.f * u[k] * u[k]) * invS;
-              gx = fmaf(coef, vx[k], gx);
-              gy = fmaf(coef, vy[k], gy);
-              gz = fmaf(coef, vz[k], gz);
-            }
-          }
-          gx += a[8]; gy += a[9]; gz += a[10];  // sum_k w_k == 1
+          // d u_k / d x = -2 u_k^2 v_k ; sum_k c_k d w_k / d x = (1/S) sum_k (c_k - cbar) d u_k / d x,
+          // evaluated from the neighbourhood moments; + a_p because sum_k w_k == 1
+          mom.logit_gradient(a, cbar, 1.0f / S, gx, gy, gz);
         }
         p.out.grad[3 * q] = gx * s;
         p.out.grad[3 * q + 1] = gy * s;

@@ -153,8 +153,9 @@ __global__ void __launch_bounds__(kBwdThreads) train_backward_l1_kernel(const __
     for (int i = 0; i < kInPad; ++i) Gd[r][i] = 0.f;
   float delta_sum = 0.f;
 
-  for (int64_t q0 = (int64_t)blockIdx.x * blockDim.x; q0 < p.n; q0 += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t q = q0 + threadIdx.x;
+  TileScheduler sched(p.map.work_counter, p.n);
+  for (int64_t tile = sched.next(); tile >= 0; tile = sched.next()) {
+    const int64_t q = tile * 32 + (threadIdx.x & 31);
     const bool live = q < p.n;
     float c[kInPad];
 #pragma unroll
@@ -208,23 +209,8 @@ __global__ void __launch_bounds__(kBwdThreads) train_backward_l1_kernel(const __
       if (has_r && nb.any) { tau[8] += rx; tau[9] += ry; tau[10] += rz; }
 
       // decoder forward for the activation pattern and a = d logit / d z
-      float a[kIn];
-#pragma unroll
-      for (int i = 0; i < kIn; ++i) a[i] = 0.f;
-#pragma unroll 8
-      for (int j = 0; j < H; ++j) {
-        const float4 r0 = w0[j * 3 + 0], r1 = w0[j * 3 + 1], r2 = w0[j * 3 + 2];
-        float pre = sm_dec[Lay::kB0 + j];
-        pre = fmaf(r0.x, z[0], pre); pre = fmaf(r0.y, z[1], pre); pre = fmaf(r0.z, z[2], pre); pre = fmaf(r0.w, z[3], pre);
-        pre = fmaf(r1.x, z[4], pre); pre = fmaf(r1.y, z[5], pre); pre = fmaf(r1.z, z[6], pre); pre = fmaf(r1.w, z[7], pre);
-        pre = fmaf(r2.x, z[8], pre); pre = fmaf(r2.y, z[9], pre); pre = fmaf(r2.z, z[10], pre);
-        const bool on = pre > 0.f;
-        if (on) mask[j >> 5] |= 1u << (j & 31);
-        const float cj = sm_dec[Lay::kWout + j] * (on ? 1.f : slope);
-        a[0] = fmaf(cj, r0.x, a[0]); a[1] = fmaf(cj, r0.y, a[1]); a[2] = fmaf(cj, r0.z, a[2]); a[3] = fmaf(cj, r0.w, a[3]);
-        a[4] = fmaf(cj, r1.x, a[4]); a[5] = fmaf(cj, r1.y, a[5]); a[6] = fmaf(cj, r1.z, a[6]); a[7] = fmaf(cj, r1.w, a[7]);
-        a[8] = fmaf(cj, r2.x, a[8]); a[9] = fmaf(cj, r2.y, a[9]); a[10] = fmaf(cj, r2.z, a[10]);
-      }
+      float logit_unused, a[kIn];
+      mlp_l1_ffma2<H, true>(sm_dec, z, slope, logit_unused, a, mask);
 
       // c' = [delta z + s tau ; delta]
 #pragma unroll
@@ -297,7 +283,8 @@ __global__ void __launch_bounds__(kBwdThreads) train_backward_l1_kernel(const __
   float* gb0 = gW0 + H * kIn;
   float* gwout = gb0 + H;
   float* gbout = gwout + H;
-  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+  for (int j0 = threadIdx.x; j0 < H; j0 += blockDim.x) {
+    const int j = (j0 + blockIdx.x) % H;  // blocks start at different rows: spreads the same-address atomics in time
     float g[kInPad];
 #pragma unroll
     for (int i = 0; i < kInPad; ++i) {

@@ -39,7 +39,7 @@ struct TrainFusedParams {
 constexpr int kFusedThreads = 128;
 
 template <int H, int K, bool kBricks>
-__global__ void __launch_bounds__(kFusedThreads, 3) train_fused_l1_kernel(const __grid_constant__ TrainFusedParams p) {
+__global__ void __launch_bounds__(kFusedThreads, 4) train_fused_l1_kernel(const __grid_constant__ TrainFusedParams p) {
   using Lay = MlpLayout<H, 1>;
   constexpr int kRows = H / 32;
   constexpr int kMaskWords = H / 32;
@@ -84,15 +84,21 @@ __global__ void __launch_bounds__(kFusedThreads, 3) train_fused_l1_kernel(const 
   uint32_t* my_m = sm_m + (warp * 32) * kMaskWords;
   const float4* w0 = reinterpret_cast<const float4*>(sm_dec + Lay::kW0);
 
-  float Gd[kRows][kInPad];
+  // Gd partial sums of this warp live in shared memory between folds (rows lane, lane + 32, ...),
+  // so their registers are free while a sample is being evaluated
+  float* my_gd = sm_red + warp * H * kInPad;
+  if (p.dec_grad) {
 #pragma unroll
-  for (int r = 0; r < kRows; ++r)
+    for (int r = 0; r < kRows; ++r)
 #pragma unroll
-    for (int i = 0; i < kInPad; ++i) Gd[r][i] = 0.f;
+      for (int i = 0; i < kInPad; i += 4)
+        *reinterpret_cast<float4*>(my_gd + (lane + 32 * r) * kInPad + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   float delta_sum = 0.f, bce_sum = 0.f, eik_sum = 0.f;
 
-  for (int64_t q0 = (int64_t)blockIdx.x * blockDim.x; q0 < p.n; q0 += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t q = q0 + threadIdx.x;
+  TileScheduler sched(p.map.work_counter, p.n);
+  for (int64_t tile = sched.next(); tile >= 0; tile = sched.next()) {
+    const int64_t q = tile * 32 + (threadIdx.x & 31);
     const bool live = q < p.n;
     float px = 0.f, py = 0.f, pz = 0.f;
     if (live) { px = p.x[3 * q]; py = p.x[3 * q + 1]; pz = p.x[3 * q + 2]; }
@@ -143,6 +149,10 @@ __global__ void __launch_bounds__(kFusedThreads, 3) train_fused_l1_kernel(const 
       float z[kIn];
 #pragma unroll
       for (int i = 0; i < kIn; ++i) z[i] = 0.f;
+      // the feature rows pass through registers exactly once: blend + neighbourhood moments
+      // (both the spatial gradient and the tangent input tau0 = s J r are linear in the moments)
+      Moments mom;
+      mom.clear();
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         if (row[k] >= 0) {
@@ -152,6 +162,7 @@ __global__ void __launch_bounds__(kFusedThreads, 3) train_fused_l1_kernel(const 
 #pragma unroll
           for (int i = 0; i < kFeat; ++i) z[i] = fmaf(w[k], f[i], z[i]);
           z[8] = fmaf(w[k], vx[k], z[8]); z[9] = fmaf(w[k], vy[k], z[9]); z[10] = fmaf(w[k], vz[k], z[10]);
+          mom.add(f, u[k], vx[k], vy[k], vz[k]);
         }
       }
 
@@ -165,63 +176,25 @@ __global__ void __launch_bounds__(kFusedThreads, 3) train_fused_l1_kernel(const 
       }
 
       // ---- decoder: logit, activation pattern, a = d logit / d z
-      float out = sm_dec[Lay::kBout];
-      float a[kIn];
-#pragma unroll
-      for (int i = 0; i < kIn; ++i) a[i] = 0.f;
-#pragma unroll 8
-      for (int j = 0; j < H; ++j) {
-        const float4 r0 = w0[j * 3 + 0], r1 = w0[j * 3 + 1], r2 = w0[j * 3 + 2];
-        float pre = sm_dec[Lay::kB0 + j];
-        pre = fmaf(r0.x, z[0], pre); pre = fmaf(r0.y, z[1], pre); pre = fmaf(r0.z, z[2], pre); pre = fmaf(r0.w, z[3], pre);
-        pre = fmaf(r1.x, z[4], pre); pre = fmaf(r1.y, z[5], pre); pre = fmaf(r1.z, z[6], pre); pre = fmaf(r1.w, z[7], pre);
-        pre = fmaf(r2.x, z[8], pre); pre = fmaf(r2.y, z[9], pre); pre = fmaf(r2.z, z[10], pre);
-        const bool on = pre > 0.f;
-        if (on) mask[j >> 5] |= 1u << (j & 31);
-        const float cj = sm_dec[Lay::kWout + j] * (on ? 1.f : slope);
-        out = fmaf(cj, pre, out);
-        a[0] = fmaf(cj, r0.x, a[0]); a[1] = fmaf(cj, r0.y, a[1]); a[2] = fmaf(cj, r0.z, a[2]); a[3] = fmaf(cj, r0.w, a[3]);
-        a[4] = fmaf(cj, r1.x, a[4]); a[5] = fmaf(cj, r1.y, a[5]); a[6] = fmaf(cj, r1.z, a[6]); a[7] = fmaf(cj, r1.w, a[7]);
-        a[8] = fmaf(cj, r2.x, a[8]); a[9] = fmaf(cj, r2.y, a[9]); a[10] = fmaf(cj, r2.z, a[10]);
-      }
+      float out, a[kIn];
+      mlp_l1_ffma2<H, true>(sm_dec, z, slope, out, a, mask);
       const float sdf = out * s;
       if (p.sdf_out) p.sdf_out[q] = sdf;
 
-      // ---- features once more (L1/L2 resident), kept for both passes over the neighbours
-      float f[K][kFeat];
-      float rstd[K];
-      float ck[K], cbar = 0.f;
+      float cbar = 0.f;
 #pragma unroll
       for (int i = 0; i < kIn; ++i) cbar = fmaf(z[i], a[i], cbar);
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        rstd[k] = 1.f;
-        ck[k] = 0.f;
-        if (row[k] >= 0) {
-          load_feature_row(m.gather_features, row[k], f[k]);
-          if (layer_norm) { float mu; layer_norm8(f[k], mu, rstd[k]); }
-          float v = a[8] * vx[k] + a[9] * vy[k] + a[10] * vz[k];
-#pragma unroll
-          for (int i = 0; i < kFeat; ++i) v = fmaf(f[k][i], a[i], v);
-          ck[k] = v;
-        }
-      }
-
-      // ---- d sdf / d x (closed form) and the loss terms of this sample
-      float gx = 0.f, gy = 0.f, gz = 0.f;
       const float invS = count > 0 ? 1.0f / S : 0.f;
-      if (count > 0) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          if (row[k] >= 0) {
-            const float coef = (ck[k] - cbar) * (-2.f * u[k] * u[k]) * invS;
-            gx = fmaf(coef, vx[k], gx); gy = fmaf(coef, vy[k], gy); gz = fmaf(coef, vz[k], gz);
-          }
-        }
-        gx += a[8]; gy += a[9]; gz += a[10];
-      }
+      const float (&M)[3][kFeat] = mom.M;
+      const float (&P)[6] = mom.P;
+      const float (&qv)[3] = mom.qv;
+
+      // ---- d sdf / d x:  g_j = s (invS (a_f . M_j + a_p . P_j - cbar qv_j) + a_pj)
+      float gx = 0.f, gy = 0.f, gz = 0.f;
+      if (count > 0) mom.logit_gradient(a, cbar, invS, gx, gy, gz);
       gx *= s; gy *= s; gz *= s;
 
+      // ---- loss terms of this sample and their derivatives
       const float l = sdf / s;  // BCEWithLogits(pred / sigma, sigmoid(label / sigma))
       const float t = 1.0f / (1.0f + expf(-(p.label[q] / s)));
       const float wgt = (p.weighted && p.weight) ? fabsf(p.weight[q]) : 1.0f;
@@ -236,43 +209,38 @@ __global__ void __launch_bounds__(kFusedThreads, 3) train_fused_l1_kernel(const 
         rx = kk * gx; ry = kk * gy; rz = kk * gz;
       }
 
-      // ---- tangent input tau0 = s J r, with e_k = d w_k / d x . r
-      float e[K], dusum = 0.f;
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        e[k] = row[k] >= 0 ? -2.f * u[k] * u[k] * (vx[k] * rx + vy[k] * ry + vz[k] * rz) : 0.f;
-        dusum += e[k];
-      }
+      // ---- tangent input: sum_k e_k q_k = invS (sum_j r_j [M_j; P_j] - dusum z),  dusum = r . qv
+      const float dusum = rx * qv[0] + ry * qv[1] + rz * qv[2];
       float tau[kIn];
 #pragma unroll
-      for (int i = 0; i < kIn; ++i) tau[i] = 0.f;
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        if (row[k] >= 0) {
-          e[k] = (e[k] - w[k] * dusum) * invS;
-#pragma unroll
-          for (int i = 0; i < kFeat; ++i) tau[i] = fmaf(e[k], f[k][i], tau[i]);
-          tau[8] = fmaf(e[k], vx[k], tau[8]); tau[9] = fmaf(e[k], vy[k], tau[9]); tau[10] = fmaf(e[k], vz[k], tau[10]);
-        } else {
-          e[k] = 0.f;
-        }
-      }
+      for (int i = 0; i < kFeat; ++i)
+        tau[i] = invS * (rx * M[0][i] + ry * M[1][i] + rz * M[2][i] - dusum * z[i]);
+      tau[8] = invS * (rx * P[0] + ry * P[1] + rz * P[2] - dusum * z[8]);
+      tau[9] = invS * (rx * P[1] + ry * P[3] + rz * P[4] - dusum * z[9]);
+      tau[10] = invS * (rx * P[2] + ry * P[4] + rz * P[5] - dusum * z[10]);
       if (count > 0) { tau[8] += rx; tau[9] += ry; tau[10] += rz; }
 #pragma unroll
       for (int i = 0; i < kIn; ++i) c[i] = fmaf(delta, z[i], s * tau[i]);
       c[kIn] = delta;
       delta_sum += delta;
 
-      // ---- neural-point feature gradients
+      // ---- neural-point feature gradients: dL/df_k = a_f (delta w_k + s e_k), e_k = d w_k/d x . r
       if (p.gfeat) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           if (row[k] >= 0) {
-            const float coef = fmaf(s, e[k], delta * w[k]);
+            const float du = -2.f * u[k] * u[k] * (vx[k] * rx + vy[k] * ry + vz[k] * rz);
+            const float ek = (du - w[k] * dusum) * invS;
+            const float coef = fmaf(s, ek, delta * w[k]);
             float tt[kFeat];
 #pragma unroll
             for (int i = 0; i < kFeat; ++i) tt[i] = coef * a[i];
-            if (layer_norm) layer_norm8_vjp(f[k], rstd[k], tt);
+            if (layer_norm) {
+              float f[kFeat], mu, rs;
+              load_feature_row(m.gather_features, row[k], f);
+              layer_norm8(f, mu, rs);
+              layer_norm8_vjp(f, rs, tt);
+            }
             red_add_row(p.gfeat, row[k], tt);
             if (p.touched) p.touched[row[k]] = 1;
           }
@@ -289,6 +257,14 @@ __global__ void __launch_bounds__(kFusedThreads, 3) train_fused_l1_kernel(const 
 #pragma unroll
       for (int w = 0; w < kMaskWords; ++w) my_m[lane * kMaskWords + w] = mask[w];
       __syncwarp();
+      float Gd[kRows][kInPad];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r)
+#pragma unroll
+        for (int i = 0; i < kInPad; i += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(my_gd + (lane + 32 * r) * kInPad + i);
+          Gd[r][i] = v.x; Gd[r][i + 1] = v.y; Gd[r][i + 2] = v.z; Gd[r][i + 3] = v.w;
+        }
 #pragma unroll 4
       for (int nn = 0; nn < 32; ++nn) {
         const float4* src = reinterpret_cast<const float4*>(my_c + nn * kInPad);
@@ -304,6 +280,12 @@ __global__ void __launch_bounds__(kFusedThreads, 3) train_fused_l1_kernel(const 
           Gd[r][10] = fmaf(d, c2.z, Gd[r][10]); Gd[r][11] = fmaf(d, c2.w, Gd[r][11]);
         }
       }
+#pragma unroll
+      for (int r = 0; r < kRows; ++r)
+#pragma unroll
+        for (int i = 0; i < kInPad; i += 4)
+          *reinterpret_cast<float4*>(my_gd + (lane + 32 * r) * kInPad + i) =
+              make_float4(Gd[r][i], Gd[r][i + 1], Gd[r][i + 2], Gd[r][i + 3]);
       __syncwarp();
     }
   }
@@ -313,12 +295,6 @@ __global__ void __launch_bounds__(kFusedThreads, 3) train_fused_l1_kernel(const 
   eik_sum = warp_sum(eik_sum);
   delta_sum = warp_sum(delta_sum);
   if (lane == 0) { sm_scalar[0][warp] = bce_sum; sm_scalar[1][warp] = eik_sum; sm_scalar[2][warp] = delta_sum; }
-  if (p.dec_grad) {
-#pragma unroll
-    for (int r = 0; r < kRows; ++r)
-#pragma unroll
-      for (int i = 0; i < kInPad; ++i) sm_red[(warp * H + lane + 32 * r) * kInPad + i] = Gd[r][i];
-  }
   __syncthreads();
   if (threadIdx.x == 0) {
     float b = 0.f, e = 0.f, d = 0.f;
@@ -334,7 +310,8 @@ __global__ void __launch_bounds__(kFusedThreads, 3) train_fused_l1_kernel(const 
   float* gW0 = p.dec_grad;
   float* gb0 = gW0 + H * kIn;
   float* gwout = gb0 + H;
-  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+  for (int j0 = threadIdx.x; j0 < H; j0 += blockDim.x) {
+    const int j = (j0 + blockIdx.x) % H;  // blocks start at different rows: spreads the same-address atomics in time
     float g[kInPad];
 #pragma unroll
     for (int i = 0; i < kInPad; ++i) {

@@ -21,6 +21,20 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
         )
 
 
+_COUNTERS = {}
+
+
+def _work_counter(npm, device: torch.device) -> torch.Tensor:
+    """4 zeroed bytes per (device, stream) for the kernels' dynamic tile scheduler; the kernels
+    leave the counter at zero, so it is allocated and cleared once."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    t = _COUNTERS.get(key)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int32, device=device)
+        _COUNTERS[key] = t
+    return t
+
+
 def map_struct(npm, query_locally: bool, certainty_accum: Optional[torch.Tensor] = None) -> Tuple[_lib.ClidMap, int]:
     """ClidMap for `npm` plus the flag bits implied by the map state (locality, time filter,
     layer norm).  All pointers are borrowed from tensors that `npm` keeps alive."""
@@ -70,6 +84,7 @@ def map_struct(npm, query_locally: bool, certainty_accum: Optional[torch.Tensor]
     m.n_gather = pts.shape[0]
     m.feature_dim = int(npm.geo_feature_dim)
     m.knn = int(cfg.query_nn_k)
+    m.work_counter = _work_counter(npm, pts.device).data_ptr()
     if cfg.layer_norm_on:
         flags |= _lib.LAYER_NORM
     return m, flags

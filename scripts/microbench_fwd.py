@@ -55,3 +55,20 @@ for reps in (20, 100):
         fused.sdf_and_gradient(npm, dec, x, use_bricks=bool(args.bricks))
     e1.record(); torch.cuda.synchronize()
     print(f"back-to-back x{reps}: {e0.elapsed_time(e1)/reps*1e3:.1f} us per launch")
+
+# diagnostics: where does the time go?  (a) far queries: no candidates at all (search ~free, MLP still runs)
+# (b) all queries identical: every load hits L1 (instruction-bound time of the full path)
+def bb(xq, reps=50):
+    for _ in range(3):
+        fused.sdf_and_gradient(npm, dec, xq, use_bricks=bool(args.bricks))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fused.sdf_and_gradient(npm, dec, xq, use_bricks=bool(args.bricks))
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+far = x + 1000.0
+same = x[:1].repeat(args.n, 1).contiguous()
+srt = x[torch.argsort(((x / 1.6).floor().long() * torch.tensor([1, 4096, 4096 * 4096], device="cuda")).sum(-1))].contiguous()
+print(f"diag: normal {bb(x):.1f} us | brick-sorted queries {bb(srt):.1f} us | far (no candidates) {bb(far):.1f} us | identical queries {bb(same):.1f} us")
