@@ -21,19 +21,22 @@ _OVERLAY = {
     "utils.mapper": "clid_slam_b200.utils.mapper",
     "utils.loss": "clid_slam_b200.utils.loss",
     "utils.data_sampler": "clid_slam_b200.utils.data_sampler",
+    "model.local_point_cloud_map": "clid_slam_b200.model.local_point_cloud_map",
 }
+_FEEDERS = ("utils.data_sampler", "model.local_point_cloud_map")
 
 
-def install(replace_sampler: bool = False) -> None:
+def install(replace_sampler: bool = True) -> None:
     """Alias the reference's module names to this package in ``sys.modules`` so that an unmodified
     ``slam.py`` (``from model.neural_points import NeuralPoints`` ...) picks up the B200 path.
 
     Call it before the reference's modules are imported, with the reference tree on ``sys.path``
     (its ``utils.config``, ``utils.tools``, dataset / tracker / mesher code keeps being used as is).
-    ``utils.data_sampler`` is only replaced on request: CLID-SLAM's region-specific sampler
-    (``DataSampler.sample``) is still the reference's own code."""
+    ``replace_sampler=False`` leaves the per-frame feeders (``utils.data_sampler``,
+    ``model.local_point_cloud_map``) on the reference's own code; both implementations produce the
+    same samples for the same torch seed (tests/test_host_logic.py)."""
     for ref_name, ours in _OVERLAY.items():
-        if ref_name == "utils.data_sampler" and not replace_sampler:
+        if ref_name in _FEEDERS and not replace_sampler:
             continue
         module = importlib.import_module(ours)
         sys.modules[ref_name] = module

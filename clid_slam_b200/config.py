@@ -32,6 +32,9 @@ class Config:
         self.search_alpha: float = 0.2
         self.idw_index: int = 2
         self.buffer_size: int = int(5e7)
+        self.local_voxel_size_m: float = 0.2    # LocalPointCloudMap (utils/config.py:111,124,148)
+        self.local_buffer_size: int = int(5e6)
+        self.local_map_size: float = 100.0
         self.feature_dim: int = 8
         self.feature_std: float = 0.0
         self.color_on: bool = False
@@ -117,6 +120,7 @@ class Config:
         self.max_range = proc.get("max_range_m", self.max_range)
         vox_down_m = proc.get("vox_down_m", self.max_range * 1e-3)
         smp = args.get("sampler", {})
+        self.local_voxel_size_m = smp.get("local_voxel_size_m", vox_down_m)
         self.surface_sample_range_m = smp.get("surface_sample_range_m", vox_down_m * 3.0)
         self.surface_sample_n = smp.get("surface_sample_n", self.surface_sample_n)
         self.free_sample_begin_ratio = smp.get("free_sample_begin_ratio", self.free_sample_begin_ratio)

@@ -88,9 +88,54 @@ class DataSampler:
         return coord, sdf_label, normal, sem, color, weight
 
     def sample(self, points_torch, local_point_cloud_map, cur_pose_torch):
-        """CLID-SLAM's region-specific SDF labels (utils/data_sampler.py:260-402) need the local
-        point-cloud map (model/local_point_cloud_map.py); both are the first "next" row of the
-        scope table and are not built yet."""
-        raise NotImplementedError(
-            "DataSampler.sample (region-specific SDF labels) is scheduled after the hot path; "
-            "set config.use_pin_mapper = True to use sample_pin")
+        """CLID-SLAM's sampler (utils/data_sampler.py:260-402): the same ray samples as sample_pin,
+        but the labels of the near-surface samples come from the local point-cloud map
+        (``region_specific_sdf_estimation``: point-to-plane distance where a plane fits, nearest
+        point distance otherwise), signed by the side of the surface the sample was drawn on;
+        samples with no stored point in reach are dropped.  Returns (coord, sdf_label, weight)."""
+        cfg, dev = self.config, self.dev
+        sigma = cfg.surface_sample_range_m
+        n_surf, n_front, n_behind = cfg.surface_sample_n, cfg.free_front_n, cfg.free_behind_n
+        per_ray = 1 + n_surf + n_front + n_behind
+        count = points_torch.shape[0]
+        depth = torch.linalg.norm(points_torch, dim=1, keepdim=True)
+
+        disp_surf = torch.randn(count * n_surf, 1, device=dev) * sigma
+        ratio_surf = disp_surf / depth.repeat(n_surf, 1) + 1.0
+        margin = 2.0
+        d_front = depth.repeat(n_front, 1)
+        hi = 1.0 - margin * sigma / d_front
+        lo = cfg.free_sample_begin_ratio
+        ratio_front = torch.rand(count * n_front, 1, device=dev) * (hi - lo) + lo
+        disp_front = (ratio_front - 1.0) * d_front
+        d_behind = depth.repeat(n_behind, 1)
+        hi = cfg.free_sample_end_dist_m / d_behind + 1.0
+        lo = 1.0 + margin * sigma / d_behind
+        ratio_behind = torch.rand(count * n_behind, 1, device=dev) * (hi - lo) + lo
+        disp_behind = (ratio_behind - 1.0) * d_behind
+
+        disp = torch.cat((torch.zeros_like(depth), disp_surf, disp_front, disp_behind), 0)
+        ratio = torch.cat((torch.ones_like(depth), ratio_surf, ratio_front, ratio_behind), 0)
+        coord = points_torch.repeat(per_ray, 1) * ratio
+        depth_all = depth.repeat(per_ray, 1)
+
+        # region-specific labels for the near-surface samples (block 1 .. n_surf of the block order)
+        n_near = count * (n_surf + 1)
+        sign = torch.where(disp_surf.squeeze(1) < 0, 1, -1)
+        keep = torch.ones(count * per_ray, dtype=torch.bool, device=dev)
+        sdf_label = -1 * disp.squeeze(1)
+        near_world = transform_torch(coord[count:n_near], cur_pose_torch)
+        dist, reachable = local_point_cloud_map.region_specific_sdf_estimation(near_world)
+        keep[count:n_near] = reachable
+        sdf_label[count:n_near] = sign * dist
+
+        weight = torch.ones_like(depth_all)
+        if cfg.dist_weight_on:
+            weight[:n_near] = 1 + cfg.dist_weight_scale * 0.5 - (depth_all[:n_near] / cfg.max_range) * cfg.dist_weight_scale
+        weight[n_near:] *= -1.0
+
+        coord = coord.reshape(per_ray, -1, 3).transpose(0, 1).reshape(-1, 3)
+        sdf_label = sdf_label.reshape(per_ray, -1).transpose(0, 1).reshape(-1)
+        weight = weight.reshape(per_ray, -1).transpose(0, 1).reshape(-1)
+        keep = keep.reshape(per_ray, -1).transpose(0, 1).reshape(-1)
+        return coord[keep], sdf_label[keep], weight[keep]

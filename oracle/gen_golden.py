@@ -392,6 +392,48 @@ def sampler_case(ref, name, cfg, seed):
     print(f"  wrote {path}: {scan.shape[0]} rays -> {coord.shape[0]} samples")
 
 
+def clid_sampler_case(ref, name, cfg, seed):
+    """LocalPointCloudMap.update_map x2 + DataSampler.sample (region-specific SDF labels)."""
+    from utils.data_sampler import DataSampler
+
+    gen = torch.Generator().manual_seed(seed)
+
+    def scan(n):
+        xy = (torch.rand(n, 2, generator=gen) - 0.5) * 30
+        floor = torch.cat((xy, -1.5 + 0.2 * torch.sin(xy[:, :1] / 3)), dim=1)
+        yz = (torch.rand(n // 3, 2, generator=gen) - 0.5) * torch.tensor([20.0, 3.0])
+        wall = torch.cat((torch.full((n // 3, 1), 8.0), yz), dim=1)
+        pts = torch.cat((floor, wall), 0)
+        return pts[pts.norm(dim=1) > 1.0]
+
+    scans = [scan(1500), scan(1500)]
+    poses = [torch.eye(4, dtype=torch.float64), torch.eye(4, dtype=torch.float64)]
+    poses[1][0, 3] = 0.4
+    lmap = ref.LocalPointCloudMap(cfg)
+    out = {"cfg_sampler": np.array(json.dumps({
+        k: getattr(cfg, k) for k in ("surface_sample_range_m", "surface_sample_n", "free_front_n", "free_behind_n",
+                                      "free_sample_begin_ratio", "free_sample_end_dist_m", "dist_weight_on",
+                                      "dist_weight_scale", "max_range", "local_voxel_size_m", "local_buffer_size",
+                                      "local_map_size")})), "seed": np.int64(seed)}
+    for i, (pts, pose) in enumerate(zip(scans, poses)):
+        lmap.update_map(pose[:3, 3].float(), ref.tools.transform_torch(pts, pose))
+        out[f"scan{i}"] = pts.numpy()
+        out[f"pose{i}"] = pose.numpy()
+        out[f"map{i}_points"] = lmap.local_point_cloud_map.numpy().copy()
+        slots = torch.nonzero(lmap.buffer_pt_index >= 0).flatten()
+        out[f"map{i}_slots"] = slots.numpy()
+        out[f"map{i}_vals"] = lmap.buffer_pt_index[slots].numpy()
+    torch.manual_seed(seed)
+    coord, label, weight = DataSampler(cfg).sample(scans[1], lmap, poses[1])
+    probe = ref.tools.transform_torch(scans[1][:512] + 0.05, poses[1])
+    d, mask = lmap.region_specific_sdf_estimation(probe)
+    out.update(coord=coord.numpy(), label=label.numpy(), weight=weight.numpy(),
+               probe=probe.numpy(), probe_dist=d.numpy(), probe_mask=mask.numpy())
+    path = os.path.join(GOLDEN_DIR, f"clidsampler_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"  wrote {path}: {coord.shape[0]} samples kept, map {lmap.local_point_cloud_map.shape[0]} points")
+
+
 def main():
     """python -m oracle.gen_golden [query|train|map|sampler]   (no argument = everything)"""
     only = sys.argv[1] if len(sys.argv) > 1 else None
@@ -419,6 +461,7 @@ def main():
     if only in (None, "sampler"):
         print("sampler fixtures")
         sampler_case(ref, "ncd128", make_ref_config(ref), 41)
+        clid_sampler_case(ref, "ncd128", make_ref_config(ref), 43)
     print("done")
 
 

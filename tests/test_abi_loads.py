@@ -98,7 +98,9 @@ def test_install_aliases_reference_module_names():
         "from utils.loss import sdf_bce_loss\n"
         "assert NeuralPoints.__module__ == 'clid_slam_b200.model.neural_points'\n"
         "assert Mapper.__module__ == 'clid_slam_b200.utils.mapper' and Decoder.__module__.startswith('clid_slam_b200')\n"
-        "assert 'utils.data_sampler' not in sys.modules or not sys.modules['utils.data_sampler'].__name__.startswith('clid')\n"
+        "from model.local_point_cloud_map import LocalPointCloudMap\n"
+        "assert LocalPointCloudMap.__module__ == 'clid_slam_b200.model.local_point_cloud_map'\n"
+        "assert sys.modules['utils.data_sampler'].__name__ == 'clid_slam_b200.utils.data_sampler'\n"
         "print('ok')\n" % ROOT
     )
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)

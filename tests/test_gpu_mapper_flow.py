@@ -29,10 +29,12 @@ def _scan(gen, device, n=6000):
     return pts[pts.norm(dim=1) > 1.0]
 
 
+@pytest.mark.parametrize("sampler", ["pin", "clid"])
 @pytest.mark.parametrize("mode", ["numerical", "analytic"])
-def test_three_frames_train_and_write_back(mode):
+def test_three_frames_train_and_write_back(mode, sampler):
     from clid_slam_b200.config import ncd128
     from clid_slam_b200.model.decoder import Decoder
+    from clid_slam_b200.model.local_point_cloud_map import LocalPointCloudMap
     from clid_slam_b200.model.neural_points import NeuralPoints
     from clid_slam_b200.utils.mapper import Mapper
     from clid_slam_b200.utils.tools import freeze_model
@@ -40,7 +42,8 @@ def test_three_frames_train_and_write_back(mode):
     torch.manual_seed(42)
     cfg = ncd128()
     cfg.device = "cuda"
-    cfg.use_pin_mapper = True
+    cfg.use_pin_mapper = sampler == "pin"  # "clid": region-specific labels from the local point-cloud map
+    cfg.local_buffer_size = 500_009
     cfg.buffer_size = 2_000_003
     cfg.feature_std = 0.0  # reference default: features start at exactly zero
     if mode == "analytic":
@@ -49,7 +52,7 @@ def test_three_frames_train_and_write_back(mode):
     npm = NeuralPoints(cfg)
     frames = 3
     ds = FakeDataset(frames)
-    mapper = Mapper(cfg, ds, npm, None, dec)
+    mapper = Mapper(cfg, ds, npm, LocalPointCloudMap(cfg), dec)
     gen = torch.Generator(device="cuda").manual_seed(5)
     first_loss = last_loss = None
     for frame in range(frames):

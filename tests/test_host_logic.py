@@ -182,3 +182,33 @@ def test_gradient_sync_with_two_gloo_ranks():
         assert torch.allclose(o["cert"], torch.arange(6, dtype=torch.float32) + 1.5)
         assert o["ts"].tolist() == [1, 5, 2]
     assert torch.equal(outs[0]["dec"], outs[1]["dec"])
+
+
+def test_clid_sampler_and_local_map_match_reference_fixture():
+    """LocalPointCloudMap.update_map / region_specific_sdf_estimation and DataSampler.sample against
+    the reference (same torch seed on CPU => same random draws)."""
+    from clid_slam_b200.model.local_point_cloud_map import LocalPointCloudMap
+    from clid_slam_b200.utils.tools import transform_torch
+
+    fx = gio.load("clidsampler", "ncd128")
+    cfg = ncd128()
+    cfg.device = "cpu"
+    for k, v in json.loads(str(fx["cfg_sampler"])).items():
+        setattr(cfg, k, v)
+    lmap = LocalPointCloudMap(cfg)
+    for i in range(2):
+        pose = gio.t(fx[f"pose{i}"])
+        lmap.update_map(pose[:3, 3].float(), transform_torch(gio.t(fx[f"scan{i}"]), pose))
+        assert torch.equal(lmap.local_point_cloud_map, gio.t(fx[f"map{i}_points"]))
+        table = torch.full((cfg.local_buffer_size,), -1, dtype=torch.int64)
+        table[gio.t(fx[f"map{i}_slots"])] = gio.t(fx[f"map{i}_vals"])
+        assert torch.equal(lmap.buffer_pt_index, table)
+    d, mask = lmap.region_specific_sdf_estimation(gio.t(fx["probe"]))
+    assert torch.equal(mask, gio.t(fx["probe_mask"]))
+    gio.assert_close(d, fx["probe_dist"], 1e-4, 1e-6, "region-specific |sdf|", 2e-3)
+    torch.manual_seed(int(fx["seed"]))
+    coord, label, weight = DataSampler(cfg).sample(gio.t(fx["scan1"]), lmap, gio.t(fx["pose1"]))
+    assert coord.shape == tuple(fx["coord"].shape)
+    assert torch.equal(coord, gio.t(fx["coord"]))
+    gio.assert_close(label, fx["label"], 1e-4, 1e-6, "labels", 2e-3)
+    assert torch.equal(weight, gio.t(fx["weight"]))
