@@ -78,7 +78,8 @@ class ClidLossArgs(C.Structure):
 class ClidTrainFusedArgs(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("ts", C.c_void_p), ("label", C.c_void_p), ("weight", C.c_void_p),
-        ("n", C.c_int64), ("n_norm", C.c_int64), ("weight_e", C.c_float), ("weighted", C.c_int32),
+        ("n", C.c_int64), ("n_norm", C.c_int64), ("nd_norm", C.c_int64),
+        ("weight_e", C.c_float), ("num_eps", C.c_float), ("weighted", C.c_int32), ("numerical", C.c_int32),
         ("gfeat", C.c_void_p), ("touched", C.c_void_p), ("dec_grad", C.c_void_p), ("loss", C.c_void_p),
         ("sdf_out", C.c_void_p),
     ]

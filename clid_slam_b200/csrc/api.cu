@@ -192,7 +192,7 @@ static int launch_train_backward(const TrainBwdParams& p, cudaStream_t stream) {
   return CLID_OK;
 }
 
-template <int H, int K, bool kBricks>
+template <int H, int K, bool kBricks, bool kNumerical>
 static int launch_train_fused(const TrainFusedParams& p, cudaStream_t stream) {
   DeviceInfo info;
   if (int rc = device_info(&info)) return rc;
@@ -201,7 +201,7 @@ static int launch_train_fused(const TrainFusedParams& p, cudaStream_t stream) {
                                         : 2 * CLID_MAX_KC;
   size_t smem = (MlpLayout<H, 1>::kFloats + kSearchFloats + kWarps * 32 * kInPad + kWarps * 32 * (H / 32) +
                  kWarps * H * kInPad) * sizeof(float);
-  auto kern = train_fused_l1_kernel<H, K, kBricks>;
+  auto kern = train_fused_l1_kernel<H, K, kBricks, kNumerical>;
   static thread_local int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {
     if (smem > 48 * 1024) {
@@ -212,7 +212,9 @@ static int launch_train_fused(const TrainFusedParams& p, cudaStream_t stream) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     if (blocks_per_sm < 1) blocks_per_sm = 1;
   }
-  int64_t want = (p.n + kFusedThreads - 1) / kFusedThreads;
+  const int64_t per_tile = kNumerical ? kNumTileSamples : 32;  // base samples per 32-lane tile
+  const int64_t tiles = (p.n + per_tile - 1) / per_tile;
+  int64_t want = (tiles * 32 + kFusedThreads - 1) / kFusedThreads;
   int64_t cap = (int64_t)info.sm_count * blocks_per_sm;
   int grid = (int)(want < cap ? want : cap);
   kern<<<grid, kFusedThreads, smem, stream>>>(p);
@@ -228,9 +230,14 @@ static int dispatch_train_fused(const TrainFusedParams& p, cudaStream_t stream) 
                      H, p.dec.levels);
   if (p.map.knn > 6) return set_error(CLID_EUNSUPPORTED, "fused training is compiled for query_nn_k <= 6");
   const bool bricks = p.flags & CLID_USE_BRICKS;
-  if (H == 64) return bricks ? launch_train_fused<64, 6, true>(p, stream) : launch_train_fused<64, 6, false>(p, stream);
-  if (H == 32) return bricks ? launch_train_fused<32, 6, true>(p, stream) : launch_train_fused<32, 6, false>(p, stream);
-  return bricks ? launch_train_fused<128, 6, true>(p, stream) : launch_train_fused<128, 6, false>(p, stream);
+  const bool num = p.num_eps > 0.f;  // set by clid_train_fused only in numerical mode
+#define CLID_FUSED(HH) \
+  (bricks ? (num ? launch_train_fused<HH, 6, true, true>(p, stream) : launch_train_fused<HH, 6, true, false>(p, stream)) \
+          : (num ? launch_train_fused<HH, 6, false, true>(p, stream) : launch_train_fused<HH, 6, false, false>(p, stream)))
+  if (H == 64) return CLID_FUSED(64);
+  if (H == 32) return CLID_FUSED(32);
+  return CLID_FUSED(128);
+#undef CLID_FUSED
 }
 
 static int dispatch_train_backward(const ClidMap* map, const ClidDecoder* dec, const float* x, const int32_t* knn_idx,
@@ -358,7 +365,13 @@ int clid_train_fused(const ClidMap* map, const ClidDecoder* dec, const ClidTrain
   p.x = a->x; p.ts = a->ts; p.label = a->label; p.weight = a->weight;
   p.gfeat = a->gfeat; p.touched = a->touched; p.dec_grad = a->dec_grad; p.loss = a->loss; p.sdf_out = a->sdf_out;
   p.n = a->n; p.n_norm = a->n_norm > 0 ? a->n_norm : a->n;
+  p.nd_norm = a->nd_norm > 0 ? a->nd_norm : (a->n + 9) / 10;
   p.weight_e = a->weight_e; p.weighted = a->weighted; p.flags = flags;
+  p.num_eps = 0.f;
+  if (a->numerical) {
+    if (!(a->num_eps > 0.f)) return set_error(CLID_EINVAL, "numerical mode needs num_eps > 0");
+    p.num_eps = a->num_eps;
+  }
   return dispatch_train_fused(p, static_cast<cudaStream_t>(stream));
 }
 

@@ -1,13 +1,23 @@
-// One-kernel mapping iteration for the analytic-gradient mode (utils/mapper.py:642-835 with
-// numerical_grad_on: False): per sample, in one thread and without leaving registers,
-//   kNN search -> IDW blend -> decoder -> d sdf/dx            (as query_forward_kernel)
-//   bce + eikonal loss terms and their derivatives            (utils/loss.py:44-62, mapper.py:780-798)
+// One-kernel mapping iteration (utils/mapper.py:642-835): per evaluated point, in one thread and
+// without leaving registers,
+//   kNN search -> IDW blend -> decoder (-> closed-form d sdf/dx)   (as query_forward_kernel)
+//   bce + eikonal loss terms and their derivatives                  (utils/loss.py:44-62, mapper.py:780-798)
 //   closed-form backward: feature-gradient scatter, decoder-gradient fold
-// Every quantity the backward needs (neighbour rows, weights, activation pattern, a = d out/d z)
-// is still live when the loss derivative is known, because in analytic mode d L / d logit and
-// d L / d grad of a sample depend on that sample alone.  Replaces three launches
-// (clid_query_forward + clid_sdf_loss + clid_train_backward) and the re-gather / MLP
+// Replaces clid_query_forward + clid_sdf_loss + clid_train_backward and the re-gather / MLP
 // re-evaluation of the split backward.
+//
+// Analytic eikonal gradient (numerical_grad_on: False): d L / d logit and d L / d grad of a sample
+// depend on that sample alone, so everything the backward needs is still live when they are known.
+//
+// Numerical eikonal gradient (the default of every shipped run file; mapper.py:985-1034): the
+// gradient of sample i (i % 10 == 0) needs the SDF at six shifted copies of it.  The evaluation
+// slots are arranged so that those seven evaluations sit in the same warp: a tile covers 20
+// consecutive samples,
+//     lanes  0.. 6   sample 20t      and its +x -x +y -y +z -z copies
+//     lanes  7..13   sample 20t + 10 and its six copies
+//     lanes 14..31   the other 18 samples of the tile
+// (exactly the reference's x[::10] subset), the six values are exchanged with warp shuffles after
+// the decoder, and each shifted lane continues with its own d L / d logit = +- s r_axis / (2 eps).
 #pragma once
 #include "common.cuh"
 #include "query_bwd.cuh"
@@ -30,15 +40,18 @@ struct TrainFusedParams {
   float* loss;           // [3] += total, bce, eikonal
   float* sdf_out;        // [n] or NULL (diagnostics)
   int64_t n;
-  int64_t n_norm;        // mean denominator (global batch size when sharded)
+  int64_t n_norm;        // mean denominator of the bce term (global batch size when sharded)
+  int64_t nd_norm;       // mean denominator of the numerical eikonal term (global decimated count)
   float weight_e;
+  float num_eps;         // central-difference step (numerical mode)
   int weighted;
   uint32_t flags;
 };
 
 constexpr int kFusedThreads = 128;
+constexpr int kNumTileSamples = 20;  // base samples per warp tile in numerical mode
 
-template <int H, int K, bool kBricks>
+template <int H, int K, bool kBricks, bool kNumerical>
 __global__ void __launch_bounds__(kFusedThreads, 4) train_fused_l1_kernel(const __grid_constant__ TrainFusedParams p) {
   using Lay = MlpLayout<H, 1>;
   constexpr int kRows = H / 32;
@@ -55,7 +68,7 @@ __global__ void __launch_bounds__(kFusedThreads, 4) train_fused_l1_kernel(const 
   BrickScratch& scratch = *reinterpret_cast<BrickScratch*>(smem + Lay::kFloats + 2 * 64 * kBrickSlots);
   float* sm_c = smem + Lay::kFloats + kSearchFloats;                            // [warps][32][12]
   uint32_t* sm_m = reinterpret_cast<uint32_t*>(sm_c + kWarps * 32 * kInPad);     // [warps][32][words]
-  float* sm_red = reinterpret_cast<float*>(sm_m + kWarps * 32 * kMaskWords);     // [warps][H][12] epilogue
+  float* sm_red = reinterpret_cast<float*>(sm_m + kWarps * 32 * kMaskWords);     // [warps][H][12] partial Gd
   __shared__ float sm_scalar[3][kWarps];
 
   const ClidMap& m = p.map;
@@ -82,7 +95,6 @@ __global__ void __launch_bounds__(kFusedThreads, 4) train_fused_l1_kernel(const 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* my_c = sm_c + (warp * 32) * kInPad;
   uint32_t* my_m = sm_m + (warp * 32) * kMaskWords;
-  const float4* w0 = reinterpret_cast<const float4*>(sm_dec + Lay::kW0);
 
   // Gd partial sums of this warp live in shared memory between folds (rows lane, lane + 32, ...),
   // so their registers are free while a sample is being evaluated
@@ -96,12 +108,35 @@ __global__ void __launch_bounds__(kFusedThreads, 4) train_fused_l1_kernel(const 
   }
   float delta_sum = 0.f, bce_sum = 0.f, eik_sum = 0.f;
 
-  TileScheduler sched(p.map.work_counter, p.n);
+  // lane role (numerical mode): which sample of the tile, and which of its 7 evaluations
+  int role_sample = lane, role_variant = 0;
+  if constexpr (kNumerical) {
+    if (lane < 14) {
+      role_sample = lane < 7 ? 0 : 10;
+      role_variant = lane < 7 ? lane : lane - 7;
+    } else {
+      const int r = lane - 14;             // 0..17 -> samples 1..9 and 11..19
+      role_sample = r < 9 ? r + 1 : r + 2;
+    }
+  }
+  const int64_t tile_samples = kNumerical ? kNumTileSamples : 32;
+  const int64_t n_tiles_work = (p.n + tile_samples - 1) / tile_samples;
+
+  TileScheduler sched(p.map.work_counter, n_tiles_work * 32);  // the scheduler counts 32-slot tiles
   for (int64_t tile = sched.next(); tile >= 0; tile = sched.next()) {
-    const int64_t q = tile * 32 + (threadIdx.x & 31);
+    const int64_t q = tile * tile_samples + role_sample;
     const bool live = q < p.n;
     float px = 0.f, py = 0.f, pz = 0.f;
-    if (live) { px = p.x[3 * q]; py = p.x[3 * q + 1]; pz = p.x[3 * q + 2]; }
+    if (live) {
+      px = p.x[3 * q]; py = p.x[3 * q + 1]; pz = p.x[3 * q + 2];
+      if constexpr (kNumerical) {
+        // x + eps e_a for odd variants 1,3,5 ; x - eps e_a for 2,4,6 (mapper.py:991-1003)
+        const float sh = (role_variant & 1) ? p.num_eps : -p.num_eps;
+        if (role_variant == 1 || role_variant == 2) px += sh;
+        if (role_variant == 3 || role_variant == 4) py += sh;
+        if (role_variant == 5 || role_variant == 6) pz += sh;
+      }
+    }
     TopK<K> top;
     top.init();
     int count = 0;
@@ -115,18 +150,20 @@ __global__ void __launch_bounds__(kFusedThreads, 4) train_fused_l1_kernel(const 
 #pragma unroll
     for (int w = 0; w < kMaskWords; ++w) mask[w] = 0u;
 
+    // ---- part 1 (per lane): neighbours, blend, side effects, decoder
+    int row[K];
+    float vx[K], vy[K], vz[K], w[K], u[K];
+    float S = 0.f, sdf = 0.f, cbar = 0.f;
+    float z[kIn], a[kIn];
+    Moments mom;
+#pragma unroll
+    for (int i = 0; i < kIn; ++i) { z[i] = 0.f; a[i] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < K; ++k) { row[k] = -1; vx[k] = vy[k] = vz[k] = 0.f; u[k] = 0.f; w[k] = 0.f; }
     if (live) {
-      // ---- neighbour rows, offsets, inverse-distance weights
-      int row[K];
-      float vx[K], vy[K], vz[K], w[K], u[K];
-      float S = 0.f;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        const bool valid = k < knn && top.id[k] >= 0;
-        row[k] = -1;
-        vx[k] = vy[k] = vz[k] = 0.f;
-        u[k] = 0.f;
-        if (valid) {
+        if (k < knn && top.id[k] >= 0) {
           float qx, qy, qz;
           if constexpr (kBricks) {
             const float4 r = __ldg(reinterpret_cast<const float4*>(p.bricks.records) + top.id[k]);
@@ -145,14 +182,9 @@ __global__ void __launch_bounds__(kFusedThreads, 4) train_fused_l1_kernel(const 
 #pragma unroll
       for (int k = 0; k < K; ++k) w[k] = row[k] >= 0 ? u[k] / S : 0.f;
 
-      // ---- blend
-      float z[kIn];
-#pragma unroll
-      for (int i = 0; i < kIn; ++i) z[i] = 0.f;
-      // the feature rows pass through registers exactly once: blend + neighbourhood moments
-      // (both the spatial gradient and the tangent input tau0 = s J r are linear in the moments)
-      Moments mom;
-      mom.clear();
+      // the feature rows pass through registers exactly once: blend (+ neighbourhood moments, which
+      // the analytic spatial gradient and the tangent input tau0 = s J r are linear in)
+      if constexpr (!kNumerical) mom.clear();
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         if (row[k] >= 0) {
@@ -162,76 +194,104 @@ __global__ void __launch_bounds__(kFusedThreads, 4) train_fused_l1_kernel(const 
 #pragma unroll
           for (int i = 0; i < kFeat; ++i) z[i] = fmaf(w[k], f[i], z[i]);
           z[8] = fmaf(w[k], vx[k], z[8]); z[9] = fmaf(w[k], vy[k], z[9]); z[10] = fmaf(w[k], vz[k], z[10]);
-          mom.add(f, u[k], vx[k], vy[k], vz[k]);
+          if constexpr (!kNumerical) mom.add(f, u[k], vx[k], vy[k], vz[k]);
         }
       }
 
-      // ---- side effects (neural_points.py:708-733)
+      // side effects (neural_points.py:708-733); the shifted copies carry no timestamp
+      // (Mapper.sdf queries without ts, mapper.py:968-969)
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         if (row[k] >= 0) {
           atomicAdd(m.certainty_accum + row[k], w[k]);
-          if (p.ts && m.gather_ts_update) atomicMax(m.gather_ts_update + row[k], p.ts[q]);
+          if (role_variant == 0 && p.ts && m.gather_ts_update) atomicMax(m.gather_ts_update + row[k], p.ts[q]);
         }
       }
 
-      // ---- decoder: logit, activation pattern, a = d logit / d z
-      float out, a[kIn];
+      float out;
       mlp_l1_ffma2<H, true>(sm_dec, z, slope, out, a, mask);
-      const float sdf = out * s;
-      if (p.sdf_out) p.sdf_out[q] = sdf;
-
-      float cbar = 0.f;
+      sdf = out * s;
+      if (p.sdf_out && role_variant == 0) p.sdf_out[q] = sdf;
 #pragma unroll
       for (int i = 0; i < kIn; ++i) cbar = fmaf(z[i], a[i], cbar);
-      const float invS = count > 0 ? 1.0f / S : 0.f;
-      const float (&M)[3][kFeat] = mom.M;
-      const float (&P)[6] = mom.P;
-      const float (&qv)[3] = mom.qv;
+    }
 
-      // ---- d sdf / d x:  g_j = s (invS (a_f . M_j + a_p . P_j - cbar qv_j) + a_pj)
-      float gx = 0.f, gy = 0.f, gz = 0.f;
-      if (count > 0) mom.logit_gradient(a, cbar, invS, gx, gy, gz);
-      gx *= s; gy *= s; gz *= s;
-
-      // ---- loss terms of this sample and their derivatives
+    // ---- part 2: loss terms and d L / d logit (numerical mode: warp exchange of the shifted values)
+    float delta = 0.f, rx = 0.f, ry = 0.f, rz = 0.f;  // r = d L / d (d sdf/dx), analytic mode only
+    const float invS = (live && count > 0) ? 1.0f / S : 0.f;
+    if constexpr (kNumerical) {
+      const int g0 = lane < 7 ? 0 : 7;  // first lane of this lane's group (meaningful for lane < 14)
+      const float s_xp = __shfl_sync(0xffffffffu, sdf, g0 + 1), s_xn = __shfl_sync(0xffffffffu, sdf, g0 + 2);
+      const float s_yp = __shfl_sync(0xffffffffu, sdf, g0 + 3), s_yn = __shfl_sync(0xffffffffu, sdf, g0 + 4);
+      const float s_zp = __shfl_sync(0xffffffffu, sdf, g0 + 5), s_zn = __shfl_sync(0xffffffffu, sdf, g0 + 6);
+      if (live && lane < 14 && p.weight_e > 0.f) {
+        const float two_eps = 2.0f * p.num_eps;
+        const float gx = (s_xp - s_xn) / two_eps, gy = (s_yp - s_yn) / two_eps, gz = (s_zp - s_zn) / two_eps;
+        const float gn = sqrtf(gx * gx + gy * gy + gz * gz);
+        const float dev = gn - 1.0f;
+        if (role_variant == 0) eik_sum += dev * dev;
+        else {
+          // d L / d sdf(x +- eps e_a) = +- r_a / (2 eps), r = weight_e 2 (|g|-1)/nd g/|g| ; times s for the logit
+          const float kk = gn > 0.f ? p.weight_e * 2.0f * dev / (float)p.nd_norm / gn * s / two_eps : 0.f;
+          const float ga = role_variant <= 2 ? gx : (role_variant <= 4 ? gy : gz);
+          delta = (role_variant & 1) ? kk * ga : -kk * ga;
+        }
+      }
+    }
+    if (live && role_variant == 0) {
       const float l = sdf / s;  // BCEWithLogits(pred / sigma, sigmoid(label / sigma))
       const float t = 1.0f / (1.0f + expf(-(p.label[q] / s)));
       const float wgt = (p.weighted && p.weight) ? fabsf(p.weight[q]) : 1.0f;
       bce_sum += wgt * ((1.0f - t) * l + fmaxf(-l, 0.f) + log1pf(expf(-fabsf(l))));
-      const float delta = wgt * (1.0f / (1.0f + expf(-l)) - t) * inv_n;
-      float rx = 0.f, ry = 0.f, rz = 0.f;
-      if (p.weight_e > 0.f) {
-        const float gn = sqrtf(gx * gx + gy * gy + gz * gz);
-        const float dev = gn - 1.0f;
-        eik_sum += dev * dev;
-        const float kk = gn > 0.f ? p.weight_e * 2.0f * dev * inv_n / gn : 0.f;
-        rx = kk * gx; ry = kk * gy; rz = kk * gz;
+      delta = wgt * (1.0f / (1.0f + expf(-l)) - t) * inv_n;
+      if constexpr (!kNumerical) {
+        if (p.weight_e > 0.f) {
+          float gx = 0.f, gy = 0.f, gz = 0.f;
+          if (count > 0) mom.logit_gradient(a, cbar, invS, gx, gy, gz);  // g_j = s (invS (a.M_j + a.P_j - cbar qv_j) + a_pj)
+          gx *= s; gy *= s; gz *= s;
+          const float gn = sqrtf(gx * gx + gy * gy + gz * gz);
+          const float dev = gn - 1.0f;
+          eik_sum += dev * dev;
+          const float kk = gn > 0.f ? p.weight_e * 2.0f * dev * inv_n / gn : 0.f;
+          rx = kk * gx; ry = kk * gy; rz = kk * gz;
+        }
       }
+    }
 
-      // ---- tangent input: sum_k e_k q_k = invS (sum_j r_j [M_j; P_j] - dusum z),  dusum = r . qv
-      const float dusum = rx * qv[0] + ry * qv[1] + rz * qv[2];
-      float tau[kIn];
+    // ---- part 3 (per lane): c' = [delta z + s tau0 ; delta] and the feature-gradient scatter
+    if (live) {
+      float dusum = 0.f;
+      if constexpr (!kNumerical) {
+        // tangent input: sum_k e_k q_k = invS (sum_j r_j [M_j; P_j] - dusum z),  dusum = r . qv
+        const float (&M)[3][kFeat] = mom.M;
+        const float (&P)[6] = mom.P;
+        dusum = rx * mom.qv[0] + ry * mom.qv[1] + rz * mom.qv[2];
+        float tau[kIn];
 #pragma unroll
-      for (int i = 0; i < kFeat; ++i)
-        tau[i] = invS * (rx * M[0][i] + ry * M[1][i] + rz * M[2][i] - dusum * z[i]);
-      tau[8] = invS * (rx * P[0] + ry * P[1] + rz * P[2] - dusum * z[8]);
-      tau[9] = invS * (rx * P[1] + ry * P[3] + rz * P[4] - dusum * z[9]);
-      tau[10] = invS * (rx * P[2] + ry * P[4] + rz * P[5] - dusum * z[10]);
-      if (count > 0) { tau[8] += rx; tau[9] += ry; tau[10] += rz; }
+        for (int i = 0; i < kFeat; ++i) tau[i] = invS * (rx * M[0][i] + ry * M[1][i] + rz * M[2][i] - dusum * z[i]);
+        tau[8] = invS * (rx * P[0] + ry * P[1] + rz * P[2] - dusum * z[8]);
+        tau[9] = invS * (rx * P[1] + ry * P[3] + rz * P[4] - dusum * z[9]);
+        tau[10] = invS * (rx * P[2] + ry * P[4] + rz * P[5] - dusum * z[10]);
+        if (count > 0) { tau[8] += rx; tau[9] += ry; tau[10] += rz; }
 #pragma unroll
-      for (int i = 0; i < kIn; ++i) c[i] = fmaf(delta, z[i], s * tau[i]);
+        for (int i = 0; i < kIn; ++i) c[i] = fmaf(delta, z[i], s * tau[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kIn; ++i) c[i] = delta * z[i];
+      }
       c[kIn] = delta;
       delta_sum += delta;
 
-      // ---- neural-point feature gradients: dL/df_k = a_f (delta w_k + s e_k), e_k = d w_k/d x . r
+      // neural-point feature gradients: dL/df_k = a_f (delta w_k + s e_k), e_k = d w_k/d x . r
       if (p.gfeat) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           if (row[k] >= 0) {
-            const float du = -2.f * u[k] * u[k] * (vx[k] * rx + vy[k] * ry + vz[k] * rz);
-            const float ek = (du - w[k] * dusum) * invS;
-            const float coef = fmaf(s, ek, delta * w[k]);
+            float coef = delta * w[k];
+            if constexpr (!kNumerical) {
+              const float du = -2.f * u[k] * u[k] * (vx[k] * rx + vy[k] * ry + vz[k] * rz);
+              coef = fmaf(s, (du - w[k] * dusum) * invS, coef);
+            }
             float tt[kFeat];
 #pragma unroll
             for (int i = 0; i < kFeat; ++i) tt[i] = coef * a[i];
@@ -255,7 +315,7 @@ __global__ void __launch_bounds__(kFusedThreads, 4) train_fused_l1_kernel(const 
       dst[1] = make_float4(c[4], c[5], c[6], c[7]);
       dst[2] = make_float4(c[8], c[9], c[10], c[11]);
 #pragma unroll
-      for (int w = 0; w < kMaskWords; ++w) my_m[lane * kMaskWords + w] = mask[w];
+      for (int ww = 0; ww < kMaskWords; ++ww) my_m[lane * kMaskWords + ww] = mask[ww];
       __syncwarp();
       float Gd[kRows][kInPad];
 #pragma unroll
@@ -300,7 +360,7 @@ __global__ void __launch_bounds__(kFusedThreads, 4) train_fused_l1_kernel(const 
     float b = 0.f, e = 0.f, d = 0.f;
     for (int w = 0; w < kWarps; ++w) { b += sm_scalar[0][w]; e += sm_scalar[1][w]; d += sm_scalar[2][w]; }
     const float bce = b * inv_n;
-    const float eik = p.weight_e > 0.f ? e * inv_n : 0.f;
+    const float eik = p.weight_e > 0.f ? e / (float)(kNumerical ? p.nd_norm : p.n_norm) : 0.f;
     atomicAdd(p.loss + 1, bce);
     atomicAdd(p.loss + 2, eik);
     atomicAdd(p.loss + 0, bce + p.weight_e * eik);

@@ -117,8 +117,12 @@ class FusedTrainer:
         n = x.shape[0]
         if n == 0 and not sync and shards is None:
             return
-        if self.single_kernel and not (self.numerical and self.weight_e > 0):
-            loss = self._iteration_single_kernel(x, label, ts, weight, n_global)
+        numerical = self.numerical and self.weight_e > 0
+        # the one-kernel numerical mode evaluates the x[::10] subset inside the warp tiles; explicit
+        # subsets (eik_index, sharded batches) and other decimations take the three-launch path
+        one_kernel_ok = (not numerical) or (int(cfg.gradient_decimation) == 10 and eik_index is None)
+        if self.single_kernel and one_kernel_ok:
+            loss = self._iteration_single_kernel(x, label, ts, weight, n_global, nd_global, numerical)
             return self._finish_iteration(loss, apply_step, sync, shards)
         nd = 0
         x_all, ts_all = x, ts
@@ -185,8 +189,8 @@ class FusedTrainer:
 
         return self._finish_iteration(loss, apply_step, sync, shards)
 
-    def _iteration_single_kernel(self, x, label, ts, weight, n_global):
-        """clid_train_fused: forward + loss + backward of the analytic mode in one launch."""
+    def _iteration_single_kernel(self, x, label, ts, weight, n_global, nd_global=0, numerical=False):
+        """clid_train_fused: forward + loss + backward in one launch (analytic or numerical eikonal)."""
         npm, dec, lib, dev = self.npm, self.dec, self.lib, self.device
         n = x.shape[0]
         loss = torch.zeros(3, dtype=torch.float32, device=dev)
@@ -205,7 +209,9 @@ class FusedTrainer:
         a.x, a.ts = x.data_ptr(), (None if tsd is None else tsd.data_ptr())
         a.label = _lib.ptr(label_f, torch.float32, "sdf_label")
         a.weight = _lib.ptr(w, torch.float32, "weight")
-        a.n, a.n_norm = n, int(n_global)
+        a.n, a.n_norm, a.nd_norm = n, int(n_global), int(nd_global)
+        a.numerical = int(bool(numerical))
+        a.num_eps = float(self.cfg.voxel_size_m * self.cfg.num_grad_step_ratio)
         a.weight_e = self.weight_e
         a.weighted = int(bool(self.cfg.loss_weight_on))
         a.gfeat = self.feat_grad.data_ptr() if self.train_features else None

@@ -216,21 +216,29 @@ CLID_API int clid_train_backward(const ClidMap* map, const ClidDecoder* dec, con
                                  int64_t n, int64_t n_r, uint32_t flags, float* gfeat,
                                  uint8_t* touched, float* dec_grad, clid_stream_t stream);
 
-/* One-kernel mapping iteration for the analytic-gradient mode (loss.numerical_grad_on: False):
- * clid_query_forward (training mode) + clid_sdf_loss + clid_train_backward fused per sample, i.e.
- * utils/mapper.py:660-835 from query_feature to cur_loss.backward() in a single launch.  Possible
- * because with the analytic gradient d L / d logit and d L / d grad of a sample depend on that
- * sample alone.  Same outputs and accumulation rules as the three calls; sdf_out [n] is optional.
- * `map` needs everything clid_query_forward needs (CLID_USE_BRICKS honoured) plus certainty_accum. */
+/* One-kernel mapping iteration: clid_query_forward (training mode) + clid_sdf_loss +
+ * clid_train_backward fused per evaluated point, i.e. utils/mapper.py:660-835 from query_feature to
+ * cur_loss.backward() in a single launch.  Same outputs and accumulation rules as the three
+ * calls; sdf_out [n] is optional.  `map` needs everything clid_query_forward needs
+ * (CLID_USE_BRICKS honoured) plus certainty_accum.
+ *   numerical == 0: analytic eikonal gradient (loss.numerical_grad_on: False); d L / d logit and
+ *                   d L / d grad of a sample depend on that sample alone.
+ *   numerical != 0: get_numerical_gradient (utils/mapper.py:985-1034) on the samples i % 10 == 0
+ *                   (gradient_decimation is fixed at 10 here); the six shifted copies of such a
+ *                   sample are evaluated by neighbouring lanes of the same warp and exchanged with
+ *                   shuffles.  Other decimations use the three-call path. */
 typedef struct ClidTrainFusedArgs {
   const float* x;        /* [n,3] */
   const int32_t* ts;     /* [n] or NULL */
   const float* label;    /* [n] */
   const float* weight;   /* [n] or NULL */
   int64_t n;
-  int64_t n_norm;        /* mean denominator; 0 = n */
+  int64_t n_norm;        /* mean denominator of the bce term; 0 = n */
+  int64_t nd_norm;       /* mean denominator of the numerical eikonal term; 0 = ceil(n / 10) */
   float weight_e;        /* 0 disables the eikonal term */
+  float num_eps;         /* central-difference step, voxel_size_m * num_grad_step_ratio (numerical) */
   int32_t weighted;      /* loss_weight_on */
+  int32_t numerical;     /* 0 analytic, 1 numerical eikonal gradient */
   float* gfeat;          /* [n_gather+1,F] += or NULL */
   uint8_t* touched;      /* [n_gather+1] or NULL */
   float* dec_grad;       /* flat [W0,b0,wout,bout] += or NULL (frozen decoder) */

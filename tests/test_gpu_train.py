@@ -55,8 +55,6 @@ def test_fused_training_matches_reference(name, single_kernel):
     from clid_slam_b200.ops.train import FusedTrainer
 
     fx, m, cfg, npm, dec, frozen = _setup(name)
-    if single_kernel and cfg.numerical_grad and cfg.ekional_loss_on:
-        pytest.skip("the numerical-gradient mode always uses the three-launch path")
     trainer = FusedTrainer(cfg, npm, dec)
     trainer.single_kernel = single_kernel
     for it in range(int(fx["n_iters"])):
