@@ -25,6 +25,7 @@ TIME_FILTER = 1 << 2
 LAYER_NORM = 1 << 3
 LEAKY_RELU = 1 << 4
 USE_BRICKS = 1 << 5
+TILE_KERNELS = 1 << 6
 
 _f32p = C.c_void_p  # device pointers travel as plain addresses
 
@@ -33,7 +34,7 @@ class ClidBricks(C.Structure):
     _fields_ = [
         ("headers", C.c_void_p), ("records", C.c_void_p), ("stencil", C.c_void_p),
         ("origin", C.c_int32 * 3), ("dims", C.c_int32 * 3), ("span", C.c_int32), ("reach", C.c_int32),
-        ("n_records", C.c_int32), ("reserved", C.c_int32),
+        ("n_records", C.c_int32), ("apron", C.c_int32),
     ]
 
 
@@ -81,7 +82,7 @@ class ClidTrainFusedArgs(C.Structure):
         ("n", C.c_int64), ("n_norm", C.c_int64), ("nd_norm", C.c_int64),
         ("weight_e", C.c_float), ("num_eps", C.c_float), ("weighted", C.c_int32), ("numerical", C.c_int32),
         ("gfeat", C.c_void_p), ("touched", C.c_void_p), ("dec_grad", C.c_void_p), ("loss", C.c_void_p),
-        ("sdf_out", C.c_void_p),
+        ("sdf_out", C.c_void_p), ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t),
     ]
 
 
@@ -119,6 +120,7 @@ _SIGNATURES = [
     ("clid_train_backward", C.c_int,
      [C.POINTER(ClidMap), C.POINTER(ClidDecoder), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
       C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("clid_train_fused_scratch_bytes", C.c_size_t, [C.c_int64, C.c_int32]),
     ("clid_train_fused", C.c_int,
      [C.POINTER(ClidMap), C.POINTER(ClidDecoder), C.POINTER(ClidTrainFusedArgs), C.c_uint32, C.c_void_p]),
     ("clid_adam_step", C.c_int, [C.POINTER(ClidAdamArgs), C.c_void_p]),

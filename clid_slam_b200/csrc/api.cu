@@ -1,13 +1,17 @@
-// C ABI of libclid_sdf.so: argument validation, kernel selection, launches.
+// C ABI of libclid_sdf.so: argument validation, kernel selection, launches of the plain kernels.
 // Declarations and the reference functions each entry point replaces: include/clid_sdf.h
+// The template kernels are instantiated in inst_*.cu (see launch.h).
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 
+#define CLID_PLAIN_KERNELS 1  // this translation unit owns the non-template __global__ functions
 #include "common.cuh"
+#include "launch.h"
 #include "query_bwd.cuh"
 #include "query_fwd.cuh"
 #include "train.cuh"
+#include "tile_kernel.cuh"
 #include "train_fused.cuh"
 
 namespace clid {
@@ -22,15 +26,11 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
-static int cuda_fail(cudaError_t e, const char* what) {
+int cuda_fail(cudaError_t e, const char* what) {
   return set_error(CLID_ECUDA, "%s: %s", what, cudaGetErrorString(e));
 }
 
-struct DeviceInfo {
-  int sm_count = 0;
-};
-
-static int device_info(DeviceInfo* info) {
+int device_info(DeviceInfo* info) {
   static thread_local int cached_dev = -1;
   static thread_local DeviceInfo cached;
   int dev = 0;
@@ -44,8 +44,6 @@ static int device_info(DeviceInfo* info) {
   *info = cached;
   return CLID_OK;
 }
-
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static int check_decoder(const ClidDecoder* d) {
   if (d->in_dim != kIn) return set_error(CLID_EUNSUPPORTED, "decoder in_dim %d (only %d = feature_dim 8 + 3)", d->in_dim, kIn);
@@ -80,54 +78,6 @@ static int check_map(const ClidMap* m, uint32_t flags) {
   return CLID_OK;
 }
 
-template <int H, int L, int K, bool kBricks>
-static int launch_query(const QueryParams& p, cudaStream_t stream) {
-  DeviceInfo info;
-  if (int rc = device_info(&info)) return rc;
-  constexpr int kThreads = kQueryThreads;
-  constexpr int kDecFloats = H > 0 ? MlpLayout<(H > 0 ? H : 4), (H > 0 ? L : 1)>::kFloats : 0;
-  size_t smem = kDecFloats * sizeof(float) +
-                (kBricks ? 64 * kBrickSlots * sizeof(uint64_t) + sizeof(BrickScratch) : CLID_MAX_KC * sizeof(int64_t));
-  auto kern = query_forward_kernel<H, L, K, kBricks>;
-  static thread_local int blocks_per_sm = 0;
-  if (blocks_per_sm == 0) {
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-    }
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kThreads, smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
-  }
-  int64_t want = (p.n + kThreads - 1) / kThreads;
-  int64_t cap = (int64_t)info.sm_count * blocks_per_sm;
-  int grid = (int)(want < cap ? want : cap);
-  kern<<<grid, kThreads, smem, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return cuda_fail(e, "query_forward_kernel launch");
-  return CLID_OK;
-}
-
-template <int H, int L>
-static int dispatch_query_k(const QueryParams& p, cudaStream_t stream) {
-  const bool bricks = p.flags & CLID_USE_BRICKS;
-  if (p.map.knn <= 6) return bricks ? launch_query<H, L, 6, true>(p, stream) : launch_query<H, L, 6, false>(p, stream);
-  return bricks ? launch_query<H, L, 8, true>(p, stream) : launch_query<H, L, 8, false>(p, stream);
-}
-
-static int dispatch_query(const QueryParams& p, bool has_dec, cudaStream_t stream) {
-  if (!has_dec) return dispatch_query_k<0, 1>(p, stream);
-  const int H = p.dec.hidden_dim, L = p.dec.levels;
-  if (L == 1 && H == 64) return dispatch_query_k<64, 1>(p, stream);
-  if (L == 1 && H == 32) return dispatch_query_k<32, 1>(p, stream);
-  if (L == 1 && H == 128) return dispatch_query_k<128, 1>(p, stream);
-  if (L == 2 && H == 32) return dispatch_query_k<32, 2>(p, stream);
-  if (L == 2 && H == 64) return dispatch_query_k<64, 2>(p, stream);
-  return set_error(CLID_EUNSUPPORTED,
-                   "decoder %d x %d not in the fused kernel set {64x1, 32x1, 128x1, 32x2, 64x2}; "
-                   "use the unfused query + torch decoder path", H, L);
-}
-
 template <bool kSecond>
 static int launch_query_backward(const ClidMap* map, const float* x, const int32_t* knn_idx, const float* gz,
                                  const float* ggx, int64_t n, uint32_t flags, float* gx, float* g_gz, float* gfeat,
@@ -151,11 +101,7 @@ static int launch_query_backward(const ClidMap* map, const float* x, const int32
   if (int rc = device_info(&info)) return rc;
   int64_t want = (n + 127) / 128, cap = (int64_t)info.sm_count * 8;
   int grid = (int)(want < cap ? want : cap);
-  if (map->knn <= 6) query_backward_kernel<6, kSecond><<<grid, 128, 0, stream>>>(p);
-  else query_backward_kernel<8, kSecond><<<grid, 128, 0, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return cuda_fail(e, what);
-  return CLID_OK;
+  return kSecond ? launch_query_backward_second(p, grid, stream) : launch_query_backward_first(p, grid, stream);
 }
 
 static int elementwise_grid(int64_t work, int threads) {
@@ -164,99 +110,6 @@ static int elementwise_grid(int64_t work, int threads) {
   int64_t want = (work + threads - 1) / threads;
   int64_t cap = (int64_t)info.sm_count * 16;
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
-}
-
-template <int H, int K>
-static int launch_train_backward(const TrainBwdParams& p, cudaStream_t stream) {
-  DeviceInfo info;
-  if (int rc = device_info(&info)) return rc;
-  constexpr int kWarps = kBwdThreads / 32;
-  size_t smem = (MlpLayout<H, 1>::kFloats + kWarps * 32 * kInPad + kWarps * 32 * (H / 32) + kWarps * H * kInPad) * sizeof(float);
-  auto kern = train_backward_l1_kernel<H, K>;
-  static thread_local int blocks_per_sm = 0;
-  if (blocks_per_sm == 0) {
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-    }
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBwdThreads, smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
-  }
-  int64_t want = (p.n + kBwdThreads - 1) / kBwdThreads;
-  int64_t cap = (int64_t)info.sm_count * blocks_per_sm;
-  int grid = (int)(want < cap ? want : cap);
-  kern<<<grid, kBwdThreads, smem, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return cuda_fail(e, "train_backward_l1_kernel launch");
-  return CLID_OK;
-}
-
-template <int H, int K, bool kBricks, bool kNumerical>
-static int launch_train_fused(const TrainFusedParams& p, cudaStream_t stream) {
-  DeviceInfo info;
-  if (int rc = device_info(&info)) return rc;
-  constexpr int kWarps = kFusedThreads / 32;
-  constexpr int kSearchFloats = kBricks ? (2 * 64 * kBrickSlots + (int)(sizeof(BrickScratch) / sizeof(float)))
-                                        : 2 * CLID_MAX_KC;
-  size_t smem = (MlpLayout<H, 1>::kFloats + kSearchFloats + kWarps * 32 * kInPad + kWarps * 32 * (H / 32) +
-                 kWarps * H * kInPad) * sizeof(float);
-  auto kern = train_fused_l1_kernel<H, K, kBricks, kNumerical>;
-  static thread_local int blocks_per_sm = 0;
-  if (blocks_per_sm == 0) {
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-    }
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kFusedThreads, smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
-  }
-  const int64_t per_tile = kNumerical ? kNumTileSamples : 32;  // base samples per 32-lane tile
-  const int64_t tiles = (p.n + per_tile - 1) / per_tile;
-  int64_t want = (tiles * 32 + kFusedThreads - 1) / kFusedThreads;
-  int64_t cap = (int64_t)info.sm_count * blocks_per_sm;
-  int grid = (int)(want < cap ? want : cap);
-  kern<<<grid, kFusedThreads, smem, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return cuda_fail(e, "train_fused_l1_kernel launch");
-  return CLID_OK;
-}
-
-static int dispatch_train_fused(const TrainFusedParams& p, cudaStream_t stream) {
-  const int H = p.dec.hidden_dim;
-  if (p.dec.levels != 1 || (H != 32 && H != 64 && H != 128))
-    return set_error(CLID_EUNSUPPORTED, "fused training is compiled for one hidden level with H in {32,64,128}; got %d x %d",
-                     H, p.dec.levels);
-  if (p.map.knn > 6) return set_error(CLID_EUNSUPPORTED, "fused training is compiled for query_nn_k <= 6");
-  const bool bricks = p.flags & CLID_USE_BRICKS;
-  const bool num = p.num_eps > 0.f;  // set by clid_train_fused only in numerical mode
-#define CLID_FUSED(HH) \
-  (bricks ? (num ? launch_train_fused<HH, 6, true, true>(p, stream) : launch_train_fused<HH, 6, true, false>(p, stream)) \
-          : (num ? launch_train_fused<HH, 6, false, true>(p, stream) : launch_train_fused<HH, 6, false, false>(p, stream)))
-  if (H == 64) return CLID_FUSED(64);
-  if (H == 32) return CLID_FUSED(32);
-  return CLID_FUSED(128);
-#undef CLID_FUSED
-}
-
-static int dispatch_train_backward(const ClidMap* map, const ClidDecoder* dec, const float* x, const int32_t* knn_idx,
-                                   const float* dlogit, const float* dgrad, int64_t n, int64_t n_r, uint32_t flags,
-                                   float* gfeat, uint8_t* touched, float* dec_grad, cudaStream_t stream) {
-  TrainBwdParams p;
-  memset(&p, 0, sizeof(p));
-  p.map = *map; p.dec = *dec;
-  p.x = x; p.knn_idx = knn_idx; p.dlogit = dlogit; p.dgrad = dgrad;
-  p.gfeat = gfeat; p.touched = touched; p.dec_grad = dec_grad;
-  p.n = n; p.n_r = n_r; p.flags = flags;
-  const int H = dec->hidden_dim;
-  if (dec->levels != 1 || (H != 32 && H != 64 && H != 128))
-    return set_error(CLID_EUNSUPPORTED, "fused backward is compiled for one hidden level with H in {32,64,128}; got %d x %d",
-                     H, dec->levels);
-  const bool k6 = map->knn <= 6;
-  if (H == 64) return k6 ? launch_train_backward<64, 6>(p, stream) : launch_train_backward<64, 8>(p, stream);
-  if (H == 32) return k6 ? launch_train_backward<32, 6>(p, stream) : launch_train_backward<32, 8>(p, stream);
-  return k6 ? launch_train_backward<128, 6>(p, stream) : launch_train_backward<128, 8>(p, stream);
 }
 
 }  // namespace clid
@@ -291,7 +144,19 @@ int clid_query_forward(const ClidMap* map, const ClidDecoder* dec, const float* 
   p.ts = ts;
   p.n = n;
   p.flags = flags;
-  return dispatch_query(p, dec != nullptr, static_cast<cudaStream_t>(stream));
+  // brick index with an apron, one-level decoder, plain inference outputs: phase-parked tile kernel
+  if ((flags & CLID_TILE_KERNELS) && (flags & CLID_USE_BRICKS) && dec && !(flags & CLID_TRAINING_MODE) && !out->z && !out->weights && !out->knn_idx &&
+      tile_supported(*map, *dec, *map->bricks)) {
+    TileParams t;
+    memset(&t, 0, sizeof(t));
+    t.map = *map; t.dec = *dec; t.bricks = *map->bricks;
+    t.x = x; t.ts = ts;
+    t.sdf_out = out->sdf; t.grad_out = out->grad; t.nn_count = out->nn_count; t.certainty = out->certainty;
+    t.n = n; t.flags = flags;
+    return launch_tile(t, kTileInfer, static_cast<cudaStream_t>(stream));
+  }
+  return (flags & CLID_USE_BRICKS) ? dispatch_query_bricks(p, dec != nullptr, static_cast<cudaStream_t>(stream))
+                                   : dispatch_query_hashed(p, dec != nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int clid_query_backward(const ClidMap* map, const float* x, const int32_t* knn_idx, const float* gz, int64_t n,
@@ -343,8 +208,20 @@ int clid_train_backward(const ClidMap* map, const ClidDecoder* dec, const float*
   if (!map->gather_points || !map->gather_features || !aligned16(map->gather_features))
     return set_error(CLID_EINVAL, "gather arrays are NULL or misaligned");
   if (gfeat && !aligned16(gfeat)) return set_error(CLID_EINVAL, "gfeat must be 16-byte aligned");
-  return dispatch_train_backward(map, dec, x, knn_idx, dlogit, dgrad, n, n_r, flags, gfeat, touched, dec_grad,
-                                 static_cast<cudaStream_t>(stream));
+  TrainBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.map = *map; p.dec = *dec;
+  p.x = x; p.knn_idx = knn_idx; p.dlogit = dlogit; p.dgrad = dgrad;
+  p.gfeat = gfeat; p.touched = touched; p.dec_grad = dec_grad;
+  p.n = n; p.n_r = n_r; p.flags = flags;
+  return dispatch_train_backward(p, static_cast<cudaStream_t>(stream));
+}
+
+size_t clid_train_fused_scratch_bytes(int64_t n, int32_t numerical) {
+  if (n <= 0) return 0;
+  const int64_t per_tile = numerical ? kNumTile : 32;
+  const int64_t tiles = (n + per_tile - 1) / per_tile;
+  return (size_t)tiles * 32 * kFoldRow * sizeof(float);
 }
 
 int clid_train_fused(const ClidMap* map, const ClidDecoder* dec, const ClidTrainFusedArgs* a, uint32_t flags,
@@ -372,7 +249,35 @@ int clid_train_fused(const ClidMap* map, const ClidDecoder* dec, const ClidTrain
     if (!(a->num_eps > 0.f)) return set_error(CLID_EINVAL, "numerical mode needs num_eps > 0");
     p.num_eps = a->num_eps;
   }
-  return dispatch_train_fused(p, static_cast<cudaStream_t>(stream));
+  const bool have_scratch = a->scratch && a->scratch_bytes >= clid_train_fused_scratch_bytes(a->n, a->numerical);
+  if (a->scratch && (reinterpret_cast<uintptr_t>(a->scratch) & 15u)) return set_error(CLID_EINVAL, "scratch must be 16-byte aligned");
+  DecoderGradParams g;
+  memset(&g, 0, sizeof(g));
+  g.dec = *dec; g.rows = static_cast<const float*>(a->scratch); g.dec_grad = p.dec_grad; g.flags = flags;
+  g.n_rows = (int64_t)(clid_train_fused_scratch_bytes(a->n, a->numerical) / (kFoldRow * sizeof(float)));
+  if ((flags & CLID_TILE_KERNELS) && (flags & CLID_USE_BRICKS) && tile_supported(*map, *dec, *map->bricks) &&
+      (!a->dec_grad || have_scratch)) {
+    TileParams t;
+    memset(&t, 0, sizeof(t));
+    t.map = *map; t.dec = *dec; t.bricks = *map->bricks;
+    t.x = p.x; t.ts = p.ts; t.label = p.label; t.weight = p.weight;
+    t.sdf_out = p.sdf_out; t.gfeat = p.gfeat; t.touched = p.touched; t.loss = p.loss;
+    t.fold_rows = p.dec_grad ? static_cast<float*>(a->scratch) : nullptr;
+    t.n = p.n; t.n_norm = p.n_norm; t.nd_norm = p.nd_norm;
+    t.weight_e = p.weight_e; t.num_eps = p.num_eps; t.weighted = p.weighted; t.flags = flags;
+    if (int rc = launch_tile(t, a->numerical ? kTileTrainNumerical : kTileTrainAnalytic, static_cast<cudaStream_t>(stream))) return rc;
+    return p.dec_grad ? launch_decoder_grad(g, static_cast<cudaStream_t>(stream)) : CLID_OK;
+  }
+  if (p.dec_grad && have_scratch) {
+    // decoder-gradient rows go to scratch; a dense reduction kernel folds them afterwards
+    p.fold_rows = static_cast<float*>(a->scratch);
+    if (int rc = (flags & CLID_USE_BRICKS) ? dispatch_train_fused_bricks(p, static_cast<cudaStream_t>(stream))
+                                            : dispatch_train_fused_hashed(p, static_cast<cudaStream_t>(stream)))
+      return rc;
+    return launch_decoder_grad(g, static_cast<cudaStream_t>(stream));
+  }
+  return (flags & CLID_USE_BRICKS) ? dispatch_train_fused_bricks(p, static_cast<cudaStream_t>(stream))
+                                   : dispatch_train_fused_hashed(p, static_cast<cudaStream_t>(stream));
 }
 
 int clid_adam_step(const ClidAdamArgs* a, clid_stream_t stream) {

@@ -1,0 +1,46 @@
+// Host-side launch plumbing shared by the translation units of libclid_sdf.so.  The template
+// kernels are instantiated in separate inst_*.cu files so that nvcc can compile them in parallel
+// (clid_slam_b200/build.py); api.cu holds the C ABI, the argument validation and the plain kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "clid_sdf.h"
+
+namespace clid {
+
+struct QueryParams;
+struct TrainBwdParams;
+struct TrainFusedParams;
+struct QueryBwdParams;
+struct TileParams;
+struct DecoderGradParams;
+
+int set_error(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+struct DeviceInfo {
+  int sm_count = 0;
+};
+int device_info(DeviceInfo* info);
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// inst_query_bricks.cu / inst_query_hashed.cu
+int dispatch_query_bricks(const QueryParams& p, bool has_dec, cudaStream_t stream);
+int dispatch_query_hashed(const QueryParams& p, bool has_dec, cudaStream_t stream);
+// inst_query_bwd.cu
+int launch_query_backward_first(const QueryBwdParams& p, int grid, cudaStream_t stream);
+int launch_query_backward_second(const QueryBwdParams& p, int grid, cudaStream_t stream);
+// inst_train_bwd.cu
+int dispatch_train_backward(const TrainBwdParams& p, cudaStream_t stream);
+// inst_fused_bricks.cu / inst_fused_hashed.cu
+int dispatch_train_fused_bricks(const TrainFusedParams& p, cudaStream_t stream);
+int dispatch_train_fused_hashed(const TrainFusedParams& p, cudaStream_t stream);
+
+// inst_tile.cu: phase-parked tile kernels (mode: TileMode) and the decoder-gradient reduction
+bool tile_supported(const ClidMap& map, const ClidDecoder& dec, const ClidBricks& bricks);
+int launch_tile(TileParams& p, int mode, cudaStream_t stream);
+int launch_decoder_grad(const DecoderGradParams& p, cudaStream_t stream);
+
+}  // namespace clid

@@ -116,7 +116,9 @@ __device__ __forceinline__ int search_hashed(const ClidMap& m, const int64_t* __
 // Phase 2: every lane pops up to kWalkBatch candidates, issues their record loads together, then
 // ranks them; a warp iterates ceil(max-over-lanes(candidates) / kWalkBatch) times with all lanes
 // converged instead of diverging inside nested loops.
-constexpr int kHalfSlots = 2 * kBrickSlots;
+// A neighbourhood is at most 5 cells wide (span <= 2, reach <= 2): 5 consecutive z cells touch at
+// most 3 of the 2-cell z halves, so at most 3 x 2 x 2 half-bricks can be non-empty.
+constexpr int kHalfSlots = 12;
 #ifndef CLID_WALK_BATCH
 #define CLID_WALK_BATCH 4
 #endif
@@ -364,6 +366,7 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
 // model/neural_points.py:971-1030 radius_neighborhood_search -> dist2 [n,kc] f32, idx [n,kc] i64
 // model/neural_points.py:1032-1051 query_certainty           -> max over cells of certainty
 // One thread per (query, cell) so both outputs are written fully coalesced.
+#ifdef CLID_PLAIN_KERNELS  // defined once, in api.cu
 __global__ void __launch_bounds__(256) radius_search_kernel(const ClidMap m, const float* __restrict__ x, int64_t n,
                                                             bool time_filter, float* __restrict__ dist2_out,
                                                             int64_t* __restrict__ idx_out) {
@@ -414,5 +417,7 @@ __global__ void __launch_bounds__(256) query_certainty_kernel(const ClidMap m, c
     out[q] = best;
   }
 }
+
+#endif  // CLID_PLAIN_KERNELS
 
 }  // namespace clid

@@ -39,6 +39,7 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+#ifdef CLID_PLAIN_KERNELS  // defined once, in api.cu
 __global__ void __launch_bounds__(256) sdf_loss_kernel(const LossParams p) {
   __shared__ float red[2][8];
   float bce_sum = 0.f, eik_sum = 0.f;
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(256) sdf_loss_kernel(const LossParams p) {
     atomicAdd(p.loss + 0, bce + p.weight_e * eik);
   }
 }
+#endif  // CLID_PLAIN_KERNELS
 
 // ------------------------------------------------------------------------------------------
 // backward (one hidden level): thread per sample, decoder gradients through the masked sums
@@ -341,6 +343,7 @@ __device__ __forceinline__ float adam_update(float p, float g, float& mm, float&
   return p - a.step_size * (mm / denom);
 }
 
+#ifdef CLID_PLAIN_KERNELS
 __global__ void __launch_bounds__(256) adam_kernel(const AdamParams a) {
   // feature rows: one thread per float4 half-row
   const int64_t halves = a.rows * 2;
@@ -379,5 +382,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamParams a) {
     }
   }
 }
+
+#endif  // CLID_PLAIN_KERNELS
 
 }  // namespace clid

@@ -39,6 +39,7 @@ struct TrainFusedParams {
   float* dec_grad;       // flat [W0,b0,wout,bout] += or NULL (frozen decoder)
   float* loss;           // [3] += total, bce, eikonal
   float* sdf_out;        // [n] or NULL (diagnostics)
+  float* fold_rows;      // kFoldOut: [tiles*32][16] rows (c'[12], activation bits) for decoder_grad_kernel
   int64_t n;
   int64_t n_norm;        // mean denominator of the bce term (global batch size when sharded)
   int64_t nd_norm;       // mean denominator of the numerical eikonal term (global decimated count)
@@ -51,7 +52,11 @@ struct TrainFusedParams {
 constexpr int kFusedThreads = 128;
 constexpr int kNumTileSamples = 20;  // base samples per warp tile in numerical mode
 
-template <int H, int K, bool kBricks, bool kNumerical>
+// kFoldOut: the decoder-gradient fold (Gd += d c') is not done by the warp itself; every lane writes
+// its 64-byte row [c'(12) | activation bits | pad] to global memory and decoder_grad_kernel
+// (tile_kernel.cuh) reduces all rows afterwards.  The warp-serial fold costs ~28 % of this kernel's
+// time (profiles/), as a separate dense reduction it is a few microseconds.
+template <int H, int K, bool kBricks, bool kNumerical, bool kFoldOut>
 __global__ void __launch_bounds__(kFusedThreads, 4) train_fused_l1_kernel(const __grid_constant__ TrainFusedParams p) {
   using Lay = MlpLayout<H, 1>;
   constexpr int kRows = H / 32;
@@ -99,7 +104,7 @@ __global__ void __launch_bounds__(kFusedThreads, 4) train_fused_l1_kernel(const 
   // Gd partial sums of this warp live in shared memory between folds (rows lane, lane + 32, ...),
   // so their registers are free while a sample is being evaluated
   float* my_gd = sm_red + warp * H * kInPad;
-  if (p.dec_grad) {
+  if (!kFoldOut && p.dec_grad) {
 #pragma unroll
     for (int r = 0; r < kRows; ++r)
 #pragma unroll
@@ -308,8 +313,22 @@ __global__ void __launch_bounds__(kFusedThreads, 4) train_fused_l1_kernel(const 
       }
     }
 
+    if constexpr (kFoldOut) {
+      // ---- row for the decoder-gradient reduction (dead lanes write zeros: c stays 0 for them)
+      if (p.fold_rows) {
+        float4* dst = reinterpret_cast<float4*>(p.fold_rows + (tile * 32 + lane) * 16);
+        dst[0] = make_float4(c[0], c[1], c[2], c[3]);
+        dst[1] = make_float4(c[4], c[5], c[6], c[7]);
+        dst[2] = make_float4(c[8], c[9], c[10], c[11]);
+        float4 mk = make_float4(0.f, 0.f, 0.f, 0.f);
+        mk.x = __uint_as_float(mask[0]);
+        if constexpr (kMaskWords > 1) mk.y = __uint_as_float(mask[1]);
+        if constexpr (kMaskWords > 2) { mk.z = __uint_as_float(mask[2]); mk.w = __uint_as_float(mask[3]); }
+        dst[3] = mk;
+      }
+    }
     // ---- decoder-gradient fold (see train_backward_l1_kernel)
-    if (p.dec_grad) {
+    if (!kFoldOut && p.dec_grad) {
       float4* dst = reinterpret_cast<float4*>(my_c + lane * kInPad);
       dst[0] = make_float4(c[0], c[1], c[2], c[3]);
       dst[1] = make_float4(c[4], c[5], c[6], c[7]);
@@ -364,9 +383,9 @@ __global__ void __launch_bounds__(kFusedThreads, 4) train_fused_l1_kernel(const 
     atomicAdd(p.loss + 1, bce);
     atomicAdd(p.loss + 2, eik);
     atomicAdd(p.loss + 0, bce + p.weight_e * eik);
-    if (p.dec_grad && p.dec.out_bias) atomicAdd(p.dec_grad + H * kIn + 2 * H, d);
+    if (!kFoldOut && p.dec_grad && p.dec.out_bias) atomicAdd(p.dec_grad + H * kIn + 2 * H, d);
   }
-  if (!p.dec_grad) return;
+  if (kFoldOut || !p.dec_grad) return;
   float* gW0 = p.dec_grad;
   float* gb0 = gW0 + H * kIn;
   float* gwout = gb0 + H;

@@ -82,7 +82,7 @@ def _make_stencil_table(offsets_cpu: torch.Tensor, reach: int, span: int) -> tor
 class BrickIndex:
     """Device tensors of one index plus the ClidBricks struct that points at them."""
 
-    def __init__(self, headers, records, stencil, origin, dims, span, reach):
+    def __init__(self, headers, records, stencil, origin, dims, span, reach, apron=0):
         self.headers, self.records, self.stencil = headers, records, stencil
         s = _lib.ClidBricks()
         s.headers = headers.data_ptr()
@@ -92,6 +92,7 @@ class BrickIndex:
             s.origin[i] = int(origin[i])
             s.dims[i] = int(dims[i])
         s.span, s.reach, s.n_records = int(span), int(reach), int(records.shape[0])
+        s.apron = int(apron)
         self.struct = s
         self.n_bricks = int(dims[0]) * int(dims[1]) * int(dims[2])
 
@@ -134,8 +135,11 @@ def build(npm, query_locally: bool) -> Optional[BrickIndex]:
         return None
     cells, pts, rows = cells[keep], pts[keep], rows[keep]
 
-    lo = cells.amin(0)
-    hi = cells.amax(0)
+    # one empty brick all around the occupied box (ClidBricks.apron): a neighbourhood that can
+    # contain points then has its lower-corner brick in [0, dims - 2] on every axis, so the kernels
+    # range-test a query once instead of once per brick
+    lo = cells.amin(0) - 4
+    hi = cells.amax(0) + 4
     lo_c, hi_c = lo.cpu(), hi.cpu()
     dims = [int((hi_c[i] - lo_c[i]) // 4 + 1) for i in range(3)]
     n_bricks = dims[0] * dims[1] * dims[2]
@@ -163,4 +167,4 @@ def build(npm, query_locally: bool) -> Optional[BrickIndex]:
     headers[:, 3] = count.to(torch.int32)
 
     stencil = _stencil_table(offsets_cpu, reach, span).to(dev)
-    return BrickIndex(headers, records, stencil, lo_c.tolist(), dims, span, reach)
+    return BrickIndex(headers, records, stencil, lo_c.tolist(), dims, span, reach, apron=1)

@@ -90,6 +90,8 @@ class FusedTrainer:
         # analytic (or no) eikonal: forward + loss + backward run as ONE kernel (clid_train_fused);
         # set False to use the three-launch path (always used by the numerical-gradient mode)
         self.single_kernel = True
+        self._scratch = None        # device scratch of clid_train_fused (rows for the decoder-gradient reduction)
+        self.use_scratch = True     # False: the warps fold the decoder gradients inside the one kernel
 
     # ------------------------------------------------------------------
     def _shifted(self, x: torch.Tensor, eik_index: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -202,6 +204,8 @@ class FusedTrainer:
         if bricks is not None:
             m.bricks = C.pointer(bricks.struct)
             flags |= _lib.USE_BRICKS
+            if _q.USE_TILE_KERNELS:
+                flags |= _lib.TILE_KERNELS
         if dec.use_leaky_relu:
             flags |= _lib.LEAKY_RELU
         ds = dec.abi_struct()
@@ -218,6 +222,11 @@ class FusedTrainer:
         a.touched = None if self.touched is None else self.touched.data_ptr()
         a.dec_grad = None if self.dec_grad is None else self.dec_grad.data_ptr()
         a.loss = loss.data_ptr()
+        if self.dec_grad is not None and self.use_scratch:
+            need = int(lib.clid_train_fused_scratch_bytes(n, a.numerical))
+            if self._scratch is None or self._scratch.numel() < need:
+                self._scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+            a.scratch, a.scratch_bytes = self._scratch.data_ptr(), need
         if self.forward_events is not None:
             ev0 = torch.cuda.Event(enable_timing=True)
             ev0.record()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CLID_ABI_VERSION 1
+#define CLID_ABI_VERSION 2
 #define CLID_MAX_LEVELS 3   /* hidden layers of the decoder MLP */
 #define CLID_MAX_KNN 8      /* query_nn_k */
 #define CLID_MAX_KC 256     /* probed cells per query */
@@ -49,7 +49,10 @@ enum ClidFlags {
   CLID_TIME_FILTER = 1 << 2,   /* travel-distance window on point_ts_create (:1003-1009) */
   CLID_LAYER_NORM = 1 << 3,    /* F.layer_norm over the feature dim, no affine, eps 1e-5 (:632-633) */
   CLID_LEAKY_RELU = 1 << 4,    /* decoder.py:66-74, slope 0.01 */
-  CLID_USE_BRICKS = 1 << 5     /* probe through ClidMap.bricks instead of the hash table */
+  CLID_USE_BRICKS = 1 << 5,    /* probe through ClidMap.bricks instead of the hash table */
+  CLID_TILE_KERNELS = 1 << 6   /* with an aproned span-2 brick index and a one-level decoder: run the
+                                  phase-parked 28-warps/SM tile kernel instead of the register-resident
+                                  one (same results; DESIGN.md section 4 compares them)               */
 };
 
 /* Brick index: a compact, per-frame restatement of "which neural point does the voxel hash
@@ -77,7 +80,9 @@ typedef struct ClidBricks {
   int32_t span;                   /* bricks per axis one neighbourhood can touch               */
   int32_t reach;                  /* num_nei_cells: the neighbourhood is [-reach, reach]^3     */
   int32_t n_records;
-  int32_t reserved;
+  int32_t apron;                  /* empty bricks surrounding the indexed bricks on every side (0 or 1).
+                                     With apron >= 1 and span == 2 the phase-parked tile kernels are used
+                                     (one range test per query instead of one per brick).             */
 } ClidBricks;
 
 /* Neural-point map state read by a query.  model/neural_points.py:79-133 */
@@ -244,7 +249,15 @@ typedef struct ClidTrainFusedArgs {
   float* dec_grad;       /* flat [W0,b0,wout,bout] += or NULL (frozen decoder) */
   float* loss;           /* [3] += total, bce, eikonal */
   float* sdf_out;        /* [n] or NULL */
+  void* scratch;         /* clid_train_fused_scratch_bytes(n, numerical) bytes of device scratch, or NULL.
+                            With it every evaluated point writes its 64-byte decoder-gradient row
+                            [delta z + s tau ; delta | activation bits] there and a second, dense kernel
+                            reduces the rows into dec_grad (2 launches); without it the warps fold the
+                            rows themselves inside the one kernel (slower).  Unused when dec_grad == NULL. */
+  size_t scratch_bytes;
 } ClidTrainFusedArgs;
+/* Device scratch clid_train_fused wants for n samples (64 bytes per evaluated point, 16-byte aligned). */
+CLID_API size_t clid_train_fused_scratch_bytes(int64_t n, int32_t numerical);
 CLID_API int clid_train_fused(const ClidMap* map, const ClidDecoder* dec, const ClidTrainFusedArgs* args,
                               uint32_t flags, clid_stream_t stream);
 

@@ -13,7 +13,7 @@ from oracle import sdf_oracle as oc
 # Parity tolerances (BASELINE.json north_star: 1e-4 rel on SDF values/gradients, 1e-3 on loss).
 # The absolute floors cover fp32 cancellation noise where the value itself is ~0:
 SDF_RTOL, SDF_ATOL = 1e-4, 2e-7     # metres; sdf_scale is 0.055 m, so the floor is ~4e-6 of scale
-GRAD_RTOL, GRAD_ATOL = 1e-4, 2e-6   # d sdf / d x is O(1)
+GRAD_RTOL, GRAD_ATOL = 1e-4, 5e-6   # d sdf / d x is O(1): the floor is 5e-6 of the gradient norm
 Z_RTOL, Z_ATOL = 1e-5, 1e-6
 LOSS_RTOL = 1e-3
 

@@ -48,10 +48,24 @@ def test_query_feature_matches_reference_fixture(name):
         gio.assert_close(npm.point_certainties, fx["after_certainties"], 1e-5, 1e-5, "certainty side effect")
 
 
-@pytest.mark.parametrize("bricks", [False, True], ids=["hashed", "bricks"])
+def _kernel_family(monkeypatch, family):
+    """hashed: reference hash table; bricks: brick index, register-resident kernels; tiles: brick
+    index, phase-parked tile kernels.  Returns the use_bricks argument."""
+    from clid_slam_b200.ops import query as q
+
+    monkeypatch.setattr(q, "USE_TILE_KERNELS", family == "tiles")
+    return family != "hashed"
+
+
+FAMILIES = ["hashed", "bricks", "tiles"]
+
+
+@pytest.mark.parametrize("family", FAMILIES)
 @pytest.mark.parametrize("name", gio.names("query"))
-def test_fused_forward_matches_reference_fixture(name, bricks):
+def test_fused_forward_matches_reference_fixture(name, family, monkeypatch):
     from clid_slam_b200 import fused
+
+    bricks = _kernel_family(monkeypatch, family)
 
     fx = gio.load("query", name)
     m = gio.oracle_map(fx)
@@ -71,10 +85,12 @@ def test_fused_forward_matches_reference_fixture(name, bricks):
     gio.assert_close(npm.local_point_certainties, m.local_certainties, 0, 0, "no side effect")
 
 
-@pytest.mark.parametrize("bricks", [False, True], ids=["hashed", "bricks"])
-@pytest.mark.parametrize("layer_norm,levels,hidden", [(False, 1, 64), (True, 1, 64), (False, 2, 32)])
-def test_fused_forward_matches_oracle_large(layer_norm, levels, hidden, bricks):
+@pytest.mark.parametrize("family", FAMILIES)
+@pytest.mark.parametrize("layer_norm,levels,hidden", [(False, 1, 64), (True, 1, 64), (False, 2, 32), (False, 1, 32), (False, 1, 128)])
+def test_fused_forward_matches_oracle_large(layer_norm, levels, hidden, family, monkeypatch):
     from clid_slam_b200 import fused
+
+    bricks = _kernel_family(monkeypatch, family)
 
     cfg = oc.OracleConfig(buffer_size=2_000_003, layer_norm_on=layer_norm, geo_mlp_level=levels,
                           geo_mlp_hidden_dim=hidden, local_map_radius=80.0)

@@ -49,14 +49,19 @@ def _check_final_state(fx, npm, dec):
         gio.assert_close(a, b, 1e-3, 1e-5, "decoder after Adam", 2e-3)
 
 
-@pytest.mark.parametrize("single_kernel", [True, False], ids=["one-kernel", "three-kernels"])
+# rows: decoder-gradient rows to scratch + reduction kernel (default); infold: the warps fold them inside
+# the one kernel; tiles: phase-parked tile kernels; three-kernels: forward / loss / backward launches
+@pytest.mark.parametrize("variant", ["rows", "infold", "tiles", "three-kernels"])
 @pytest.mark.parametrize("name", L1_CASES)
-def test_fused_training_matches_reference(name, single_kernel):
+def test_fused_training_matches_reference(name, variant, monkeypatch):
+    from clid_slam_b200.ops import query as q
     from clid_slam_b200.ops.train import FusedTrainer
 
+    monkeypatch.setattr(q, "USE_TILE_KERNELS", variant == "tiles")
     fx, m, cfg, npm, dec, frozen = _setup(name)
     trainer = FusedTrainer(cfg, npm, dec)
-    trainer.single_kernel = single_kernel
+    trainer.single_kernel = variant != "three-kernels"
+    trainer.use_scratch = variant != "infold"
     for it in range(int(fx["n_iters"])):
         x, label, ts, weight = _batch(fx, it)
         loss = trainer.iteration(x, label, ts, weight, apply_step=False)
