@@ -193,7 +193,21 @@ def run_native(args):
     else:
         batches = [sample_batch(npm.neural_points, BATCH, gen) for _ in range(n_batches)]
     host_batches = [tuple(t.cpu().pin_memory() for t in b) for b in batches]
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
+    flush_w = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
+    flush_r = torch.zeros(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=device)
+    flush_sink = torch.zeros((), dtype=torch.float32, device=device)
+
+    class _Flush:
+        """Evict the step's working set from the 126 MB L2: write a 256 MiB buffer, then read another
+        256 MiB one, so the lines the step evicts are clean (a write-only flush leaves the L2 full of
+        dirty lines whose write-back is charged to whatever runs next)."""
+
+        @staticmethod
+        def zero_():
+            flush_w.zero_()
+            flush_sink.copy_(flush_r.sum())
+
+    flush = _Flush()
 
     trainer = FusedTrainer(cfg, npm, dec)
     n_global = BATCH * world
@@ -201,20 +215,27 @@ def run_native(args):
     if cfg.numerical_grad:
         nd_global = world * ((BATCH + cfg.gradient_decimation - 1) // cfg.gradient_decimation)
 
-    def step(i, from_host=False):
-        if from_host:
-            x, label, weight, ts = (t.to(device, non_blocking=True) for t in host_batches[i % n_batches])
-        else:
-            x, label, weight, ts = batches[i % n_batches]
-        loss = trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global,
-                                 sync=world > 1 and shards is None, shards=shards)
-        return loss
-
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    multi = world > 1
+    if not multi:
+        # single GPU: the iteration is one CUDA graph per input buffer (ops/train.py StepPipeline)
+        from clid_slam_b200.ops.train import StepPipeline
+
+        pipe_dev = StepPipeline(trainer, BATCH, n_global=n_global, nd_global=nd_global, buffers=batches)
+        pipe_host = StepPipeline(trainer, BATCH, n_global=n_global, nd_global=nd_global)
+
+        def step(i):
+            return pipe_dev.run(i % n_batches)
+    else:
+        def step(i):
+            x, label, weight, ts = batches[i % n_batches]
+            return trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global,
+                                     sync=shards is None, shards=shards)
 
     for i in range(max(args.warmup, 3)):
         flush.zero_()
@@ -225,7 +246,6 @@ def run_native(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    trainer.forward_events, trainer.backward_events = [], []
     launches0 = trainer.launches
     events = []
     sync_all()
@@ -240,25 +260,44 @@ def run_native(args):
     sync_all()
     torch.cuda.nvtx.range_pop()
     total_ms = sum(a.elapsed_time(b) for a, b in events)
-    fwd_ms = [a.elapsed_time(b) for a, b in trainer.forward_events]
-    bwd_ms = [a.elapsed_time(b) for a, b in trainer.backward_events]
     launches = trainer.launches - launches0
-    trainer.forward_events = trainer.backward_events = None
 
-    # ---- end to end: host (pinned) batch -> device, step, loss back to the host, every step
+    # ---- end to end: host (pinned) batch -> device, step, loss back to the host, every step.
+    # Single GPU: batch i + 1 crosses PCIe on the copy stream while step i runs (StepPipeline).
     e2e_events = []
     sync_all()
+    if not multi:
+        pipe_host.stage(0, host_batches[0])
     for i in range(args.steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        loss = step(i, from_host=True)
+        if not multi:
+            pipe_host.stage((i + 1) % 2, host_batches[(i + 1) % n_batches])
+            loss = pipe_host.run(i % 2)
+        else:
+            x, label, weight, ts = (t.to(device, non_blocking=True) for t in host_batches[i % n_batches])
+            loss = trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global,
+                                     sync=shards is None, shards=shards)
         loss_host = loss.cpu()  # device -> host read of the step's result (synchronises)
         e1.record()
         e2e_events.append((e0, e1))
     sync_all()
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_events)
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- kernel-only timing for the roofline: the same step launched call by call (no graph) with
+    # CUDA events around the dominant kernel, same L2 hygiene
+    trainer.forward_events, trainer.backward_events = [], []
+    for i in range(min(args.steps, 30)):
+        flush.zero_()
+        x, label, weight, ts = batches[i % n_batches]
+        trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global,
+                          sync=multi and shards is None, shards=shards)
+    sync_all()
+    fwd_ms = [a.elapsed_time(b) for a, b in trainer.forward_events]
+    bwd_ms = [a.elapsed_time(b) for a, b in trainer.backward_events]
+    trainer.forward_events = trainer.backward_events = None
 
     # ---- inference-only forward (what the 40 % roofline target is stated on), same L2 hygiene
     inf_events = []
@@ -293,7 +332,8 @@ def run_native(args):
         fwd_avg_ms = statistics.mean(fwd_ms)
         one_kernel = not bwd_ms  # analytic mode: forward + loss + backward are one launch (clid_train_fused)
         b_kernel = b_fwd + b_bwd if one_kernel else b_fwd
-        kernel_name = ("train_fused_l1_kernel<64,6,bricks> (forward + loss + backward of the step)" if one_kernel
+        kernel_name = ("train_fused_l1_kernel<64,6,bricks,rows> (forward + loss + backward of the step; its per-point "
+                       "decoder-gradient rows are reduced by decoder_grad_kernel afterwards)" if one_kernel
                        else "query_forward_kernel<64,1,6,bricks> (training forward)")
         achieved = b_kernel * evals / (fwd_avg_ms * 1e-3) / 1e9
         traffic = None
@@ -313,7 +353,7 @@ def run_native(args):
                             "0.4 m voxels), ncd128 decoder 11->64->1, Kc=81, K=6, brick index, "
                             f"{args.mode} eikonal gradient",
                 "samples_per_step": samples_per_step, "neural_points": int(npm.count()),
-                "mean_valid_candidates": mean_nn, "l2": "flushed (256 MiB write) before every timed step",
+                "mean_valid_candidates": mean_nn, "l2": "flushed before every timed step (256 MiB write, then 256 MiB read so evictions are clean)",
                 "parallelism": ("single GPU" if world == 1 else
                                 f"x{world}: samples sharded by map slab, one flat NCCL all-reduce "
                                 f"[decoder grads | loss | {int(shards.shared_rows.numel())} shared feature rows] per step"
@@ -326,6 +366,8 @@ def run_native(args):
                 "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_sample": b_kernel, "samples_per_launch": evals,
                 "kernel_ms_avg": fwd_avg_ms,
+                "timing": "CUDA events around the kernel in a call-by-call replay of the step (the timed region itself "
+                          "runs as one CUDA graph per step), same inputs and L2 flush",
                 "backward_kernel_ms_avg": statistics.mean(bwd_ms) if bwd_ms else None,
                 "inference_forward": {
                     "kernel": "query_forward_kernel<64,1,6,bricks> (sdf + grad, no side effects; the kernel the "

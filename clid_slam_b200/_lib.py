@@ -97,7 +97,7 @@ class ClidAdamArgs(C.Structure):
         ("dec_tensors", C.c_int32),
         ("dec_grad", C.c_void_p), ("dec_m", C.c_void_p), ("dec_v", C.c_void_p),
         ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-        ("weight_decay", C.c_float), ("step", C.c_int32),
+        ("weight_decay", C.c_float), ("step", C.c_int32), ("step_state", C.c_void_p),
     ]
 
 
@@ -123,6 +123,8 @@ _SIGNATURES = [
     ("clid_train_fused_scratch_bytes", C.c_size_t, [C.c_int64, C.c_int32]),
     ("clid_train_fused", C.c_int,
      [C.POINTER(ClidMap), C.POINTER(ClidDecoder), C.POINTER(ClidTrainFusedArgs), C.c_uint32, C.c_void_p]),
+    ("clid_decoder_grad_reduce", C.c_int,
+     [C.POINTER(ClidDecoder), C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p]),
     ("clid_adam_step", C.c_int, [C.POINTER(ClidAdamArgs), C.c_void_p]),
     ("clid_radius_search", C.c_int,
      [C.POINTER(ClidMap), C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -64,7 +64,9 @@ static int check_map(const ClidMap* m, uint32_t flags) {
     if (!m->bricks) return set_error(CLID_EINVAL, "CLID_USE_BRICKS without ClidMap.bricks");
     const ClidBricks* b = m->bricks;
     if (!b->headers || !b->records || !b->stencil) return set_error(CLID_EINVAL, "brick index arrays are NULL");
-    if (b->span < 1 || b->span > 2) return set_error(CLID_EUNSUPPORTED, "brick span %d outside 1..2", b->span);
+    if (b->span != 2 || b->apron < 1 || b->reach > 2)
+      return set_error(CLID_EUNSUPPORTED, "brick index must have span 2, a one-brick apron and reach <= 2 (span %d, apron %d, reach %d)",
+                       b->span, b->apron, b->reach);
     if (!aligned16(b->headers) || !aligned16(b->records)) return set_error(CLID_EINVAL, "brick arrays must be 16-byte aligned");
   } else {
     if (m->kc < 1 || m->kc > CLID_MAX_KC) return set_error(CLID_EINVAL, "kc %d outside 1..%d", m->kc, CLID_MAX_KC);
@@ -251,10 +253,6 @@ int clid_train_fused(const ClidMap* map, const ClidDecoder* dec, const ClidTrain
   }
   const bool have_scratch = a->scratch && a->scratch_bytes >= clid_train_fused_scratch_bytes(a->n, a->numerical);
   if (a->scratch && (reinterpret_cast<uintptr_t>(a->scratch) & 15u)) return set_error(CLID_EINVAL, "scratch must be 16-byte aligned");
-  DecoderGradParams g;
-  memset(&g, 0, sizeof(g));
-  g.dec = *dec; g.rows = static_cast<const float*>(a->scratch); g.dec_grad = p.dec_grad; g.flags = flags;
-  g.n_rows = (int64_t)(clid_train_fused_scratch_bytes(a->n, a->numerical) / (kFoldRow * sizeof(float)));
   if ((flags & CLID_TILE_KERNELS) && (flags & CLID_USE_BRICKS) && tile_supported(*map, *dec, *map->bricks) &&
       (!a->dec_grad || have_scratch)) {
     TileParams t;
@@ -265,24 +263,34 @@ int clid_train_fused(const ClidMap* map, const ClidDecoder* dec, const ClidTrain
     t.fold_rows = p.dec_grad ? static_cast<float*>(a->scratch) : nullptr;
     t.n = p.n; t.n_norm = p.n_norm; t.nd_norm = p.nd_norm;
     t.weight_e = p.weight_e; t.num_eps = p.num_eps; t.weighted = p.weighted; t.flags = flags;
-    if (int rc = launch_tile(t, a->numerical ? kTileTrainNumerical : kTileTrainAnalytic, static_cast<cudaStream_t>(stream))) return rc;
-    return p.dec_grad ? launch_decoder_grad(g, static_cast<cudaStream_t>(stream)) : CLID_OK;
+    return launch_tile(t, a->numerical ? kTileTrainNumerical : kTileTrainAnalytic, static_cast<cudaStream_t>(stream));
   }
   if (p.dec_grad && have_scratch) {
     // decoder-gradient rows go to scratch; a dense reduction kernel folds them afterwards
     p.fold_rows = static_cast<float*>(a->scratch);
-    if (int rc = (flags & CLID_USE_BRICKS) ? dispatch_train_fused_bricks(p, static_cast<cudaStream_t>(stream))
-                                            : dispatch_train_fused_hashed(p, static_cast<cudaStream_t>(stream)))
-      return rc;
-    return launch_decoder_grad(g, static_cast<cudaStream_t>(stream));
   }
   return (flags & CLID_USE_BRICKS) ? dispatch_train_fused_bricks(p, static_cast<cudaStream_t>(stream))
                                    : dispatch_train_fused_hashed(p, static_cast<cudaStream_t>(stream));
 }
 
+int clid_decoder_grad_reduce(const ClidDecoder* dec, const void* scratch, int64_t n, int32_t numerical, uint32_t flags,
+                             float* dec_grad, clid_stream_t stream) {
+  if (!dec || !dec_grad) return set_error(CLID_EINVAL, "dec/dec_grad is NULL");
+  if (n < 0) return set_error(CLID_EINVAL, "n = %lld", (long long)n);
+  if (n == 0) return CLID_OK;
+  if (!scratch || (reinterpret_cast<uintptr_t>(scratch) & 15u)) return set_error(CLID_EINVAL, "scratch is NULL or misaligned");
+  if (int rc = check_decoder(dec)) return rc;
+  DecoderGradParams g;
+  memset(&g, 0, sizeof(g));
+  g.dec = *dec; g.rows = static_cast<const float*>(scratch); g.dec_grad = dec_grad; g.flags = flags;
+  g.n_rows = (int64_t)(clid_train_fused_scratch_bytes(n, numerical) / (kFoldRow * sizeof(float)));
+  return launch_decoder_grad(g, static_cast<cudaStream_t>(stream));
+}
+
 int clid_adam_step(const ClidAdamArgs* a, clid_stream_t stream) {
   if (!a) return set_error(CLID_EINVAL, "args is NULL");
-  if (a->rows < 0 || a->step < 1) return set_error(CLID_EINVAL, "rows = %lld, step = %d", (long long)a->rows, a->step);
+  if (a->rows < 0 || (!a->step_state && a->step < 1))
+    return set_error(CLID_EINVAL, "rows = %lld, step = %d", (long long)a->rows, a->step);
   if (a->rows > 0 && (!a->feat || !a->feat_grad || !a->feat_m || !a->feat_v))
     return set_error(CLID_EINVAL, "feature buffers are NULL");
   if (a->rows > 0 && (!aligned16(a->feat) || !aligned16(a->feat_grad) || !aligned16(a->feat_m) || !aligned16(a->feat_v)))
@@ -299,11 +307,18 @@ int clid_adam_step(const ClidAdamArgs* a, clid_stream_t stream) {
   p.dec_tensors = a->dec_tensors;
   p.dec_grad = a->dec_grad; p.dec_m = a->dec_m; p.dec_v = a->dec_v;
   p.beta1 = a->beta1; p.beta2 = a->beta2; p.eps = a->eps; p.weight_decay = a->weight_decay;
-  // torch evaluates the bias corrections in double on the host (torch/optim/adam.py)
-  const double bc1 = 1.0 - pow((double)a->beta1, (double)a->step);
-  const double bc2 = 1.0 - pow((double)a->beta2, (double)a->step);
-  p.step_size = (float)((double)a->lr / bc1);
-  p.bc2_sqrt = (float)sqrt(bc2);
+  if (a->step_state) {
+    // device-resident step counter (graph-capturable): advance it, then read the scalars in the kernel
+    AdamStepState* st = static_cast<AdamStepState*>(a->step_state);
+    adam_advance_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(st, a->lr, a->beta1, a->beta2);
+    p.step_scalars = &st->step_size;
+  } else {
+    // torch evaluates the bias corrections in double on the host (torch/optim/adam.py)
+    const double bc1 = 1.0 - pow((double)a->beta1, (double)a->step);
+    const double bc2 = 1.0 - pow((double)a->beta2, (double)a->step);
+    p.step_size = (float)((double)a->lr / bc1);
+    p.bc2_sqrt = (float)sqrt(bc2);
+  }
   int grid = elementwise_grid(a->rows * 2 > 0 ? a->rows * 2 : 1, 256);
   adam_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();

@@ -42,27 +42,34 @@ struct TileScheduler {
   int64_t next_static;
   int64_t stride;
   int lane;
+  int ticket;  // dynamic: the ticket drawn for the NEXT call (valid in lane 0), fetched one tile ahead
   __device__ __forceinline__ TileScheduler(int32_t* counter_, int64_t n) : counter(counter_) {
     n_tiles = (n + 31) >> 5;
     lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     next_static = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     stride = (int64_t)gridDim.x * warps_per_block;
+    ticket = 0;
+    if (counter != nullptr) draw();
   }
-  // returns the tile index for this warp or -1 when the work is exhausted (warp-uniform)
+  __device__ __forceinline__ void draw() {
+    if (lane == 0) {
+      ticket = atomicAdd(counter, 1);
+      if ((int64_t)ticket == n_tiles + stride - 1) atomicExch(counter, 0);  // last ticket of the launch
+    }
+  }
+  // returns the tile index for this warp or -1 when the work is exhausted (warp-uniform).  The
+  // atomic for the following tile is issued here, so its round trip overlaps the tile's work.
   __device__ __forceinline__ int64_t next() {
     if (counter == nullptr) {
       const int64_t t = next_static;
       next_static += stride;
       return t < n_tiles ? t : -1;
     }
-    int t = 0;
-    if (lane == 0) {
-      t = atomicAdd(counter, 1);
-      if ((int64_t)t == n_tiles + stride - 1) atomicExch(counter, 0);  // last ticket of the launch
-    }
-    t = __shfl_sync(0xffffffffu, t, 0);
-    return t < n_tiles ? (int64_t)t : -1;
+    const int t = __shfl_sync(0xffffffffu, ticket, 0);
+    if ((int64_t)t >= n_tiles) return -1;  // every warp draws exactly one ticket past the end
+    draw();
+    return (int64_t)t;
   }
 };
 
@@ -86,13 +93,38 @@ struct MlpLayout {
 template <int H, int L>
 __device__ __forceinline__ void stage_decoder(float* sm, const ClidDecoder& dec) {
   using Lay = MlpLayout<H, L>;
-  for (int i = threadIdx.x; i < H * kInPad; i += blockDim.x) {
-    int j = i / kInPad, c = i - j * kInPad;
-    sm[Lay::kW0 + i] = c < kIn ? dec.weight[0][j * kIn + c] : 0.f;
+  // first layer: all loads of a thread are issued before its stores (one global round trip)
+  constexpr int kW = H * kIn;
+  constexpr int kMaxPer = (kW + 127) / 128;  // CTAs have at least 128 threads
+  float v[kMaxPer];
+#pragma unroll
+  for (int r = 0; r < kMaxPer; ++r) {
+    const int i = threadIdx.x + r * blockDim.x;
+    v[r] = i < kW ? __ldg(dec.weight[0] + i) : 0.f;
   }
-  for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    sm[Lay::kB0 + i] = dec.bias[0] ? dec.bias[0][i] : 0.f;
-    sm[Lay::kWout + i] = dec.out_weight[i];
+  float b = 0.f, wo = 0.f;
+  if (threadIdx.x < H) {
+    b = dec.bias[0] ? __ldg(dec.bias[0] + threadIdx.x) : 0.f;
+    wo = __ldg(dec.out_weight + threadIdx.x);
+  }
+#pragma unroll
+  for (int r = 0; r < kMaxPer; ++r) {
+    const int i = threadIdx.x + r * blockDim.x;
+    if (i < kW) {
+      const int j = i / kIn, c = i - j * kIn;
+      sm[Lay::kW0 + j * kInPad + c] = v[r];
+    }
+  }
+  for (int j = threadIdx.x; j < H; j += blockDim.x) sm[Lay::kW0 + j * kInPad + kIn] = 0.f;  // padding column
+  if (threadIdx.x < H) {
+    sm[Lay::kB0 + threadIdx.x] = b;
+    sm[Lay::kWout + threadIdx.x] = wo;
+  }
+  if (H > blockDim.x) {
+    for (int i = threadIdx.x + blockDim.x; i < H; i += blockDim.x) {
+      sm[Lay::kB0 + i] = dec.bias[0] ? dec.bias[0][i] : 0.f;
+      sm[Lay::kWout + i] = dec.out_weight[i];
+    }
   }
 #pragma unroll
   for (int l = 1; l < L; ++l) {

@@ -109,79 +109,83 @@ __device__ __forceinline__ int search_hashed(const ClidMap& m, const int64_t* __
 
 // ---- candidate enumeration through the brick index ---------------------------------------
 // Payload of the top-K: record index.  A 64-cell brick is walked as two 32-cell halves (z < 2,
-// z >= 2) so every bit operation is a single 32-bit instruction.
-// Phase 1 (warp-converged): load the <= 8 brick headers, AND with the stencil, compact the
-// non-empty (want, occupancy, first-record) half-brick triples into this thread's column of shared
-// memory and prefetch the 128-byte record lines they span towards L2.
-// Phase 2: every lane pops up to kWalkBatch candidates, issues their record loads together, then
-// ranks them; a warp iterates ceil(max-over-lanes(candidates) / kWalkBatch) times with all lanes
-// converged instead of diverging inside nested loops.
-// A neighbourhood is at most 5 cells wide (span <= 2, reach <= 2): 5 consecutive z cells touch at
-// most 3 of the 2-cell z halves, so at most 3 x 2 x 2 half-bricks can be non-empty.
+// z >= 2) so every bit operation is a single 32-bit instruction.  The grid carries a one-brick
+// empty apron (ClidBricks.apron) and a neighbourhood spans 2 x 2 x 2 bricks (span == 2): a query is
+// range-tested once, the eight header addresses follow by constant strides.
+// Phase 1: load the 8 brick headers, AND with the stencil, compact the non-empty (want, occupancy,
+// first-record) half-brick triples into this lane's scratch column (word s of the column is
+// col[s * kStride]: want in slots 0..11, occupancy in 12..23, first record in 24..35).
+// Phase 2 (warp-converged): every lane pops up to kWalkBatch candidates, issues their record loads
+// together, then ranks them; a warp iterates ceil(max-over-lanes(candidates) / kWalkBatch) times
+// instead of diverging inside nested loops.
+// A neighbourhood is at most 5 cells wide (reach <= 2): 5 consecutive z cells touch at most 3 of the
+// 2-cell z halves, so at most 3 x 2 x 2 half-bricks can be non-empty.
 constexpr int kHalfSlots = 12;
 #ifndef CLID_WALK_BATCH
 #define CLID_WALK_BATCH 4
 #endif
 constexpr int kWalkBatch = CLID_WALK_BATCH;
+#ifndef CLID_PF_RECORDS
+#define CLID_PF_RECORDS 1   // L2 prefetch of the record lines of every non-empty half-brick
+#endif
+#ifndef CLID_PF_FEATURES
+#define CLID_PF_FEATURES 1  // L2 prefetch of the feature row of every candidate that enters the top-K
+#endif
 
-struct BrickScratch {
+struct BrickScratch {  // [slot][thread] columns of a 128-thread CTA
   uint32_t want[kHalfSlots][kQueryThreads];
   uint32_t occ[kHalfSlots][kQueryThreads];
   int base[kHalfSlots][kQueryThreads];
 };
 
-template <int K>
-__device__ __forceinline__ int search_bricks(const ClidMap& m, const ClidBricks& b,
-                                             const uint64_t* __restrict__ stencil, BrickScratch& sc, bool live,
-                                             float px, float py, float pz, TopK<K>& top) {
-  const int tid = threadIdx.x;
-  // lower corner of the neighbourhood, in cells relative to the brick grid origin
+template <int K, int kStride>
+__device__ __forceinline__ int search_bricks(const ClidMap& m, const ClidBricks& b, const uint64_t* stencil,
+                                           uint32_t* col, bool live, float px, float py, float pz,
+                                           TopK<K>& top) {
   const int rx = cell_of(px, m.resolution) - b.origin[0] - b.reach;
   const int ry = cell_of(py, m.resolution) - b.origin[1] - b.reach;
   const int rz = cell_of(pz, m.resolution) - b.origin[2] - b.reach;
-  const int bx0 = rx >> 2, by0 = ry >> 2, bz0 = rz >> 2;  // arithmetic shifts: floor for negatives
-  const int span = b.span;
-  const int nslots = span * span * span;
-  const uint2* st = reinterpret_cast<const uint2*>(stencil) + (((rz & 3) * 4 + (ry & 3)) * 4 + (rx & 3)) * nslots;
-  const uint4* headers = reinterpret_cast<const uint4*>(b.headers);
+  const int bx0 = rx >> 2, by0 = ry >> 2, bz0 = rz >> 2;
+  const int D0 = b.dims[0], D1 = b.dims[1];
+  const bool in = live && (unsigned)bx0 < (unsigned)(D0 - 1) && (unsigned)by0 < (unsigned)(D1 - 1) &&
+                  (unsigned)bz0 < (unsigned)(b.dims[2] - 1);
   const float4* records = reinterpret_cast<const float4*>(b.records);
-
   int nfill = 0;
+  if (in) {
+    const uint2* st = reinterpret_cast<const uint2*>(stencil) + (((rz & 3) * 4 + (ry & 3)) * 4 + (rx & 3)) * 8;
+    const uint4* h0 = reinterpret_cast<const uint4*>(b.headers) + ((int64_t)bz0 * D1 + by0) * D0 + bx0;
+    const int sy = D0, sz = D0 * D1;
+    uint4 h[8];
 #pragma unroll
-  for (int s = 0; s < kBrickSlots; ++s) {
-    if (s < nslots) {
-      const int dx = s % span, dy = (s / span) % span, dz = s / (span * span);
-      const int bx = bx0 + dx, by = by0 + dy, bz = bz0 + dz;
-      const bool in = live && (unsigned)bx < (unsigned)b.dims[0] && (unsigned)by < (unsigned)b.dims[1] &&
-                      (unsigned)bz < (unsigned)b.dims[2];
-      uint4 h = make_uint4(0, 0, 0, 0);
-      if (in) h = __ldg(headers + ((int64_t)bz * b.dims[1] + by) * b.dims[0] + bx);
+    for (int s = 0; s < 8; ++s) h[s] = __ldg(h0 + (s & 1) + ((s >> 1) & 1) * sy + (s >> 2) * sz);
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
       const uint2 sten = st[s];
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        const uint32_t occ = half ? h.y : h.x;
+        const uint32_t occ = half ? h[s].y : h[s].x;
         const uint32_t want = occ & (half ? sten.y : sten.x);
         if (want) {
-          const int base = (int)h.z + (half ? __popc(h.x) : 0);
-          sc.want[nfill][tid] = want;
-          sc.occ[nfill][tid] = occ;
-          sc.base[nfill][tid] = base;
+          const int base = (int)h[s].z + (half ? __popc(h[s].x) : 0);
+          col[nfill * kStride] = want;
+          col[(kHalfSlots + nfill) * kStride] = occ;
+          col[(2 * kHalfSlots + nfill) * kStride] = (uint32_t)base;
           ++nfill;
-          // first and last wanted record of this half: pull their 128-byte lines towards L2 now,
-          // so the serial walk below does not pay a DRAM round trip per step
-          const int first = base + __popc(occ & ((want & (0u - want)) - 1u));
-          const int last = base + __popc(occ & ((0x80000000u >> __clz(want)) - 1u));
-          prefetch_l2(records + first);
-          if ((last >> 3) != (first >> 3)) prefetch_l2(records + last);
+          // the records of a half-brick are contiguous: pull their first and last line towards L2
+#if CLID_PF_RECORDS
+          prefetch_l2(records + base);
+          prefetch_l2(records + base + __popc(occ) - 1);
+#endif
         }
       }
     }
   }
-
-  int count = 0, cur = 0;
+  // cursor over the filled slots: a pointer into the lane's column and the number of slots left
+  int count = 0, left = nfill;
+  const uint32_t* sp = col;
   uint32_t w = 0, occ = 0;
   int base = 0;
-  if (nfill > 0) { w = sc.want[0][tid]; occ = sc.occ[0][tid]; base = sc.base[0][tid]; }
+  if (nfill > 0) { w = sp[0]; occ = sp[kHalfSlots * kStride]; base = (int)sp[2 * kHalfSlots * kStride]; }
   while (__any_sync(0xffffffffu, w != 0)) {
     int rec[kWalkBatch];
 #pragma unroll
@@ -191,9 +195,22 @@ __device__ __forceinline__ int search_bricks(const ClidMap& m, const ClidBricks&
         const int bit = __ffs(w) - 1;
         w &= w - 1;
         rec[j] = base + __popc(occ & ((1u << bit) - 1u));
-        if (w == 0 && ++cur < nfill) { w = sc.want[cur][tid]; occ = sc.occ[cur][tid]; base = sc.base[cur][tid]; }
+        if (w == 0 && left > 1) {
+          --left;
+          sp += kStride;
+          w = sp[0]; occ = sp[kHalfSlots * kStride]; base = (int)sp[2 * kHalfSlots * kStride];
+        }
       }
     }
+#ifdef CLID_TILE_DEBUG
+#pragma unroll
+    for (int j = 0; j < kWalkBatch; ++j)
+      if (rec[j] >= b.n_records && blockIdx.x < 3) {
+        printf("bad rec %d (n %d) blk %d thr %d nfill %d left %d base %d occ %08x w %08x in %d\n", rec[j], b.n_records, blockIdx.x,
+               threadIdx.x, nfill, left, base, occ, w, (int)in);
+        rec[j] = -1;
+      }
+#endif
     float4 r[kWalkBatch];
 #pragma unroll
     for (int j = 0; j < kWalkBatch; ++j) r[j] = __ldg(records + (rec[j] < 0 ? 0 : rec[j]));
@@ -203,7 +220,9 @@ __device__ __forceinline__ int search_bricks(const ClidMap& m, const ClidBricks&
       if (rec[j] >= 0 && !(d2 > m.max_valid_dist2)) {
         ++count;
         if (d2 < top.d[K - 1]) {
+#if CLID_PF_FEATURES
           prefetch_l2(m.gather_features + (int64_t)__float_as_int(r[j].w) * kFeat);  // likely neighbour
+#endif
           top.insert(d2, rec[j]);
         }
       }
@@ -224,8 +243,10 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
 
   if constexpr (H > 0) stage_decoder<H, L>(sm_dec, p.dec);
   if constexpr (kBricks) {
-    const int n_st = 64 * p.bricks.span * p.bricks.span * p.bricks.span;
-    for (int i = threadIdx.x; i < n_st; i += blockDim.x) stencil[i] = p.bricks.stencil[i];
+    const uint4* st_src = reinterpret_cast<const uint4*>(p.bricks.stencil);
+    uint4* st_dst = reinterpret_cast<uint4*>(stencil);
+#pragma unroll
+    for (int i = threadIdx.x; i < 64 * kBrickSlots / 2; i += kQueryThreads) st_dst[i] = __ldg(st_src + i);
   } else {
     for (int c = threadIdx.x; c < m.kc; c += blockDim.x) {
       int64_t h = m.neighbor_dx[3 * c] * m.primes[0] + m.neighbor_dx[3 * c + 1] * m.primes[1] +
@@ -252,7 +273,7 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
     TopK<K> top;
     top.init();
     int count = 0;
-    if constexpr (kBricks) count = search_bricks<K>(m, p.bricks, stencil, scratch, live, px, py, pz, top);
+    if constexpr (kBricks) count = search_bricks<K, kQueryThreads>(m, p.bricks, stencil, &scratch.want[0][threadIdx.x], live, px, py, pz, top);
     else if (live) count = search_hashed<K>(m, cell_mod, px, py, pz, local, time_filter, top);
     if (!live) continue;
 

@@ -209,18 +209,6 @@ __global__ void pack_decoder_kernel(const ClidDecoder dec, float* __restrict__ d
 }
 #endif
 
-// Candidate search through the brick index (see search_bricks in query_fwd.cuh) for grids that
-// carry a one-brick empty apron: one range test per query instead of one per brick, header
-// addresses by constant strides, scratch columns in the warp's park slice.
-// col = this lane's column: word s of the column is col[s * 32].
-#ifndef CLID_TILE_PF_REC
-#define CLID_TILE_PF_REC 0   // L2 prefetch of the record lines of every non-empty half-brick
-#endif
-#ifndef CLID_TILE_PF_FEAT
-#define CLID_TILE_PF_FEAT 0  // L2 prefetch of the feature row of every candidate that enters the top-K
-#endif
-constexpr int kTileHalfSlots = 12;
-
 // one 32-byte feature row with a single 256-bit load (LDG.E.256, sm_100+): one L1 wavefront per
 // lane instead of two
 __device__ __forceinline__ void load_feature_row256(const float* __restrict__ feats, int id, float (&f)[kFeat]) {
@@ -229,99 +217,6 @@ __device__ __forceinline__ void load_feature_row256(const float* __restrict__ fe
                : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7])
                : "l"(p));
 }
-template <int K>
-__device__ __forceinline__ int tile_search(const ClidMap& m, const ClidBricks& b, const uint64_t* stencil,
-                                           uint32_t* col, bool live, float px, float py, float pz,
-                                           TopK<K>& top) {
-  const int rx = cell_of(px, m.resolution) - b.origin[0] - b.reach;
-  const int ry = cell_of(py, m.resolution) - b.origin[1] - b.reach;
-  const int rz = cell_of(pz, m.resolution) - b.origin[2] - b.reach;
-  const int bx0 = rx >> 2, by0 = ry >> 2, bz0 = rz >> 2;
-  const int D0 = b.dims[0], D1 = b.dims[1];
-  const bool in = live && (unsigned)bx0 < (unsigned)(D0 - 1) && (unsigned)by0 < (unsigned)(D1 - 1) &&
-                  (unsigned)bz0 < (unsigned)(b.dims[2] - 1);
-  const float4* records = reinterpret_cast<const float4*>(b.records);
-  int nfill = 0;
-  if (in) {
-    const uint2* st = reinterpret_cast<const uint2*>(stencil) + (((rz & 3) * 4 + (ry & 3)) * 4 + (rx & 3)) * 8;
-    const uint4* h0 = reinterpret_cast<const uint4*>(b.headers) + ((int64_t)bz0 * D1 + by0) * D0 + bx0;
-    const int sy = D0, sz = D0 * D1;
-    uint4 h[8];
-#pragma unroll
-    for (int s = 0; s < 8; ++s) h[s] = __ldg(h0 + (s & 1) + ((s >> 1) & 1) * sy + (s >> 2) * sz);
-#pragma unroll
-    for (int s = 0; s < 8; ++s) {
-      const uint2 sten = st[s];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const uint32_t occ = half ? h[s].y : h[s].x;
-        const uint32_t want = occ & (half ? sten.y : sten.x);
-        if (want) {
-          const int base = (int)h[s].z + (half ? __popc(h[s].x) : 0);
-          col[nfill * 32] = want;
-          col[(kTileHalfSlots + nfill) * 32] = occ;
-          col[(2 * kTileHalfSlots + nfill) * 32] = (uint32_t)base;
-          ++nfill;
-          // the records of a half-brick are contiguous: pull their first and last line towards L2
-#if CLID_TILE_PF_REC
-          prefetch_l2(records + base);
-          prefetch_l2(records + base + __popc(occ) - 1);
-#endif
-        }
-      }
-    }
-  }
-  // cursor over the filled slots: a pointer into the lane's column and the number of slots left
-  int count = 0, left = nfill;
-  const uint32_t* sp = col;
-  uint32_t w = 0, occ = 0;
-  int base = 0;
-  if (nfill > 0) { w = sp[0]; occ = sp[kTileHalfSlots * 32]; base = (int)sp[2 * kTileHalfSlots * 32]; }
-  while (__any_sync(0xffffffffu, w != 0)) {
-    int rec[kWalkBatch];
-#pragma unroll
-    for (int j = 0; j < kWalkBatch; ++j) {
-      rec[j] = -1;
-      if (w) {
-        const int bit = __ffs(w) - 1;
-        w &= w - 1;
-        rec[j] = base + __popc(occ & ((1u << bit) - 1u));
-        if (w == 0 && left > 1) {
-          --left;
-          sp += 32;
-          w = sp[0]; occ = sp[kTileHalfSlots * 32]; base = (int)sp[2 * kTileHalfSlots * 32];
-        }
-      }
-    }
-#ifdef CLID_TILE_DEBUG
-#pragma unroll
-    for (int j = 0; j < kWalkBatch; ++j)
-      if (rec[j] >= b.n_records && blockIdx.x < 3) {
-        printf("bad rec %d (n %d) blk %d thr %d nfill %d left %d base %d occ %08x w %08x in %d\n", rec[j], b.n_records, blockIdx.x,
-               threadIdx.x, nfill, left, base, occ, w, (int)in);
-        rec[j] = -1;
-      }
-#endif
-    float4 r[kWalkBatch];
-#pragma unroll
-    for (int j = 0; j < kWalkBatch; ++j) r[j] = __ldg(records + (rec[j] < 0 ? 0 : rec[j]));
-#pragma unroll
-    for (int j = 0; j < kWalkBatch; ++j) {
-      const float d2 = dist2_torch(r[j].x - px, r[j].y - py, r[j].z - pz);
-      if (rec[j] >= 0 && !(d2 > m.max_valid_dist2)) {
-        ++count;
-        if (d2 < top.d[K - 1]) {
-#if CLID_TILE_PF_FEAT
-          prefetch_l2(m.gather_features + (int64_t)__float_as_int(r[j].w) * kFeat);  // likely neighbour
-#endif
-          top.insert(d2, rec[j]);
-        }
-      }
-    }
-  }
-  return count;
-}
-
 template <int H, int K, int kMode>
 __global__ void __launch_bounds__(kTileThreads, kTileBlocksPerSm) sdf_tile_kernel(const __grid_constant__ TileParams p) {
   using Lay = TileDec<H>;
@@ -385,7 +280,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileBlocksPerSm) sdf_tile_kerne
     // ---- search
     TopK<K> top;
     top.init();
-    const int count = tile_search<K>(m, p.bricks, stencil, col, live, px, py, pz, top);
+    const int count = search_bricks<K, 32>(m, p.bricks, stencil, col, live, px, py, pz, top);
     __syncwarp();  // the scratch columns are re-used as the park slice below
 
     // ---- blend, pass A: neighbour records -> offsets, weights, side effects, positional moments
@@ -766,10 +661,6 @@ __global__ void __launch_bounds__(DgSmem<H>::kWarps * 32, 1) decoder_grad_kernel
   if (lane == 0) sm_delta[warp] = dsum;
   __syncthreads();
   // element (j, i) of the CTA's Gd: one thread each sums the kDgWarps partials, then forms its outputs
-  float* gW0 = p.dec_grad;
-  float* gb0 = gW0 + H * kIn;
-  float* gwout = gb0 + H;
-  float* gbout = gwout + H;
   for (int e = threadIdx.x; e < H * kInPad; e += blockDim.x) {
     float v = 0.f;
 #pragma unroll 8
@@ -777,24 +668,29 @@ __global__ void __launch_bounds__(DgSmem<H>::kWarps * 32, 1) decoder_grad_kernel
     sm_gd[e] = v;  // only this thread reads and writes column e of the partials
   }
   __syncthreads();
-  for (int j0 = threadIdx.x; j0 < H; j0 += blockDim.x) {
-    const int j = (j0 + blockIdx.x) % H;  // blocks start at different rows: spreads same-address atomics in time
+  // outputs in the flat dec_grad order, staged in shared memory so the atomics below are coalesced
+  // (32 consecutive floats per instruction = 4 sectors, instead of 32 sectors with the row stride)
+  float* sm_out = sm_rows;  // the staged rows are dead
+  for (int e = threadIdx.x; e < H * kIn; e += blockDim.x) {
+    const int j = e / kIn, i = e - j * kIn;
+    sm_out[e] = __ldg(p.dec.out_weight + j) * sm_gd[j * kInPad + i];
+  }
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
     const float* g = sm_gd + j * kInPad;
-    const float wout = __ldg(p.dec.out_weight + j);
     float dw = p.dec.bias[0] ? __ldg(p.dec.bias[0] + j) * g[kIn] : 0.f;
 #pragma unroll
-    for (int i = 0; i < kIn; ++i) {
-      atomicAdd(gW0 + j * kIn + i, wout * g[i]);
-      dw = fmaf(__ldg(p.dec.weight[0] + j * kIn + i), g[i], dw);
-    }
-    if (p.dec.bias[0]) atomicAdd(gb0 + j, wout * g[kIn]);
-    atomicAdd(gwout + j, dw);
+    for (int i = 0; i < kIn; ++i) dw = fmaf(__ldg(p.dec.weight[0] + j * kIn + i), g[i], dw);
+    sm_out[H * kIn + j] = p.dec.bias[0] ? __ldg(p.dec.out_weight + j) * g[kIn] : 0.f;
+    sm_out[H * kIn + H + j] = dw;
   }
-  if (threadIdx.x == 0 && p.dec.out_bias) {
+  if (threadIdx.x == 0) {
     float d = 0.f;
     for (int w = 0; w < kDgWarps; ++w) d += sm_delta[w];
-    atomicAdd(gbout, d);
+    sm_out[H * kIn + 2 * H] = p.dec.out_bias ? d : 0.f;
   }
+  __syncthreads();
+  constexpr int kOut = H * kIn + 2 * H + 1;
+  for (int e = threadIdx.x; e < kOut; e += blockDim.x) atomicAdd(p.dec_grad + e, sm_out[e]);
 }
 
 }  // namespace clid

@@ -334,6 +334,15 @@ struct AdamParams {
   float beta1, beta2, eps, weight_decay;
   float step_size;        // lr / (1 - beta1^t)
   float bc2_sqrt;         // sqrt(1 - beta2^t)
+  const float* step_scalars;  // device {step_size, bc2_sqrt} (ClidAdamArgs.step_state + 4) or NULL
+};
+
+// ClidAdamArgs.step_state: the optimiser's step counter and the two scalars derived from it
+struct AdamStepState {
+  int32_t step;
+  float step_size;
+  float bc2_sqrt;
+  int32_t pad;
 };
 
 __device__ __forceinline__ float adam_update(float p, float g, float& mm, float& vv, const AdamParams& a) {
@@ -344,7 +353,22 @@ __device__ __forceinline__ float adam_update(float p, float g, float& mm, float&
 }
 
 #ifdef CLID_PLAIN_KERNELS
-__global__ void __launch_bounds__(256) adam_kernel(const AdamParams a) {
+// step += 1; bias corrections in double, as torch/optim/adam.py evaluates them on the host
+__global__ void adam_advance_kernel(AdamStepState* st, float lr, float beta1, float beta2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const int t = st->step + 1;
+    st->step = t;
+    const double bc1 = 1.0 - pow((double)beta1, (double)t);
+    const double bc2 = 1.0 - pow((double)beta2, (double)t);
+    st->step_size = (float)((double)lr / bc1);
+    st->bc2_sqrt = (float)sqrt(bc2);
+  }
+}
+#endif
+
+#ifdef CLID_PLAIN_KERNELS
+__global__ void __launch_bounds__(256) adam_kernel(AdamParams a) {
+  if (a.step_scalars) { a.step_size = a.step_scalars[0]; a.bc2_sqrt = a.step_scalars[1]; }
   // feature rows: one thread per float4 half-row
   const int64_t halves = a.rows * 2;
   for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h < halves; h += (int64_t)gridDim.x * blockDim.x) {

@@ -79,8 +79,10 @@ __global__ void __launch_bounds__(kFusedThreads, 4) train_fused_l1_kernel(const 
   const ClidMap& m = p.map;
   stage_decoder<H, 1>(sm_dec, p.dec);
   if constexpr (kBricks) {
-    const int n_st = 64 * p.bricks.span * p.bricks.span * p.bricks.span;
-    for (int i = threadIdx.x; i < n_st; i += blockDim.x) stencil[i] = p.bricks.stencil[i];
+    const uint4* st_src = reinterpret_cast<const uint4*>(p.bricks.stencil);
+    uint4* st_dst = reinterpret_cast<uint4*>(stencil);
+#pragma unroll
+    for (int i = threadIdx.x; i < 64 * kBrickSlots / 2; i += kFusedThreads) st_dst[i] = __ldg(st_src + i);
   } else {
     for (int c = threadIdx.x; c < m.kc; c += blockDim.x) {
       int64_t h = m.neighbor_dx[3 * c] * m.primes[0] + m.neighbor_dx[3 * c + 1] * m.primes[1] +
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(kFusedThreads, 4) train_fused_l1_kernel(const 
     TopK<K> top;
     top.init();
     int count = 0;
-    if constexpr (kBricks) count = search_bricks<K>(m, p.bricks, stencil, scratch, live, px, py, pz, top);
+    if constexpr (kBricks) count = search_bricks<K, kQueryThreads>(m, p.bricks, stencil, &scratch.want[0][threadIdx.x], live, px, py, pz, top);
     else if (live) count = search_hashed<K>(m, cell_mod, px, py, pz, local, time_filter, top);
 
     float c[kInPad];

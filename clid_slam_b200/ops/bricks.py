@@ -106,7 +106,7 @@ def build(npm, query_locally: bool) -> Optional[BrickIndex]:
     offsets_cpu = npm.neighbor_dx.detach().cpu()
     reach = int(offsets_cpu.abs().max().item()) if offsets_cpu.numel() else 0
     span = (2 * reach + 7) // 4
-    if span > 2 or npm.count() == 0:  # the kernel walks at most 2x2x2 bricks (num_nei_cells <= 2)
+    if span != 2 or npm.count() == 0:  # the kernels walk exactly 2x2x2 bricks (num_nei_cells 1 or 2)
         return None
     if not hash_is_alias_free(int(npm.buffer_size), reach):
         return None

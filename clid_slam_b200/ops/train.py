@@ -92,6 +92,9 @@ class FusedTrainer:
         self.single_kernel = True
         self._scratch = None        # device scratch of clid_train_fused (rows for the decoder-gradient reduction)
         self.use_scratch = True     # False: the warps fold the decoder gradients inside the one kernel
+        # device-resident Adam step counter {step, step_size, bc2_sqrt, pad} (ClidAdamArgs.step_state):
+        # lets a whole iteration be captured in a CUDA graph (StepPipeline); None = host-side counter
+        self.step_state = None
 
     # ------------------------------------------------------------------
     def _shifted(self, x: torch.Tensor, eik_index: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -238,6 +241,13 @@ class FusedTrainer:
             ev1.record()
             self.forward_events.append((ev0, ev1))
         self.launches += 1 if n > 0 else 0
+        if a.scratch and n > 0:
+            # the per-point decoder-gradient rows sit in scratch: dense reduction into dec_grad
+            with torch.cuda.device(dev):
+                rc = lib.clid_decoder_grad_reduce(C.byref(ds), a.scratch, n, a.numerical, flags, self.dec_grad.data_ptr(),
+                                                  _lib.current_stream(dev))
+            _lib.check(rc, "clid_decoder_grad_reduce")
+            self.launches += 1
         return loss
 
     def _finish_iteration(self, loss, apply_step, sync, shards):
@@ -312,5 +322,121 @@ class FusedTrainer:
                 aa.dec_grad, aa.dec_m, aa.dec_v = self.dec_grad.data_ptr(), self.dec_m.data_ptr(), self.dec_v.data_ptr()
             aa.lr, aa.beta1, aa.beta2 = float(cfg.lr), 0.9, 0.99
             aa.eps, aa.weight_decay, aa.step = float(cfg.adam_eps), float(cfg.weight_decay), self.step
+            aa.step_state = None if self.step_state is None else self.step_state.data_ptr()
             _lib.check(lib.clid_adam_step(C.byref(aa), stream), "clid_adam_step")
             self.launches += 1
+
+
+class StepPipeline:
+    """Steady-state driver of a FusedTrainer for fixed-size batches.
+
+    The whole iteration (loss clear, fused forward + loss + backward, decoder-gradient reduction,
+    Adam) is captured ONCE in a CUDA graph per input buffer and replayed, so a step costs one graph
+    launch on the host instead of ~10 Python/ctypes calls.  Batches that live on the host are staged
+    through two device buffers on a copy stream: while step i runs, batch i + 1 is already crossing
+    PCIe.  The optimiser's step counter lives on the device (ClidAdamArgs.step_state).
+
+        pipe = StepPipeline(trainer, n)
+        pipe.stage(0, host_batch0)                 # pinned (x, label, weight, ts)
+        for i in range(steps):
+            pipe.stage((i + 1) % 2, host_batch[i + 1])
+            loss = pipe.run(i % 2)                 # device tensor [3]; .cpu() to read it
+    """
+
+    def __init__(self, trainer: FusedTrainer, n: int, n_global: int = 0, nd_global: int = 0, with_ts: bool = True,
+                 buffers=None):
+        """buffers: optional list of caller-owned device batches (x [n,3] f32, label [n] f32, weight [n]
+        f32, ts [n] i32 | None) to capture on directly (no staging copies); default: two staging buffers."""
+        if trainer.step != 0 and trainer.step_state is None:
+            raise RuntimeError("StepPipeline must own the optimiser from its first step")
+        self.trainer, self.n = trainer, int(n)
+        dev = trainer.device
+        self.device = dev
+        if trainer.step_state is None:
+            trainer.step_state = torch.zeros(4, dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        if buffers is not None:
+            self.bufs = [tuple(b) for b in buffers]
+            for x, label, weight, ts in self.bufs:
+                if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == (n, 3)
+                        and label.dtype == torch.float32 and weight.dtype == torch.float32
+                        and (ts is None or ts.dtype == torch.int32)):
+                    raise ValueError("buffers must be contiguous device tensors: x [n,3] f32, label/weight [n] f32, ts [n] i32")
+        else:
+            self.bufs = []
+            for _ in range(2):
+                self.bufs.append((torch.zeros(n, 3, **f32), torch.zeros(n, **f32), torch.zeros(n, **f32),
+                                  torch.zeros(n, dtype=torch.int32, device=dev) if with_ts else None))
+        nb = len(self.bufs)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ready = [torch.cuda.Event() for _ in range(nb)]   # buffer k holds a staged batch
+        self.free = [torch.cuda.Event() for _ in range(nb)]    # the step that read buffer k has finished
+        self.graphs, self.losses = [], []
+        trainer.npm.brick_index(True)  # build the index outside the capture
+        # warm-up on a side stream (first launches configure kernel attributes), then capture
+        state = self._snapshot()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self._iteration(0, n_global, nd_global)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        for k in range(nb):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                loss = self._iteration(k, n_global, nd_global)
+            self.graphs.append(g)
+            self.losses.append(loss)
+        torch.cuda.synchronize(dev)
+        self._restore(state)  # the warm-up iteration must not count
+        for k in range(nb):
+            self.free[k].record(torch.cuda.current_stream(dev))
+            self.ready[k].record(torch.cuda.current_stream(dev))  # caller-owned buffers are ready as they are
+
+    def _iteration(self, k, n_global, nd_global):
+        x, label, weight, ts = self.bufs[k]
+        return self.trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global)
+
+    def _snapshot(self):
+        t = self.trainer
+        npm = t.npm
+        tensors = [npm.local_geo_features.data, npm.local_point_certainties, npm.local_point_ts_update, t.feat_grad, t.feat_m,
+                   t.feat_v, t.step_state] + [p.data for p in t.dec_tensors if p is not None]
+        for extra in (t.touched, t.dec_grad, t.dec_m, t.dec_v):
+            if extra is not None:
+                tensors.append(extra)
+        return [(x, x.clone()) for x in tensors], t.step, len(t.losses), t.launches
+
+    def _restore(self, state):
+        pairs, step, n_losses, launches = state
+        for live, saved in pairs:
+            live.copy_(saved)
+        t = self.trainer
+        t.step = step
+        del t.losses[n_losses:]
+        t.launches = launches
+
+    def stage(self, k: int, batch) -> None:
+        """Copy a batch (x, label, weight, ts), host-pinned or device, into input buffer k on the copy stream."""
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[k])
+            for dst, src in zip(self.bufs[k], batch):
+                if dst is not None:
+                    dst.copy_(src, non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+
+    def run(self, k: int) -> torch.Tensor:
+        """Replay the iteration on input buffer k (after its staged batch has arrived)."""
+        stream = torch.cuda.current_stream(self.device)
+        stream.wait_event(self.ready[k])
+        self.graphs[k].replay()
+        self.free[k].record(stream)
+        t = self.trainer
+        t.step += 1
+        t.launches += self.launches_per_step
+        return self.losses[k]
+
+    @property
+    def launches_per_step(self) -> int:
+        # fused kernel [+ decoder-gradient reduction] + Adam advance + Adam
+        return 3 + (1 if self.trainer.dec_grad is not None else 0)

@@ -251,15 +251,23 @@ typedef struct ClidTrainFusedArgs {
   float* sdf_out;        /* [n] or NULL */
   void* scratch;         /* clid_train_fused_scratch_bytes(n, numerical) bytes of device scratch, or NULL.
                             With it every evaluated point writes its 64-byte decoder-gradient row
-                            [delta z + s tau ; delta | activation bits] there and a second, dense kernel
-                            reduces the rows into dec_grad (2 launches); without it the warps fold the
-                            rows themselves inside the one kernel (slower).  Unused when dec_grad == NULL. */
+                            [delta z + s tau ; delta | activation bits] there and the caller reduces the
+                            rows into dec_grad with clid_decoder_grad_reduce afterwards (dec_grad is not
+                            touched by this call); without it the warps fold the rows themselves inside
+                            the one kernel (slower).  Unused when dec_grad == NULL.                    */
   size_t scratch_bytes;
 } ClidTrainFusedArgs;
 /* Device scratch clid_train_fused wants for n samples (64 bytes per evaluated point, 16-byte aligned). */
 CLID_API size_t clid_train_fused_scratch_bytes(int64_t n, int32_t numerical);
 CLID_API int clid_train_fused(const ClidMap* map, const ClidDecoder* dec, const ClidTrainFusedArgs* args,
                               uint32_t flags, clid_stream_t stream);
+
+/* Second half of clid_train_fused when it was given scratch: the dense reduction of the per-point rows
+ *   Gd[j][i'] = sum_n act'(pre_nj) c'_ni'  ->  dW0 = wout (.) Gd, db0, dwout, dbout
+ * (the decoder part of cur_loss.backward(), utils/mapper.py:834-835) accumulated into the flat
+ * dec_grad [W0 (HxD), b0 (H), wout (H), bout (1)].  n / numerical as passed to clid_train_fused. */
+CLID_API int clid_decoder_grad_reduce(const ClidDecoder* dec, const void* scratch, int64_t n, int32_t numerical,
+                                      uint32_t flags, float* dec_grad, clid_stream_t stream);
 
 /* torch.optim.Adam step (utils/tools.py:205-255: betas (0.9, 0.99), eps adam_eps) on the touched
  * neural-point feature rows and on the decoder tensors; applied gradients are re-zeroed.
@@ -280,6 +288,12 @@ typedef struct ClidAdamArgs {
   float* dec_v;
   float lr, beta1, beta2, eps, weight_decay;
   int32_t step;            /* 1-based, shared by every parameter like torch's per-call optimiser */
+  void* step_state;        /* NULL, or 16 bytes of device memory {int32 step; float step_size; float
+                              bc2_sqrt; pad} owned by the caller and zero-initialised when the optimiser
+                              is created.  With it the step counter lives on the device: the call first
+                              advances it (a one-thread kernel evaluates the bias corrections in double,
+                              like torch does on the host) and `step` is ignored -- so a whole iteration
+                              can be captured once in a CUDA graph and replayed.                       */
 } ClidAdamArgs;
 CLID_API int clid_adam_step(const ClidAdamArgs* args, clid_stream_t stream);
 
