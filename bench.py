@@ -222,12 +222,15 @@ def run_native(args):
             torch.cuda.synchronize()
 
     multi = world > 1
-    if not multi:
-        # single GPU: the iteration is one CUDA graph per input buffer (ops/train.py StepPipeline)
+    graphed = os.environ.get("CLID_BENCH_NO_GRAPH", "0") != "1"
+    if graphed:
+        # the iteration (and, for N > 1, the NCCL all-reduce inside it) is one CUDA graph per input
+        # buffer (ops/train.py StepPipeline)
         from clid_slam_b200.ops.train import StepPipeline
 
-        pipe_dev = StepPipeline(trainer, BATCH, n_global=n_global, nd_global=nd_global, buffers=batches)
-        pipe_host = StepPipeline(trainer, BATCH, n_global=n_global, nd_global=nd_global)
+        kw = dict(n_global=n_global, nd_global=nd_global, shards=shards, sync=multi and shards is None)
+        pipe_dev = StepPipeline(trainer, BATCH, buffers=batches, **kw)
+        pipe_host = StepPipeline(trainer, BATCH, **kw)
 
         def step(i):
             return pipe_dev.run(i % n_batches)
@@ -235,7 +238,7 @@ def run_native(args):
         def step(i):
             x, label, weight, ts = batches[i % n_batches]
             return trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global,
-                                     sync=shards is None, shards=shards)
+                                     sync=multi and shards is None, shards=shards)
 
     for i in range(max(args.warmup, 3)):
         flush.zero_()
@@ -266,13 +269,13 @@ def run_native(args):
     # Single GPU: batch i + 1 crosses PCIe on the copy stream while step i runs (StepPipeline).
     e2e_events = []
     sync_all()
-    if not multi:
+    if graphed:
         pipe_host.stage(0, host_batches[0])
     for i in range(args.steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        if not multi:
+        if graphed:
             pipe_host.stage((i + 1) % 2, host_batches[(i + 1) % n_batches])
             loss = pipe_host.run(i % 2)
         else:

@@ -63,6 +63,11 @@ class FusedTrainer:
         self.feat_v = torch.zeros_like(feats.data)
         self.dense = float(config.weight_decay) != 0.0
         self.touched = None if self.dense else torch.zeros(rows, dtype=torch.uint8, device=dev)
+        # The touched flags only save traffic: dense Adam is the identity on a row whose g = m = v = 0, so
+        # once the gathers of this mapping() call can have covered the table a couple of times the flags
+        # are dropped (no more scattered flag stores in the kernels, no flag reads in Adam).
+        self._gathers = 0
+        self.dense_switch = 2.0     # switch when gathers so far > dense_switch * rows
         self.train_features = bool(feats.requires_grad)
 
         self.dec_tensors = decoder.flat_parameters()
@@ -110,7 +115,7 @@ class FusedTrainer:
 
     def iteration(self, x: torch.Tensor, label: torch.Tensor, ts: Optional[torch.Tensor], weight: torch.Tensor,
                   apply_step: bool = True, n_global: int = 0, nd_global: int = 0, sync: bool = False,
-                  shards=None, eik_index: Optional[torch.Tensor] = None):
+                  shards=None, eik_index: Optional[torch.Tensor] = None, exchange: bool = True):
         """One mapping iteration on the batch.  With apply_step=False the optimiser step is left to
         a later `adam_step()` call, so the accumulated gradients can be inspected (tests).
 
@@ -123,11 +128,19 @@ class FusedTrainer:
         if n == 0 and not sync and shards is None:
             return
         numerical = self.numerical and self.weight_e > 0
+        self._gathers += n * int(cfg.query_nn_k)
+        if self.touched is not None and shards is None and self._gathers > self.dense_switch * self.rows:
+            # dense from here on (exact, see __init__).  Not with spatial shards: a rank only ever touches
+            # the rows of its slab, and the flags keep its Adam step off the other (N-1)/N of the table.
+            self.touched = None
         # the one-kernel numerical mode evaluates the x[::10] subset inside the warp tiles; explicit
         # subsets (eik_index, sharded batches) and other decimations take the three-launch path
         one_kernel_ok = (not numerical) or (int(cfg.gradient_decimation) == 10 and eik_index is None)
         if self.single_kernel and one_kernel_ok:
             loss = self._iteration_single_kernel(x, label, ts, weight, n_global, nd_global, numerical)
+            if not exchange:  # the caller runs pack / all-reduce / unpack / adam_step itself (StepPipeline)
+                self.losses.append(loss)
+                return loss
             return self._finish_iteration(loss, apply_step, sync, shards)
         nd = 0
         x_all, ts_all = x, ts
@@ -262,7 +275,8 @@ class FusedTrainer:
             _dist.FlatAllReduce([self.dec_grad, loss])()
             if self.train_features:
                 _dist.all_reduce_sum(self.feat_grad)
-                _dist.all_reduce_max(self.touched)
+                if self.touched is not None:
+                    _dist.all_reduce_max(self.touched)
         self.losses.append(loss)
         if apply_step:
             self.adam_step()
@@ -344,16 +358,24 @@ class StepPipeline:
     """
 
     def __init__(self, trainer: FusedTrainer, n: int, n_global: int = 0, nd_global: int = 0, with_ts: bool = True,
-                 buffers=None):
+                 buffers=None, shards=None, sync: bool = False):
         """buffers: optional list of caller-owned device batches (x [n,3] f32, label [n] f32, weight [n]
         f32, ts [n] i32 | None) to capture on directly (no staging copies); default: two staging buffers."""
         if trainer.step != 0 and trainer.step_state is None:
             raise RuntimeError("StepPipeline must own the optimiser from its first step")
         self.trainer, self.n = trainer, int(n)
         dev = trainer.device
+        if shards is None and trainer.touched is not None and 2 * n * int(trainer.cfg.query_nn_k) >= trainer.rows:
+            trainer.touched = None  # a replayed graph cannot switch later: large batches run dense from the start
         self.device = dev
         if trainer.step_state is None:
             trainer.step_state = torch.zeros(4, dtype=torch.int32, device=dev)
+        # multi-GPU (spatial shards): two graphs per buffer with the ONE NCCL all-reduce of the step launched
+        # eagerly between them -- [kernels, pack] | all-reduce(flat) | [unpack, Adam]
+        if sync and shards is None:
+            raise NotImplementedError("StepPipeline covers single-GPU and spatially sharded steps; the replicated "
+                                      "sharding (dense feature-gradient all-reduce) runs call by call")
+        self.shards = shards
         f32 = dict(dtype=torch.float32, device=dev)
         if buffers is not None:
             self.bufs = [tuple(b) for b in buffers]
@@ -378,15 +400,27 @@ class StepPipeline:
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            self._iteration(0, n_global, nd_global)
+            warm_loss = self._iteration(0, n_global, nd_global)
+            if shards is not None:
+                trainer.unpack_spatial(trainer.pack_spatial(warm_loss, shards), warm_loss, shards)
+                trainer.adam_step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        self.flats, self.post_graphs = [], []
         for k in range(nb):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 loss = self._iteration(k, n_global, nd_global)
+                flat = trainer.pack_spatial(loss, shards) if shards is not None else None
             self.graphs.append(g)
             self.losses.append(loss)
+            self.flats.append(flat)
+            if shards is not None:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2):
+                    trainer.unpack_spatial(flat, loss, shards)
+                    trainer.adam_step()
+                self.post_graphs.append(g2)
         torch.cuda.synchronize(dev)
         self._restore(state)  # the warm-up iteration must not count
         for k in range(nb):
@@ -395,7 +429,9 @@ class StepPipeline:
 
     def _iteration(self, k, n_global, nd_global):
         x, label, weight, ts = self.bufs[k]
-        return self.trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global)
+        if self.shards is None:
+            return self.trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global)
+        return self.trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global, exchange=False)
 
     def _snapshot(self):
         t = self.trainer
@@ -431,6 +467,12 @@ class StepPipeline:
         stream.wait_event(self.ready[k])
         self.graphs[k].replay()
         self.free[k].record(stream)
+        if self.shards is not None:
+            import torch.distributed as tdist
+
+            if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
+                tdist.all_reduce(self.flats[k], op=tdist.ReduceOp.SUM)
+            self.post_graphs[k].replay()
         t = self.trainer
         t.step += 1
         t.launches += self.launches_per_step
