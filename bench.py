@@ -343,7 +343,9 @@ def run_native(args):
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as fh:
-                traffic = json.load(fh).get("query_forward_kernel_dram_bytes_per_launch")
+                tj = json.load(fh)
+                traffic = tj.get("train_fused_l1_kernel_dram_bytes_per_launch" if one_kernel
+                                 else "query_forward_kernel_dram_bytes_per_launch")
         h2d = sum(tt.numel() * tt.element_size() for tt in host_batches[0])
         line = {
             "metric": "sampled-points/sec through SDF decoder+grad+loss (train step: fused gather+MLP+grad forward, "
