@@ -127,3 +127,52 @@ def test_unfused_gradients_match_reference():
     gio.assert_close(npm.local_geo_features.grad, fx["feat_grads"][0], 1e-3, 2e-9, "dL/dfeatures", 1e-3)
     for j, p in enumerate(dec.flat_parameters()):
         gio.assert_close(p.grad, fx[f"dec_grad_it0_{j}"], 1e-3, 1e-7, f"dL/ddecoder[{j}]")
+
+
+@pytest.mark.parametrize("name", L1_CASES)
+def test_step_pipeline_matches_reference(name):
+    """The graphed iteration (CUDA graph per input buffer, device-side Adam step counter, host batches
+    staged on the copy stream) reproduces the reference's losses and post-Adam state."""
+    from clid_slam_b200.ops.train import FusedTrainer, StepPipeline
+
+    fx, m, cfg, npm, dec, frozen = _setup(name)
+    trainer = FusedTrainer(cfg, npm, dec)
+    n = fx["batch_x"].shape[1]
+    pipe = StepPipeline(trainer, n)
+    n_iters = int(fx["n_iters"])
+
+    def host_batch(it):
+        x, label, ts, weight = _batch(fx, it)
+        return tuple(t.cpu().pin_memory() for t in (x, label, weight, ts.to(torch.int32)))
+
+    pipe.stage(0, host_batch(0))
+    for it in range(n_iters):
+        if it + 1 < n_iters:
+            pipe.stage((it + 1) % 2, host_batch(it + 1))
+        loss = pipe.run(it % 2).cpu()
+        gio.assert_close(loss[0], fx["loss_total"][it], hp.LOSS_RTOL, 0, f"total loss it{it}")
+        gio.assert_close(loss[1], fx["loss_bce"][it], 1e-4, 0, f"bce loss it{it}")
+        gio.assert_close(loss[2], fx["loss_eikonal"][it], 1e-4, 0, f"eikonal loss it{it}")
+    assert trainer.step == n_iters
+    assert int(trainer.step_state[0].item()) == n_iters
+    _check_final_state(fx, npm, dec)
+
+
+def test_decoder_grad_reduce_matches_infold():
+    """Rows + dense reduction kernel against the in-kernel fold on a batch large enough for many tiles."""
+    from clid_slam_b200.ops.train import FusedTrainer
+    import oracle.sdf_oracle as oc
+
+    cfg_o = oc.OracleConfig(buffer_size=2_000_003, local_map_radius=80.0)
+    mo, params, gen = hp.build_oracle_world(200, 2, seed=5, cfg=cfg_o)
+    x, label, weight, ts = oc.sample_batch(mo.points, 40000, gen)
+    grads = []
+    for use_scratch in (True, False):
+        npm = hp.product_map(mo)
+        dec = hp.product_decoder(cfg_o, params)
+        trainer = FusedTrainer(hp.product_config(cfg_o), npm, dec)
+        trainer.use_scratch = use_scratch
+        trainer.iteration(x.cuda(), label.cuda(), ts.cuda(), weight.cuda(), apply_step=False)
+        grads.append((trainer.dec_grad.clone(), trainer.feat_grad.clone()))
+    gio.assert_close(grads[0][0], grads[1][0], 1e-4, 1e-7, "decoder gradients: rows vs in-kernel fold")
+    gio.assert_close(grads[0][1], grads[1][1], 1e-4, 1e-9, "feature gradients")
