@@ -13,7 +13,10 @@ namespace clid {
 #ifndef CLID_QUERY_MIN_BLOCKS
 #define CLID_QUERY_MIN_BLOCKS 4  // resident CTAs per SM the forward kernel is register-budgeted for
 #endif
-constexpr int kQueryThreads = 128;
+#ifndef CLID_QUERY_THREADS
+#define CLID_QUERY_THREADS 128
+#endif
+constexpr int kQueryThreads = CLID_QUERY_THREADS;
 constexpr int kBrickSlots = 8;  // span 2: a neighbourhood touches at most 2x2x2 bricks
 
 struct QueryParams {

@@ -345,11 +345,12 @@ struct AdamStepState {
   int32_t pad;
 };
 
-__device__ __forceinline__ float adam_update(float p, float g, float& mm, float& vv, const AdamParams& a) {
+__device__ __forceinline__ float adam_update(float p, float g, float& mm, float& vv, const AdamParams& a,
+                                             float step_size, float bc2_sqrt) {
   mm = mm + (g - mm) * (1.0f - a.beta1);                     // exp_avg.lerp_(grad, 1 - beta1)
   vv = fmaf(1.0f - a.beta2, g * g, vv * a.beta2);            // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
-  const float denom = sqrtf(vv) / a.bc2_sqrt + a.eps;
-  return p - a.step_size * (mm / denom);
+  const float denom = sqrtf(vv) / bc2_sqrt + a.eps;
+  return p - step_size * (mm / denom);
 }
 
 #ifdef CLID_PLAIN_KERNELS
@@ -367,8 +368,10 @@ __global__ void adam_advance_kernel(AdamStepState* st, float lr, float beta1, fl
 #endif
 
 #ifdef CLID_PLAIN_KERNELS
-__global__ void __launch_bounds__(256) adam_kernel(AdamParams a) {
-  if (a.step_scalars) { a.step_size = a.step_scalars[0]; a.bc2_sqrt = a.step_scalars[1]; }
+__global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamParams a) {
+  // the parameter block stays in the constant bank: the two scalars are the only per-step values
+  const float step_size = a.step_scalars ? __ldg(a.step_scalars) : a.step_size;
+  const float bc2_sqrt = a.step_scalars ? __ldg(a.step_scalars + 1) : a.bc2_sqrt;
   // feature rows: one thread per float4 half-row
   const int64_t halves = a.rows * 2;
   for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h < halves; h += (int64_t)gridDim.x * blockDim.x) {
@@ -381,10 +384,10 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamParams a) {
     float4* pv = reinterpret_cast<float4*>(a.feat_v) + h;
     float4 p = *pp, mm = *pm, vv = *pv;
     if (a.weight_decay != 0.f) { g.x = fmaf(a.weight_decay, p.x, g.x); g.y = fmaf(a.weight_decay, p.y, g.y); g.z = fmaf(a.weight_decay, p.z, g.z); g.w = fmaf(a.weight_decay, p.w, g.w); }
-    p.x = adam_update(p.x, g.x, mm.x, vv.x, a);
-    p.y = adam_update(p.y, g.y, mm.y, vv.y, a);
-    p.z = adam_update(p.z, g.z, mm.z, vv.z, a);
-    p.w = adam_update(p.w, g.w, mm.w, vv.w, a);
+    p.x = adam_update(p.x, g.x, mm.x, vv.x, a, step_size, bc2_sqrt);
+    p.y = adam_update(p.y, g.y, mm.y, vv.y, a, step_size, bc2_sqrt);
+    p.z = adam_update(p.z, g.z, mm.z, vv.z, a, step_size, bc2_sqrt);
+    p.w = adam_update(p.w, g.w, mm.w, vv.w, a, step_size, bc2_sqrt);
     *pp = p; *pm = mm; *pv = vv;
     *pg = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamParams a) {
       if (prm) {
         for (int i = threadIdx.x; i < numel; i += blockDim.x) {
           float mm = a.dec_m[base + i], vv = a.dec_v[base + i];
-          prm[i] = adam_update(prm[i], a.dec_grad[base + i], mm, vv, a);
+          prm[i] = adam_update(prm[i], a.dec_grad[base + i], mm, vv, a, step_size, bc2_sqrt);
           a.dec_m[base + i] = mm; a.dec_v[base + i] = vv;
           a.dec_grad[base + i] = 0.f;
         }

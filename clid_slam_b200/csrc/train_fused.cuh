@@ -49,7 +49,7 @@ struct TrainFusedParams {
   uint32_t flags;
 };
 
-constexpr int kFusedThreads = 128;
+constexpr int kFusedThreads = kQueryThreads;
 constexpr int kNumTileSamples = 20;  // base samples per warp tile in numerical mode
 
 // kFoldOut: the decoder-gradient fold (Gd += d c') is not done by the warp itself; every lane writes
@@ -57,7 +57,7 @@ constexpr int kNumTileSamples = 20;  // base samples per warp tile in numerical 
 // (tile_kernel.cuh) reduces all rows afterwards.  The warp-serial fold costs ~28 % of this kernel's
 // time (profiles/), as a separate dense reduction it is a few microseconds.
 template <int H, int K, bool kBricks, bool kNumerical, bool kFoldOut>
-__global__ void __launch_bounds__(kFusedThreads, 4) train_fused_l1_kernel(const __grid_constant__ TrainFusedParams p) {
+__global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fused_l1_kernel(const __grid_constant__ TrainFusedParams p) {
   using Lay = MlpLayout<H, 1>;
   constexpr int kRows = H / 32;
   constexpr int kMaskWords = H / 32;
