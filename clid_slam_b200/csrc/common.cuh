@@ -32,44 +32,51 @@ __device__ __forceinline__ float dist2_torch(float dx, float dy, float dz) {
 }
 
 // Work distribution of the thread-per-sample kernels: a tile is 32 consecutive samples, owned by
-// one warp.  With a counter, warps fetch tiles dynamically (an atomic per tile) so per-sample cost
-// differences and the 1.7-wave tail of a static grid-stride loop even out; the warp that draws the
-// last ticket (n_tiles + n_warps - 1) resets the counter for the next launch.  Without a counter
-// the tiles are dealt round-robin.
+// one warp.  The first round is static (warp w takes tile w, no atomic on the launch path); with a
+// counter the remaining tiles are drawn dynamically (an atomic per tile, fetched one tile ahead so
+// its round trip overlaps the tile's work), which evens out per-sample cost differences and the
+// tail of a static schedule.  Every warp draws exactly one ticket past the end; the warp that draws
+// the last one (remaining + n_warps - 1) resets the counter for the next launch.  Without a
+// counter the tiles are dealt round-robin.
 struct TileScheduler {
   int32_t* counter;
   int64_t n_tiles;
   int64_t next_static;
-  int64_t stride;
+  int64_t stride;     // warps in the grid
+  int64_t remaining;  // tiles beyond the static first round
   int lane;
-  int ticket;  // dynamic: the ticket drawn for the NEXT call (valid in lane 0), fetched one tile ahead
+  int ticket;         // dynamic: the ticket drawn for the NEXT call (valid in lane 0)
+  bool first;
   __device__ __forceinline__ TileScheduler(int32_t* counter_, int64_t n) : counter(counter_) {
     n_tiles = (n + 31) >> 5;
     lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     next_static = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     stride = (int64_t)gridDim.x * warps_per_block;
+    remaining = n_tiles - stride;
     ticket = 0;
-    if (counter != nullptr) draw();
+    first = true;
+    if (counter != nullptr && remaining > 0) draw();
   }
   __device__ __forceinline__ void draw() {
     if (lane == 0) {
       ticket = atomicAdd(counter, 1);
-      if ((int64_t)ticket == n_tiles + stride - 1) atomicExch(counter, 0);  // last ticket of the launch
+      if ((int64_t)ticket == remaining + stride - 1) atomicExch(counter, 0);  // last ticket of the launch
     }
   }
-  // returns the tile index for this warp or -1 when the work is exhausted (warp-uniform).  The
-  // atomic for the following tile is issued here, so its round trip overlaps the tile's work.
+  // returns the tile index for this warp or -1 when the work is exhausted (warp-uniform)
   __device__ __forceinline__ int64_t next() {
-    if (counter == nullptr) {
+    if (counter == nullptr || first) {
+      first = false;
       const int64_t t = next_static;
       next_static += stride;
       return t < n_tiles ? t : -1;
     }
+    if (remaining <= 0) return -1;
     const int t = __shfl_sync(0xffffffffu, ticket, 0);
-    if ((int64_t)t >= n_tiles) return -1;  // every warp draws exactly one ticket past the end
+    if ((int64_t)t >= remaining) return -1;
     draw();
-    return (int64_t)t;
+    return stride + (int64_t)t;
   }
 };
 
