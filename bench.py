@@ -360,8 +360,9 @@ def run_native(args):
                 "samples_per_step": samples_per_step, "neural_points": int(npm.count()),
                 "mean_valid_candidates": mean_nn, "l2": "flushed before every timed step (256 MiB write, then 256 MiB read so evictions are clean)",
                 "parallelism": ("single GPU" if world == 1 else
-                                f"x{world}: samples sharded by map slab, one flat NCCL all-reduce "
-                                f"[decoder grads | loss | {int(shards.shared_rows.numel())} shared feature rows] per step"
+                                f"x{world}: samples and neural points sharded by map slab; per step one 3 kB NCCL "
+                                f"all-reduce [decoder grads | loss] and a neighbour send/recv of the boundary-band "
+                                f"feature gradients ({int(shards.shared_rows.numel())} band rows in total)"
                                 if shards is not None else
                                 f"x{world}: batch-sharded, replicated map, dense feature-gradient all-reduce"),
             },

@@ -306,9 +306,45 @@ class FusedTrainer:
         if self.train_features:
             self.feat_grad[shards.shared_rows] = flat[off:].view(-1, self.feat_grad.shape[1])
 
+    def neighbour_exchange(self, shards):
+        """NeighbourExchange for this trainer (None: single process, or bands overlap -> flat all-reduce)."""
+        from .. import dist as _dist
+
+        rank, world = _dist.world()
+        if world == 1 or not shards.pairwise or not self.train_features:
+            return None
+        ex = getattr(self, "_exchange", None)
+        if ex is None:
+            ex = _dist.NeighbourExchange(shards, rank, self.feat_grad)
+            if self.touched is not None:  # band rows may receive gradient from the neighbour only
+                self.touched[ex.rows()] = 1
+            self._exchange = ex
+        return ex
+
+    def small_flat(self, loss: torch.Tensor) -> torch.Tensor:
+        """[decoder grads | loss]: what every rank contributes to (all-reduce)."""
+        return torch.cat([self.dec_grad, loss]) if self.dec_grad is not None else loss.clone()
+
+    def unpack_small(self, flat: torch.Tensor, loss: torch.Tensor) -> None:
+        off = 0
+        if self.dec_grad is not None:
+            off = self.dec_grad.numel()
+            self.dec_grad.copy_(flat[:off])
+        loss.copy_(flat[off:off + 3])
+
     def sync_spatial(self, loss: torch.Tensor, shards) -> None:
         import torch.distributed as tdist
 
+        ex = self.neighbour_exchange(shards)
+        if ex is not None:
+            # [decoder grads | loss] through a 3 kB all-reduce, band rows with the two slab neighbours
+            flat = self.small_flat(loss)
+            ex.pack(self.feat_grad)
+            tdist.all_reduce(flat, op=tdist.ReduceOp.SUM)
+            ex.exchange()
+            self.unpack_small(flat, loss)
+            ex.unpack(self.feat_grad)
+            return
         flat = self.pack_spatial(loss, shards)
         if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
             tdist.all_reduce(flat, op=tdist.ReduceOp.SUM)
@@ -402,23 +438,39 @@ class StepPipeline:
         with torch.cuda.stream(side):
             warm_loss = self._iteration(0, n_global, nd_global)
             if shards is not None:
-                trainer.unpack_spatial(trainer.pack_spatial(warm_loss, shards), warm_loss, shards)
+                ex = trainer.neighbour_exchange(shards)
+                if ex is not None:
+                    trainer.unpack_small(trainer.small_flat(warm_loss), warm_loss)
+                    ex.pack(trainer.feat_grad)
+                    ex.unpack(trainer.feat_grad)
+                else:
+                    trainer.unpack_spatial(trainer.pack_spatial(warm_loss, shards), warm_loss, shards)
                 trainer.adam_step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.flats, self.post_graphs = [], []
+        self.exchange = trainer.neighbour_exchange(shards) if shards is not None else None
         for k in range(nb):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 loss = self._iteration(k, n_global, nd_global)
-                flat = trainer.pack_spatial(loss, shards) if shards is not None else None
+                flat = None
+                if shards is not None and self.exchange is not None:
+                    flat = trainer.small_flat(loss)
+                    self.exchange.pack(trainer.feat_grad)
+                elif shards is not None:
+                    flat = trainer.pack_spatial(loss, shards)
             self.graphs.append(g)
             self.losses.append(loss)
             self.flats.append(flat)
             if shards is not None:
                 g2 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g2):
-                    trainer.unpack_spatial(flat, loss, shards)
+                    if self.exchange is not None:
+                        trainer.unpack_small(flat, loss)
+                        self.exchange.unpack(trainer.feat_grad)
+                    else:
+                        trainer.unpack_spatial(flat, loss, shards)
                     trainer.adam_step()
                 self.post_graphs.append(g2)
         torch.cuda.synchronize(dev)
@@ -431,7 +483,8 @@ class StepPipeline:
         x, label, weight, ts = self.bufs[k]
         if self.shards is None:
             return self.trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global)
-        return self.trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global, exchange=False)
+        return self.trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global, shards=self.shards,
+                                      exchange=False)
 
     def _snapshot(self):
         t = self.trainer
@@ -472,6 +525,8 @@ class StepPipeline:
 
             if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
                 tdist.all_reduce(self.flats[k], op=tdist.ReduceOp.SUM)
+                if self.exchange is not None:
+                    self.exchange.exchange()
             self.post_graphs[k].replay()
         t = self.trainer
         t.step += 1

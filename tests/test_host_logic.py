@@ -212,3 +212,54 @@ def test_clid_sampler_and_local_map_match_reference_fixture():
     assert torch.equal(coord, gio.t(fx["coord"]))
     gio.assert_close(label, fx["label"], 1e-4, 1e-6, "labels", 2e-3)
     assert torch.equal(weight, gio.t(fx["weight"]))
+
+
+def _exchange_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # 3 slabs along x over a 60-cell line of points (one point per cell, res 1.0)
+        pts = torch.stack((torch.arange(60, dtype=torch.float32) + 0.5, torch.zeros(60), torch.zeros(60)), 1)
+        shards = cdist.SpatialShards(pts, 1.0, reach=2, world_size=world, axis=0)
+        assert shards.pairwise
+        grad = torch.zeros(61, 8)  # + padding row
+        mine = (shards.row_owner == rank) | shards.shared_mask
+        grad[mine] = float(rank + 1)  # every rank contributes to its slab and to all bands it can reach ...
+        left, right = shards.neighbour_rows(rank)
+        reach_rows = torch.zeros(61, dtype=torch.bool)
+        reach_rows[shards.row_owner == rank] = True
+        for rows in (left, right):
+            if rows is not None:
+                reach_rows[rows] = True
+        grad[~reach_rows] = 0.0       # ... but only the bands of its own two boundaries
+        ex = cdist.NeighbourExchange(shards, rank, grad)
+        ex.pack(grad)
+        ex.exchange()
+        ex.unpack(grad)
+        torch.save({"grad": grad, "owner": shards.row_owner, "bands": [b for b in shards.band_rows]},
+                   os.path.join(out_dir, f"x{rank}.pt"))
+    finally:
+        torch.distributed.destroy_process_group()
+
+
+def test_neighbour_exchange_with_three_gloo_ranks():
+    """Band rows end up with the sum of both contributors on both ranks; private rows are untouched."""
+    world = 3
+    port = 31500 + os.getpid() % 2000
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_exchange_worker, args=(world, port, tmp), nprocs=world, join=True)
+        outs = [torch.load(os.path.join(tmp, f"x{r}.pt")) for r in range(world)]
+    bands = outs[0]["bands"]
+    assert len(bands) == 2
+    for j, rows in enumerate(bands):  # boundary j separates ranks j and j + 1
+        want = float((j + 1) + (j + 2))
+        for r in (j, j + 1):
+            assert torch.all(outs[r]["grad"][rows] == want)
+    owner = outs[0]["owner"]
+    in_band = torch.zeros(61, dtype=torch.bool)
+    for rows in bands:
+        in_band[rows] = True
+    for r in range(world):
+        private = (owner == r) & ~in_band
+        private[-1] = False
+        assert torch.all(outs[r]["grad"][private] == float(r + 1))
