@@ -176,3 +176,38 @@ def test_decoder_grad_reduce_matches_infold():
         grads.append((trainer.dec_grad.clone(), trainer.feat_grad.clone()))
     gio.assert_close(grads[0][0], grads[1][0], 1e-4, 1e-7, "decoder gradients: rows vs in-kernel fold")
     gio.assert_close(grads[0][1], grads[1][1], 1e-4, 1e-9, "feature gradients")
+
+
+@pytest.mark.parametrize("variant", ["rows", "tiles"])
+@pytest.mark.parametrize("hidden,numerical,leaky", [(32, False, False), (128, False, False), (32, True, False),
+                                                     (128, True, True), (64, False, True)])
+def test_training_gradients_match_oracle_other_widths(hidden, numerical, leaky, variant, monkeypatch):
+    """Decoder widths / activation the reference fixtures do not cover: loss, dL/dfeatures and dL/ddecoder of
+    one iteration against torch autograd through the oracle (double backward in analytic mode)."""
+    import oracle.sdf_oracle as oc
+    from clid_slam_b200.ops import query as q
+    from clid_slam_b200.ops.train import FusedTrainer
+
+    monkeypatch.setattr(q, "USE_TILE_KERNELS", variant == "tiles")
+    cfg_o = oc.OracleConfig(buffer_size=2_000_003, local_map_radius=80.0, geo_mlp_hidden_dim=hidden,
+                            numerical_grad=numerical, gradient_decimation=10 if numerical else 1, mlp_leaky_relu=leaky)
+    mo, params, gen = hp.build_oracle_world(120, 2, seed=7, cfg=cfg_o)
+    x, label, weight, ts = oc.sample_batch(mo.points, 6000, gen)
+    npm = hp.product_map(mo)
+    dec = hp.product_decoder(cfg_o, params)
+
+    feats = mo.local_features
+    feats.requires_grad_(True)
+    for p in params:
+        p.requires_grad_(True)
+    total, l_bce, l_eik, _, _ = oc.training_loss(mo, params, x, label, ts, weight)
+    grads = torch.autograd.grad(total, [feats] + list(params))
+
+    trainer = FusedTrainer(hp.product_config(cfg_o), npm, dec)
+    loss = trainer.iteration(x.cuda(), label.cuda(), ts.cuda(), weight.cuda(), apply_step=False)
+    gio.assert_close(loss[0], total.detach(), hp.LOSS_RTOL, 0, "total loss")
+    gio.assert_close(loss[1], l_bce.detach(), 1e-4, 0, "bce loss")
+    gio.assert_close(loss[2], l_eik.detach(), 1e-4, 0, "eikonal loss")
+    gio.assert_close(trainer.feat_grad, grads[0], 1e-3, 2e-9, "dL/dfeatures", 1e-3)
+    flat = torch.cat([g.flatten() for g in grads[1:]])
+    gio.assert_close(trainer.dec_grad, flat, 1e-3, 1e-7, "dL/ddecoder")
