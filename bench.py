@@ -228,7 +228,10 @@ def run_native(args):
         # buffer (ops/train.py StepPipeline)
         from clid_slam_b200.ops.train import StepPipeline
 
-        kw = dict(n_global=n_global, nd_global=nd_global, shards=shards, sync=multi and shards is None)
+        # neighbour send/recv on a process group of its own: overlaps the [decoder grads | loss] all-reduce
+        p2p_group = dist.new_group() if multi and shards is not None else None
+        kw = dict(n_global=n_global, nd_global=nd_global, shards=shards, sync=multi and shards is None,
+                  p2p_group=p2p_group)
         pipe_dev = StepPipeline(trainer, BATCH, buffers=batches, **kw)
         pipe_host = StepPipeline(trainer, BATCH, **kw)
 
@@ -288,16 +291,23 @@ def run_native(args):
         if graphed:
             pipe_host.stage((i + 1) % 2, host_batches[(i + 1) % n_batches])
             loss = pipe_host.run(i % 2)
-            e1.record()
-            # device -> host read of this step's result, on the copy stream behind the step
-            pipe_host.copy_stream.wait_event(e1)
-            with torch.cuda.stream(pipe_host.copy_stream):
-                loss_pinned[i % 2].copy_(loss, non_blocking=True)
-                loss_ready[i % 2].record(pipe_host.copy_stream)
-            if i >= 1:
-                loss_ready[(i - 1) % 2].synchronize()
-                loss_host = loss_pinned[(i - 1) % 2].clone()
+            if multi:
+                # N > 1: the host side of a step (two graph launches + NCCL enqueues from Python) is about as
+                # long as the step itself, so the loss is simply read back here (blocking)
+                loss_host = loss.cpu()
                 losses_read += 1
+                e1.record()
+            else:
+                e1.record()
+                # device -> host read of this step's result, on the copy stream behind the step
+                pipe_host.copy_stream.wait_event(e1)
+                with torch.cuda.stream(pipe_host.copy_stream):
+                    loss_pinned[i % 2].copy_(loss, non_blocking=True)
+                    loss_ready[i % 2].record(pipe_host.copy_stream)
+                if i >= 1:
+                    loss_ready[(i - 1) % 2].synchronize()
+                    loss_host = loss_pinned[(i - 1) % 2].clone()
+                    losses_read += 1
         else:
             x, label, weight, ts = (t.to(device, non_blocking=True) for t in host_batches[i % n_batches])
             loss = trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global,
@@ -306,7 +316,7 @@ def run_native(args):
             losses_read += 1
             e1.record()
         e2e_events.append((e0, e1))
-    if graphed:
+    if graphed and not multi:
         loss_ready[(args.steps - 1) % 2].synchronize()
         loss_host = loss_pinned[(args.steps - 1) % 2].clone()
         losses_read += 1
@@ -417,8 +427,9 @@ def run_native(args):
                     # (identical in both): their difference is what the host traffic costs end to end
                     "wall_ms_per_step_incl_flush": wall_e2e_ms / args.steps,
                     "wall_ms_per_step_incl_flush_device_resident_loop": wall_dev_ms / args.steps,
-                    "pipeline": "depth 2: batch i+1 staged host->device on a copy stream during step i; the loss of "
-                                "step i-1 is read on the host after step i has been enqueued"},
+                    "pipeline": ("depth 2: batch i+1 staged host->device on a copy stream during step i; the loss of "
+                                 "step i-1 is read on the host after step i has been enqueued") if (graphed and not multi)
+                    else "batch i+1 staged host->device on a copy stream during step i; blocking loss read per step"},
             "gpu_launches": launches,
             "clocks": clocks,
             "final_loss": [float(v) for v in loss_host.tolist()],

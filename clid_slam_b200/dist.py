@@ -185,6 +185,7 @@ class NeighbourExchange:
         if not shards.pairwise:
             raise ValueError("slabs are narrower than two bands: use the flat all-reduce")
         self.rank, self.group = int(rank), group
+        self._ops = None
         self.sides = []  # (peer, rows, send, recv)
         left, right = shards.neighbour_rows(rank)
         for peer, rows in ((rank - 1, left), (rank + 1, right)):
@@ -202,11 +203,12 @@ class NeighbourExchange:
     def exchange(self) -> None:
         if world()[1] == 1 or not self.sides:
             return
-        ops = []
-        for peer, _, send, recv in self.sides:
-            ops.append(dist.P2POp(dist.isend, send, peer, self.group))
-            ops.append(dist.P2POp(dist.irecv, recv, peer, self.group))
-        for req in dist.batch_isend_irecv(ops):
+        if self._ops is None:  # the buffers are static: build the op list once
+            self._ops = []
+            for peer, _, send, recv in self.sides:
+                self._ops.append(dist.P2POp(dist.isend, send, peer, self.group))
+                self._ops.append(dist.P2POp(dist.irecv, recv, peer, self.group))
+        for req in dist.batch_isend_irecv(self._ops):
             req.wait()
 
     def unpack(self, grad: torch.Tensor) -> None:

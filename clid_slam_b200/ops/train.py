@@ -306,8 +306,10 @@ class FusedTrainer:
         if self.train_features:
             self.feat_grad[shards.shared_rows] = flat[off:].view(-1, self.feat_grad.shape[1])
 
-    def neighbour_exchange(self, shards):
-        """NeighbourExchange for this trainer (None: single process, or bands overlap -> flat all-reduce)."""
+    def neighbour_exchange(self, shards, group=None):
+        """NeighbourExchange for this trainer (None: single process, or bands overlap -> flat all-reduce).
+        group: process group for the send/recv pairs; a group of its own (dist.new_group()) lets them run
+        concurrently with the [decoder grads | loss] all-reduce of the default group."""
         from .. import dist as _dist
 
         rank, world = _dist.world()
@@ -315,7 +317,7 @@ class FusedTrainer:
             return None
         ex = getattr(self, "_exchange", None)
         if ex is None:
-            ex = _dist.NeighbourExchange(shards, rank, self.feat_grad)
+            ex = _dist.NeighbourExchange(shards, rank, self.feat_grad, group=group)
             if self.touched is not None:  # band rows may receive gradient from the neighbour only
                 self.touched[ex.rows()] = 1
             self._exchange = ex
@@ -340,8 +342,9 @@ class FusedTrainer:
             # [decoder grads | loss] through a 3 kB all-reduce, band rows with the two slab neighbours
             flat = self.small_flat(loss)
             ex.pack(self.feat_grad)
-            tdist.all_reduce(flat, op=tdist.ReduceOp.SUM)
+            work = tdist.all_reduce(flat, op=tdist.ReduceOp.SUM, async_op=True)
             ex.exchange()
+            work.wait()
             self.unpack_small(flat, loss)
             ex.unpack(self.feat_grad)
             return
@@ -394,7 +397,7 @@ class StepPipeline:
     """
 
     def __init__(self, trainer: FusedTrainer, n: int, n_global: int = 0, nd_global: int = 0, with_ts: bool = True,
-                 buffers=None, shards=None, sync: bool = False):
+                 buffers=None, shards=None, sync: bool = False, p2p_group=None):
         """buffers: optional list of caller-owned device batches (x [n,3] f32, label [n] f32, weight [n]
         f32, ts [n] i32 | None) to capture on directly (no staging copies); default: two staging buffers."""
         if trainer.step != 0 and trainer.step_state is None:
@@ -438,7 +441,7 @@ class StepPipeline:
         with torch.cuda.stream(side):
             warm_loss = self._iteration(0, n_global, nd_global)
             if shards is not None:
-                ex = trainer.neighbour_exchange(shards)
+                ex = trainer.neighbour_exchange(shards, p2p_group)
                 if ex is not None:
                     trainer.unpack_small(trainer.small_flat(warm_loss), warm_loss)
                     ex.pack(trainer.feat_grad)
@@ -449,7 +452,7 @@ class StepPipeline:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.flats, self.post_graphs = [], []
-        self.exchange = trainer.neighbour_exchange(shards) if shards is not None else None
+        self.exchange = trainer.neighbour_exchange(shards, p2p_group) if shards is not None else None
         for k in range(nb):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -524,9 +527,12 @@ class StepPipeline:
             import torch.distributed as tdist
 
             if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
-                tdist.all_reduce(self.flats[k], op=tdist.ReduceOp.SUM)
+                # the 3 kB all-reduce and the neighbour send/recv are independent: with the exchange on a
+                # process group of its own they overlap on the wire
+                work = tdist.all_reduce(self.flats[k], op=tdist.ReduceOp.SUM, async_op=True)
                 if self.exchange is not None:
                     self.exchange.exchange()
+                work.wait()
             self.post_graphs[k].replay()
         t = self.trainer
         t.step += 1
