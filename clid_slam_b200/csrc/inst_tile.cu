@@ -38,16 +38,6 @@ static int launch_tile_t(TileParams& p, cudaStream_t stream) {
     grid = (int)cap;
     p.work_counter = p.map.work_counter;  // persistent CTAs, tiles drawn with an atomic (NULL: round-robin)
   }
-#if CLID_TILE_CONST_MLP
-  {
-    static thread_local float* c_dec_addr = nullptr;
-    if (!c_dec_addr) {
-      cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&c_dec_addr), c_dec);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress");
-    }
-    pack_decoder_kernel<H><<<1, 256, 0, stream>>>(p.dec, c_dec_addr);
-  }
-#endif
   kern<<<grid, kTileThreads, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "sdf_tile_kernel launch");

@@ -205,15 +205,6 @@ __device__ __forceinline__ int search_bricks(const ClidMap& m, const ClidBricks&
         }
       }
     }
-#ifdef CLID_TILE_DEBUG
-#pragma unroll
-    for (int j = 0; j < kWalkBatch; ++j)
-      if (rec[j] >= b.n_records && blockIdx.x < 3) {
-        printf("bad rec %d (n %d) blk %d thr %d nfill %d left %d base %d occ %08x w %08x in %d\n", rec[j], b.n_records, blockIdx.x,
-               threadIdx.x, nfill, left, base, occ, w, (int)in);
-        rec[j] = -1;
-      }
-#endif
     float4 r[kWalkBatch];
 #pragma unroll
     for (int j = 0; j < kWalkBatch; ++j) r[j] = __ldg(records + (rec[j] < 0 ? 0 : rec[j]));

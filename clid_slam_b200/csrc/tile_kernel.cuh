@@ -22,8 +22,6 @@
 //            row to global memory for the decoder-gradient reduction kernel (decoder_grad_kernel)
 //   scatter  feature-gradient vector atomics (neighbour records re-read from L2)
 #pragma once
-#include <cstdio>
-
 #include "common.cuh"
 #include "query_bwd.cuh"
 #include "query_fwd.cuh"
@@ -37,12 +35,7 @@ constexpr int kTileThreads = kTileWarps * 32;
 #define CLID_TILE_BLOCKS 4
 #endif
 constexpr int kTileBlocksPerSm = CLID_TILE_BLOCKS;
-#ifdef CLID_TILE_SEPARATE
-constexpr int kParkOffset = 9;    // debug: search scratch and park slice do not alias
-#else
-constexpr int kParkOffset = 0;
-#endif
-constexpr int kParkGroups = 11 + kParkOffset;   // float4 groups per lane in the warp's park slice
+constexpr int kParkGroups = 11;   // float4 groups per lane in the warp's park slice
 constexpr int kFoldRow = 16;      // floats per row handed to decoder_grad_kernel: c'[12], mask words, pad
 constexpr int kNumTile = 20;      // base samples per tile in numerical mode (see train_fused.cuh)
 
@@ -157,58 +150,6 @@ __device__ __forceinline__ void tile_mlp(const float* __restrict__ sm, const flo
   }
 }
 
-#ifndef CLID_TILE_CONST_MLP
-#define CLID_TILE_CONST_MLP 0
-#endif
-#if CLID_TILE_CONST_MLP
-// Decoder image in constant memory (layout of TileDec<128> at most): every lane needs every weight, so
-// the weights are warp-uniform operands -- read through the constant cache they cost no LSU / shared
-// memory bandwidth and no staging registers.  Filled by pack_decoder_kernel before each launch.
-__constant__ float c_dec[TileDec<128>::kFloats];
-
-template <int H, bool kMask>
-__device__ __forceinline__ void tile_mlp_const(const float (&z)[kIn], float slope, float& out, float (&a)[kInPad],
-                                               uint32_t* __restrict__ mask) {
-  using Lay = TileDec<H>;
-#pragma unroll
-  for (int i = 0; i < kInPad; ++i) a[i] = 0.f;
-  out = c_dec[Lay::kBout];
-#pragma unroll
-  for (int jw = 0; jw < H / 32; ++jw) {
-    uint32_t bits = 0u;
-#pragma unroll 8
-    for (int jj = 0; jj < 32; ++jj) {
-      const int j = jw * 32 + jj;
-      const float* w = c_dec + Lay::kW0 + j * kInPad;
-      float p0 = w[kIn], p1 = 0.f;   // bias
-      p0 = fmaf(w[0], z[0], p0); p1 = fmaf(w[1], z[1], p1); p0 = fmaf(w[2], z[2], p0); p1 = fmaf(w[3], z[3], p1);
-      p0 = fmaf(w[4], z[4], p0); p1 = fmaf(w[5], z[5], p1); p0 = fmaf(w[6], z[6], p0); p1 = fmaf(w[7], z[7], p1);
-      p0 = fmaf(w[8], z[8], p0); p1 = fmaf(w[9], z[9], p1); p0 = fmaf(w[10], z[10], p0);
-      const float pre = p0 + p1;
-      const bool on = pre > 0.f;
-      if (kMask) bits = (bits >> 1) | (on ? 0x80000000u : 0u);
-      const float wo = c_dec[Lay::kWout + j];
-      const float cj = on ? wo : wo * slope;
-      out = fmaf(cj, pre, out);
-#pragma unroll
-      for (int i = 0; i < kIn; ++i) a[i] = fmaf(w[i], cj, a[i]);
-    }
-    if (kMask) mask[jw] = bits;
-  }
-}
-
-template <int H>
-__global__ void pack_decoder_kernel(const ClidDecoder dec, float* __restrict__ dst) {
-  using Lay = TileDec<H>;
-  for (int i = threadIdx.x; i < H * kInPad; i += blockDim.x) {
-    const int j = i / kInPad, c = i - j * kInPad;
-    dst[Lay::kW0 + i] = c < kIn ? dec.weight[0][j * kIn + c] : (dec.bias[0] ? dec.bias[0][j] : 0.f);
-  }
-  for (int i = threadIdx.x; i < H; i += blockDim.x) dst[Lay::kWout + i] = dec.out_weight[i];
-  if (threadIdx.x == 0) dst[Lay::kBout] = dec.out_bias ? dec.out_bias[0] : 0.f;
-}
-#endif
-
 // one 32-byte feature row with a single 256-bit load (LDG.E.256, sm_100+): one L1 wavefront per
 // lane instead of two
 __device__ __forceinline__ void load_feature_row256(const float* __restrict__ feats, int id, float (&f)[kFeat]) {
@@ -229,7 +170,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileBlocksPerSm) sdf_tile_kerne
   float* sm_dec = smem;
   uint64_t* stencil = reinterpret_cast<uint64_t*>(smem + Lay::kFloats);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4* park = reinterpret_cast<float4*>(smem + Lay::kFloats + 2 * 64 * 8) + warp * (kParkGroups * 32) + kParkOffset * 32 + lane;
+  float4* park = reinterpret_cast<float4*>(smem + Lay::kFloats + 2 * 64 * 8) + warp * (kParkGroups * 32) + lane;
   uint32_t* col = reinterpret_cast<uint32_t*>(smem + Lay::kFloats + 2 * 64 * 8) + warp * (kParkGroups * 128) + lane;
   __shared__ float sm_scalar[3][kTileWarps];
 
@@ -382,19 +323,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileBlocksPerSm) sdf_tile_kerne
     float out;
     float2 ap[6];
     uint32_t mask[kMaskWords];
-#if CLID_TILE_CONST_MLP
-    {
-      float zz[kIn], aa[kInPad];
-#pragma unroll
-      for (int i = 0; i < 5; ++i) { zz[2 * i] = zp[i].x; zz[2 * i + 1] = zp[i].y; }
-      zz[10] = zp[5].x;
-      tile_mlp_const<H, kTrain>(zz, slope, out, aa, mask);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) ap[i] = make_float2(aa[2 * i], aa[2 * i + 1]);
-    }
-#else
     tile_mlp<H, kTrain>(sm_dec, zp, slope, out, ap, mask);
-#endif
     const float sdf = out * s;
     float cbar = zp[5].x * ap[5].x;
 #pragma unroll

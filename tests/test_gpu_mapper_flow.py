@@ -110,3 +110,44 @@ def test_dynamic_filter_and_certainty_queries_run():
     mapper.process_frame(_scan(gen, "cuda", 3000), None, pose, 1, filter_dynamic=True)
     assert mapper.static_mask.dtype == torch.bool and mapper.static_mask.numel() > 0
     assert mapper.new_idx is not None
+
+
+@pytest.mark.parametrize("mode", ["numerical", "analytic"])
+def test_graphed_mapping_tracks_the_eager_loop(mode):
+    """mapping() with many iterations replays one CUDA graph of [replay-pool draw + iteration]; it must
+    train like the call-by-call loop (different random batches, so the comparison is statistical)."""
+    from clid_slam_b200.config import ncd128
+    from clid_slam_b200.model.decoder import Decoder
+    from clid_slam_b200.model.neural_points import NeuralPoints
+    from clid_slam_b200.utils.mapper import Mapper
+
+    iters = 40
+    results = {}
+    for graphed in (True, False):
+        torch.manual_seed(3)
+        cfg = ncd128()
+        cfg.device, cfg.use_pin_mapper, cfg.buffer_size = "cuda", True, 2_000_003
+        if mode == "analytic":
+            cfg.numerical_grad, cfg.gradient_decimation = False, 1
+        dec = Decoder(cfg, 64, 1, 1)
+        npm = NeuralPoints(cfg)
+        ds = FakeDataset(1)
+        mapper = Mapper(cfg, ds, npm, None, dec)
+        mapper.graph_min_iters = 8 if graphed else 0
+        gen = torch.Generator(device="cuda").manual_seed(9)
+        npm.travel_dist = torch.zeros(1, device="cuda")
+        mapper.process_frame(_scan(gen, "cuda"), None, torch.eye(4, device="cuda", dtype=torch.float64), 0)
+        mapper.adaptive_iter_offset = 0
+        mapper.mapping(iters)
+        losses = mapper.last_losses.cpu()
+        assert losses.shape == (iters, 3) and torch.isfinite(losses).all()
+        assert mapper.total_iter == iters
+        assert float(npm.point_certainties.sum()) > 0
+        results[graphed] = (losses, npm.geo_features.clone(), [p.detach().clone() for p in dec.parameters()])
+    lg, le = results[True][0], results[False][0]
+    assert lg[-5:, 0].mean() < 0.8 * lg[:3, 0].mean(), "the graphed loop must reduce the loss"
+    # same trajectory up to batch noise: the tail losses of the two loops agree within 15 %
+    assert abs(float(lg[-10:, 0].mean()) / float(le[-10:, 0].mean()) - 1.0) < 0.15, (lg[-10:, 0].mean(), le[-10:, 0].mean())
+    # and the decoders moved the same way
+    for a, b in zip(results[True][2], results[False][2]):
+        assert torch.nn.functional.cosine_similarity(a.flatten() - 0, b.flatten() - 0, dim=0) > 0.99
