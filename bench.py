@@ -11,9 +11,16 @@ north_star target is quoted on): 131072 samples per batch per GPU, ~1.08 M neura
 (4 wavy sheets, 0.4 m voxels, ncd128 decoder 11->64->1, Kc = 81, K = 6), analytic gradient.
 Data are synthetic (no dataset is shipped); see clid_slam_b200/synth.py.
 
-For N > 1 launch with torchrun (one rank per GPU); the map is replicated, every rank takes its
-own 131072-sample shard of an N x 131072 global batch (weak scaling), decoder gradients + loss
-go through one flat NCCL all-reduce and the replicated feature gradients through a second.
+The step runs as a CUDA graph per input buffer (clid_slam_b200/ops/train.py StepPipeline).  Three
+loops are timed with CUDA events, the L2 flushed before every step: device-resident inputs (`value`),
+host-pinned inputs staged every step with the loss read back every step (`e2e`), and a call-by-call
+replay with events around the dominant kernel (`roofline`).
+
+For N > 1 launch with torchrun (one rank per GPU): samples and neural points are sharded by map slab,
+every rank takes 131072 samples of its slab per step (weak scaling); per step one 3 kB NCCL all-reduce
+[decoder gradients | loss] and a neighbour send/recv of the boundary-band feature gradients
+(clid_slam_b200/dist.py).  `--sharding replicated` keeps the map replicated and all-reduces the dense
+feature gradient instead.
 """
 from __future__ import annotations
 
@@ -45,8 +52,8 @@ def parse_args():
                     help="eikonal gradient mode of the training step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sharding", default="spatial", choices=["spatial", "replicated"],
-                    help="N > 1: slab-partitioned samples with one flat all-reduce (default) or any-sample-anywhere "
-                         "with a dense feature-gradient all-reduce")
+                    help="N > 1: slab-partitioned samples and neural points with a neighbour exchange of the band "
+                         "gradients (default) or any-sample-anywhere with a dense feature-gradient all-reduce")
     return ap.parse_args()
 
 

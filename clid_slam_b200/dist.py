@@ -15,9 +15,11 @@ Two sharding modes (FusedTrainer.iteration):
 * spatial (`shards=SpatialShards(...)`): space is cut into slabs along one axis, a sample belongs
   to the rank that owns the slab of its voxel.  A sample only touches neural points within
   `reach` voxels, so feature rows are private to their slab's rank except for a thin band around
-  every slab boundary (`shared_rows`).  Per iteration ONE flat all-reduce carries
-  [decoder grads | loss | gradients of the shared rows]; every rank then applies the identical Adam
-  step to the shared rows and its own step to its private rows.  Other ranks' private rows go stale
+  every slab boundary (`shared_rows`).  Per iteration a 3 kB all-reduce carries [decoder grads | loss]
+  and every rank completes the gradients of its two bands with its slab neighbours (`NeighbourExchange`,
+  grouped send/recv); when bands overlap (slabs narrower than two bands) ONE flat all-reduce carries
+  [decoder grads | loss | gradients of all shared rows] instead.  Ranks then apply the identical Adam
+  step to the rows they share and their own step to their private rows.  Other ranks' private rows go stale
   locally but are never read; `SpatialShards.gather_features` re-replicates the table once per
   mapping() call.  Certainty / ts_update side effects are likewise reduced once per call
   (`reduce_side_effects`).

@@ -1,14 +1,17 @@
 """Fused training iteration of the neural-SDF map (the loop body of Mapper.mapping,
 utils/mapper.py:642-836 of the reference) on top of the C ABI:
 
-    clid_query_forward   gather + IDW + decoder (+ closed-form d sdf / d x), side effects
-    clid_sdf_loss        bce + eikonal -> per-point d L / d logit (and d L / d grad)
-    clid_train_backward  decoder gradients + scattered neural-point feature gradients
-    clid_adam_step       Adam on the touched feature rows and the decoder tensors
+    clid_train_fused           search + IDW blend + decoder (+ closed-form d sdf / d x) + bce / eikonal loss +
+                               feature-gradient scatter + certainty / ts side effects, one kernel; one 64-byte
+                               decoder-gradient row per evaluated point into scratch
+    clid_decoder_grad_reduce   dense reduction of the rows into the flat decoder gradient
+    clid_adam_step             Adam on the touched feature rows and the decoder tensors
 
-Four launches per iteration, no host synchronisation, no intermediate [N, 81, .] tensors.
-One `FusedTrainer` lives for one `mapping()` call, exactly like the reference's per-call Adam
-(fresh moments, step counter from 1).
+Three launches per iteration (plus a one-thread kernel when the step counter lives on the device), no host
+synchronisation, no intermediate [N, 81, .] tensors.  Configurations the one-kernel path does not cover
+(explicit eikonal subsets, decimations other than 10) run as clid_query_forward + clid_sdf_loss +
+clid_train_backward.  One `FusedTrainer` lives for one `mapping()` call, exactly like the reference's per-call
+Adam (fresh moments, step counter from 1).  `StepPipeline` replays the whole iteration as a CUDA graph.
 """
 from __future__ import annotations
 
@@ -92,8 +95,8 @@ class FusedTrainer:
         self.forward_events = None  # bench hook: list that receives (start, end) CUDA events of the forward
         self.backward_events = None
         self.launches = 0           # kernels of libclid_sdf.so launched so far
-        # analytic (or no) eikonal: forward + loss + backward run as ONE kernel (clid_train_fused);
-        # set False to use the three-launch path (always used by the numerical-gradient mode)
+        # forward + loss + backward run as ONE kernel (clid_train_fused), analytic and numerical eikonal;
+        # set False to use the three-launch path (clid_query_forward / clid_sdf_loss / clid_train_backward)
         self.single_kernel = True
         self._scratch = None        # device scratch of clid_train_fused (rows for the decoder-gradient reduction)
         self.use_scratch = True     # False: the warps fold the decoder gradients inside the one kernel
@@ -265,7 +268,8 @@ class FusedTrainer:
 
     def _finish_iteration(self, loss, apply_step, sync, shards):
         if shards is not None:
-            # spatial sharding: ONE flat all-reduce of [decoder grads | loss | shared-row gradients]
+            # spatial sharding: 3 kB all-reduce of [decoder grads | loss] + neighbour exchange of the band rows
+            # (or ONE flat all-reduce of [decoder grads | loss | shared-row gradients] when bands overlap)
             self.sync_spatial(loss, shards)
         elif sync:
             # replicated sharding: flat all-reduce for [decoder grads | loss scalars]; the replicated

@@ -4,7 +4,8 @@
 Same constructor, attributes (replay-pool tensors, ``new_idx``, ``adaptive_iter_offset`` ...) and
 method names; ``mapping(iter_count)`` is the training function ``slam.py:200`` calls (``train`` is
 an alias for the name BASELINE.json uses).  The loop body runs through the fused CUDA path
-(``ops.train.FusedTrainer``: four launches per iteration, no host synchronisation) whenever the
+(``ops.train.FusedTrainer``: three launches per iteration, no host synchronisation; long calls replay
+them as one CUDA graph) whenever the
 configuration is covered -- every shipped run file is -- and otherwise through the unfused CUDA
 path (our ``query_feature`` autograd Function + the torch decoder + torch.optim), which accepts
 every loss the reference implements.  Neither path has a CPU fallback.

@@ -224,8 +224,9 @@ CLID_API int clid_train_backward(const ClidMap* map, const ClidDecoder* dec, con
 /* One-kernel mapping iteration: clid_query_forward (training mode) + clid_sdf_loss +
  * clid_train_backward fused per evaluated point, i.e. utils/mapper.py:660-835 from query_feature to
  * cur_loss.backward() in a single launch.  Same outputs and accumulation rules as the three
- * calls; sdf_out [n] is optional.  `map` needs everything clid_query_forward needs
- * (CLID_USE_BRICKS honoured) plus certainty_accum.
+ * calls, except that with `scratch` the decoder gradient is left as per-point rows for
+ * clid_decoder_grad_reduce (below); sdf_out [n] is optional.  `map` needs everything
+ * clid_query_forward needs (CLID_USE_BRICKS honoured) plus certainty_accum.
  *   numerical == 0: analytic eikonal gradient (loss.numerical_grad_on: False); d L / d logit and
  *                   d L / d grad of a sample depend on that sample alone.
  *   numerical != 0: get_numerical_gradient (utils/mapper.py:985-1034) on the samples i % 10 == 0
