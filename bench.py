@@ -477,9 +477,20 @@ def cpu_reference(mode, steps, warmup, n):
         if i >= warmup:
             times.append(dt)
     total = sum(times)
+    # the inference variant beside it (workload i): query_feature -> Decoder.sdf -> get_gradient
+    fwd_times = []
+    for i in range(3):
+        x = batches[i % 2][0].clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        z, _, _, _ = oc.query_feature(m, x, None, training_mode=False, query_locally=True)
+        oc.sdf_gradient(x, oc.decoder_sdf(params, z, cfg.sdf_scale))
+        if i >= 1:
+            fwd_times.append(time.perf_counter() - t0)
     return {"value": n * steps / total, "unit": "samples/s", "cores": threads, "kind": "port",
             "sample": f"{steps} steps of {n} samples on the same 1.08M-point world ({mode} gradient), after {warmup} warm-up",
-            "ms_per_step": total / steps * 1e3}
+            "ms_per_step": total / steps * 1e3,
+            "inference_forward": {"value": n * len(fwd_times) / sum(fwd_times), "unit": "samples/s",
+                                  "sample": f"{len(fwd_times)} forward + gradient passes of {n} queries, after 1 warm-up"}}
 
 
 def run_reference(args):
