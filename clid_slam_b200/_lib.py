@@ -126,6 +126,7 @@ _SIGNATURES = [
     ("clid_decoder_grad_reduce", C.c_int,
      [C.POINTER(ClidDecoder), C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p]),
     ("clid_adam_step", C.c_int, [C.POINTER(ClidAdamArgs), C.c_void_p]),
+    ("clid_adam_advance", C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     ("clid_radius_search", C.c_int,
      [C.POINTER(ClidMap), C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("clid_query_certainty", C.c_int,

@@ -308,9 +308,10 @@ int clid_adam_step(const ClidAdamArgs* a, clid_stream_t stream) {
   p.dec_grad = a->dec_grad; p.dec_m = a->dec_m; p.dec_v = a->dec_v;
   p.beta1 = a->beta1; p.beta2 = a->beta2; p.eps = a->eps; p.weight_decay = a->weight_decay;
   if (a->step_state) {
-    // device-resident step counter (graph-capturable): advance it, then read the scalars in the kernel
+    // device-resident step counter (graph-capturable): advance it (unless step < 0), then read the scalars
+    // in the kernel
     AdamStepState* st = static_cast<AdamStepState*>(a->step_state);
-    adam_advance_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(st, a->lr, a->beta1, a->beta2);
+    if (a->step >= 0) adam_advance_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(st, a->lr, a->beta1, a->beta2);
     p.step_scalars = &st->step_size;
   } else {
     // torch evaluates the bias corrections in double on the host (torch/optim/adam.py)
@@ -319,10 +320,28 @@ int clid_adam_step(const ClidAdamArgs* a, clid_stream_t stream) {
     p.step_size = (float)((double)a->lr / bc1);
     p.bc2_sqrt = (float)sqrt(bc2);
   }
+#ifndef CLID_ADAM_BLOCKS_PER_SM
+#define CLID_ADAM_BLOCKS_PER_SM 16
+#endif
   int grid = elementwise_grid(a->rows * 2 > 0 ? a->rows * 2 : 1, 256);
+  {
+    // persistent blocks: leave thread slots for the decoder-gradient reduction that may run beside this kernel
+    DeviceInfo info;
+    if (int rc = device_info(&info)) return rc;
+    const int cap = info.sm_count * CLID_ADAM_BLOCKS_PER_SM;
+    if (grid > cap) grid = cap;
+  }
   adam_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "adam_kernel launch");
+  return CLID_OK;
+}
+
+int clid_adam_advance(void* step_state, float lr, float beta1, float beta2, clid_stream_t stream) {
+  if (!step_state) return set_error(CLID_EINVAL, "step_state is NULL");
+  adam_advance_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<AdamStepState*>(step_state), lr, beta1, beta2);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "adam_advance_kernel launch");
   return CLID_OK;
 }
 

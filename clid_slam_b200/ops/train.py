@@ -103,6 +103,11 @@ class FusedTrainer:
         # device-resident Adam step counter {step, step_size, bc2_sqrt, pad} (ClidAdamArgs.step_state):
         # lets a whole iteration be captured in a CUDA graph (StepPipeline); None = host-side counter
         self.step_state = None
+        # single GPU, apply_step=True: the decoder-gradient reduction and the decoder's Adam step run on a side
+        # stream concurrently with the (HBM-bound) Adam step of the feature rows, which does not depend on them
+        self.overlap_decoder = True
+        self._side_stream = None
+        self._pending_reduce = None
 
     # ------------------------------------------------------------------
     def _shifted(self, x: torch.Tensor, eik_index: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -140,7 +145,8 @@ class FusedTrainer:
         # subsets (eik_index, sharded batches) and other decimations take the three-launch path
         one_kernel_ok = (not numerical) or (int(cfg.gradient_decimation) == 10 and eik_index is None)
         if self.single_kernel and one_kernel_ok:
-            loss = self._iteration_single_kernel(x, label, ts, weight, n_global, nd_global, numerical)
+            defer = bool(apply_step and exchange and shards is None and not sync and self._want_overlap())
+            loss = self._iteration_single_kernel(x, label, ts, weight, n_global, nd_global, numerical, defer_reduce=defer)
             if not exchange:  # the caller runs pack / all-reduce / unpack / adam_step itself (StepPipeline)
                 self.losses.append(loss)
                 return loss
@@ -210,7 +216,8 @@ class FusedTrainer:
 
         return self._finish_iteration(loss, apply_step, sync, shards)
 
-    def _iteration_single_kernel(self, x, label, ts, weight, n_global, nd_global=0, numerical=False):
+    def _iteration_single_kernel(self, x, label, ts, weight, n_global, nd_global=0, numerical=False,
+                                 defer_reduce=False):
         """clid_train_fused: forward + loss + backward in one launch (analytic or numerical eikonal)."""
         npm, dec, lib, dev = self.npm, self.dec, self.lib, self.device
         n = x.shape[0]
@@ -258,13 +265,33 @@ class FusedTrainer:
             self.forward_events.append((ev0, ev1))
         self.launches += 1 if n > 0 else 0
         if a.scratch and n > 0:
-            # the per-point decoder-gradient rows sit in scratch: dense reduction into dec_grad
-            with torch.cuda.device(dev):
-                rc = lib.clid_decoder_grad_reduce(C.byref(ds), a.scratch, n, a.numerical, flags, self.dec_grad.data_ptr(),
-                                                  _lib.current_stream(dev))
-            _lib.check(rc, "clid_decoder_grad_reduce")
-            self.launches += 1
+            # the per-point decoder-gradient rows sit in scratch: dense reduction into dec_grad -- now, or
+            # on the side stream of the following adam_step()
+            self._pending_reduce = (ds, a.scratch, n, a.numerical, flags)
+            if not defer_reduce:
+                self._reduce_pending()
         return loss
+
+    def _want_overlap(self) -> bool:
+        """Fork the decoder side of the optimiser step onto a second stream?  It costs two extra host calls,
+        so: always inside a CUDA-graph capture (the host cost is paid once), otherwise only when the feature
+        table is large enough for its Adam step to hide the decoder-gradient reduction."""
+        if not self.overlap_decoder or self.dec_grad is None:
+            return False
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        return bool(torch.cuda.is_current_stream_capturing() or self.rows >= 262144)
+
+    def _reduce_pending(self) -> None:
+        if self._pending_reduce is None:
+            return
+        ds, scratch, n, numerical, flags = self._pending_reduce
+        self._pending_reduce = None
+        with torch.cuda.device(self.device):
+            rc = self.lib.clid_decoder_grad_reduce(C.byref(ds), scratch, n, numerical, flags, self.dec_grad.data_ptr(),
+                                                   _lib.current_stream(self.device))
+        _lib.check(rc, "clid_decoder_grad_reduce")
+        self.launches += 1
 
     def _finish_iteration(self, loss, apply_step, sync, shards):
         if shards is not None:
@@ -357,31 +384,56 @@ class FusedTrainer:
             tdist.all_reduce(flat, op=tdist.ReduceOp.SUM)
         self.unpack_spatial(flat, loss, shards)
 
-    def adam_step(self) -> None:
-        cfg, npm, lib, dev = self.cfg, self.npm, self.lib, self.device
-        stream = _lib.current_stream(dev)
+    def _adam_call(self, features: bool, decoder: bool, step_arg: int) -> None:
+        cfg, npm, dev = self.cfg, self.npm, self.device
+        aa = _lib.ClidAdamArgs()
+        if features and self.train_features:
+            aa.feat = npm.local_geo_features.data.data_ptr()
+            aa.feat_grad, aa.feat_m, aa.feat_v = (self.feat_grad.data_ptr(), self.feat_m.data_ptr(),
+                                                  self.feat_v.data_ptr())
+            aa.touched = None if self.touched is None else self.touched.data_ptr()
+            aa.rows = self.rows
+        else:
+            aa.rows = 0
+        aa.dec_tensors = len(self.dec_tensors)
+        for i, p in enumerate(self.dec_tensors):
+            aa.dec_param[i] = None if p is None else p.data.data_ptr()
+            aa.dec_numel[i] = self.dec_numel[i]
+        if decoder and self.dec_grad is not None:
+            aa.dec_grad, aa.dec_m, aa.dec_v = self.dec_grad.data_ptr(), self.dec_m.data_ptr(), self.dec_v.data_ptr()
+        aa.lr, aa.beta1, aa.beta2 = float(cfg.lr), 0.9, 0.99
+        aa.eps, aa.weight_decay, aa.step = float(cfg.adam_eps), float(cfg.weight_decay), step_arg
+        aa.step_state = None if self.step_state is None else self.step_state.data_ptr()
         with torch.cuda.device(dev):
-            self.step += 1
-            aa = _lib.ClidAdamArgs()
-            if self.train_features:
-                aa.feat = npm.local_geo_features.data.data_ptr()
-                aa.feat_grad, aa.feat_m, aa.feat_v = (self.feat_grad.data_ptr(), self.feat_m.data_ptr(),
-                                                      self.feat_v.data_ptr())
-                aa.touched = None if self.touched is None else self.touched.data_ptr()
-                aa.rows = self.rows
-            else:
-                aa.rows = 0
-            aa.dec_tensors = len(self.dec_tensors)
-            for i, p in enumerate(self.dec_tensors):
-                aa.dec_param[i] = None if p is None else p.data.data_ptr()
-                aa.dec_numel[i] = self.dec_numel[i]
-            if self.dec_grad is not None:
-                aa.dec_grad, aa.dec_m, aa.dec_v = self.dec_grad.data_ptr(), self.dec_m.data_ptr(), self.dec_v.data_ptr()
-            aa.lr, aa.beta1, aa.beta2 = float(cfg.lr), 0.9, 0.99
-            aa.eps, aa.weight_decay, aa.step = float(cfg.adam_eps), float(cfg.weight_decay), self.step
-            aa.step_state = None if self.step_state is None else self.step_state.data_ptr()
-            _lib.check(lib.clid_adam_step(C.byref(aa), stream), "clid_adam_step")
-            self.launches += 1
+            _lib.check(self.lib.clid_adam_step(C.byref(aa), _lib.current_stream(dev)), "clid_adam_step")
+        self.launches += 1
+
+    def adam_step(self) -> None:
+        dev = self.device
+        self.step += 1
+        if self._pending_reduce is None or self.dec_grad is None:
+            self._reduce_pending()
+            self._adam_call(True, True, self.step)
+            return
+        # fork: [decoder-gradient reduction -> Adam on the decoder] beside [Adam on the feature rows]
+        main = torch.cuda.current_stream(dev)
+        side = self._side_stream
+        step_arg = self.step
+        if self.step_state is not None:
+            with torch.cuda.device(dev):
+                rc = self.lib.clid_adam_advance(self.step_state.data_ptr(), float(self.cfg.lr), 0.9, 0.99, main.cuda_stream)
+            _lib.check(rc, "clid_adam_advance")
+            step_arg = -1  # both launches below belong to the step that was just advanced
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            self._reduce_pending()
+            self._adam_call(False, True, step_arg)
+        self._adam_call(True, False, step_arg)
+        join = torch.cuda.Event()
+        join.record(side)
+        main.wait_event(join)
 
 
 class StepPipeline:
@@ -438,6 +490,7 @@ class StepPipeline:
         self.free = [torch.cuda.Event() for _ in range(nb)]    # the step that read buffer k has finished
         self.graphs, self.losses = [], []
         trainer.npm.brick_index(True)  # build the index outside the capture
+        trainer._want_overlap()        # creates the side stream of the forked optimiser step outside the capture
         # warm-up on a side stream (first launches configure kernel attributes), then capture
         state = self._snapshot()
         side = torch.cuda.Stream(device=dev)
@@ -545,5 +598,5 @@ class StepPipeline:
 
     @property
     def launches_per_step(self) -> int:
-        # fused kernel [+ decoder-gradient reduction] + Adam advance + Adam
-        return 3 + (1 if self.trainer.dec_grad is not None else 0)
+        # fused kernel + Adam advance + Adam on the features [+ decoder-gradient reduction + Adam on the decoder]
+        return 3 + (2 if self.trainer.dec_grad is not None else 0)

@@ -288,6 +288,7 @@ class Mapper:
         trainer.step_state = torch.zeros(4, dtype=torch.int32, device=dev)  # device-side Adam step counter
         history = torch.empty(iter_count, 3, dtype=torch.float32, device=dev)
         history[0].copy_(body())  # first iteration eagerly: builds the brick index, configures the kernels
+        trainer._want_overlap()  # the side stream of the forked optimiser step must exist before the capture
         graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize(dev)
         with torch.cuda.graph(graph):

@@ -288,7 +288,10 @@ typedef struct ClidAdamArgs {
   float* dec_m;
   float* dec_v;
   float lr, beta1, beta2, eps, weight_decay;
-  int32_t step;            /* 1-based, shared by every parameter like torch's per-call optimiser */
+  int32_t step;            /* 1-based, shared by every parameter like torch's per-call optimiser.  With
+                              step_state: >= 0 advances the device counter first, < 0 uses it as it is
+                              (a second call for the same optimiser step, e.g. decoder and features
+                              updated by two concurrent launches after one clid_adam_advance)        */
   void* step_state;        /* NULL, or 16 bytes of device memory {int32 step; float step_size; float
                               bc2_sqrt; pad} owned by the caller and zero-initialised when the optimiser
                               is created.  With it the step counter lives on the device: the call first
@@ -297,6 +300,9 @@ typedef struct ClidAdamArgs {
                               can be captured once in a CUDA graph and replayed.                       */
 } ClidAdamArgs;
 CLID_API int clid_adam_step(const ClidAdamArgs* args, clid_stream_t stream);
+/* step_state.step += 1 and the bias-correction scalars of the new step (what clid_adam_step does first when
+ * step >= 0).  For callers that split one optimiser step over several clid_adam_step(step < 0) launches. */
+CLID_API int clid_adam_advance(void* step_state, float lr, float beta1, float beta2, clid_stream_t stream);
 
 /* NeuralPoints.radius_neighborhood_search (model/neural_points.py:971-1030): the raw candidate
  * table.  dist2_out [n,kc] f32, idx_out [n,kc] int64 global ids (-1 invalid).  Only
