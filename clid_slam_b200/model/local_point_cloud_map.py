@@ -11,7 +11,6 @@ wins, what the reference's CPU index_put does).
 """
 from __future__ import annotations
 
-import math
 
 import torch
 

@@ -20,7 +20,6 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from .. import _lib
 from ..ops import query as _q
 from ..utils.tools import voxel_down_sample_min_value_torch, voxel_down_sample_torch
 

@@ -16,7 +16,6 @@ The index is rebuilt lazily whenever the map changes (per frame), with torch ops
 """
 from __future__ import annotations
 
-import ctypes as C
 import math
 from functools import lru_cache
 from typing import Optional

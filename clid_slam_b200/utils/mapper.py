@@ -16,8 +16,6 @@ Not mirrored (outside the hot path, no caller in CLID-SLAM): ``bundle_adjustment
 from __future__ import annotations
 
 import os
-
-import math
 import sys
 
 import torch
@@ -25,8 +23,8 @@ import torch.nn.functional as F
 
 from ..ops import train as _train
 from .data_sampler import DataSampler
-from .loss import color_diff_loss, sdf_bce_loss, sdf_diff_loss, sdf_zhong_loss
-from .tools import get_gradient, get_time, setup_optimizer, transform_batch_torch, transform_torch
+from .loss import sdf_bce_loss, sdf_diff_loss, sdf_zhong_loss
+from .tools import get_gradient, setup_optimizer, transform_batch_torch, transform_torch
 
 
 class Mapper:

@@ -7,7 +7,6 @@ Plot / wandb / Open3D / PCA helpers of the reference file are out of scope.
 from __future__ import annotations
 
 import time
-from typing import Optional
 
 import torch
 import torch.nn as nn
