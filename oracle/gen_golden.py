@@ -435,7 +435,7 @@ def clid_sampler_case(ref, name, cfg, seed):
 
 
 def main():
-    """python -m oracle.gen_golden [query|train|map|sampler]   (no argument = everything)"""
+    """python -m oracle.gen_golden [query|train|train_widths|map|sampler]   (no argument = everything)"""
     only = sys.argv[1] if len(sys.argv) > 1 else None
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     ref = ref_loader.load()
@@ -455,6 +455,9 @@ def main():
     if only in (None, "train"):
         print("train fixtures")
         _train_cases(ref, one_frame, two_frames)
+    if only in (None, "train_widths"):
+        print("train fixtures, other decoder widths")
+        _train_width_cases(ref, one_frame)
     if only in (None, "map"):
         print("map fixtures")
         _map_cases(ref, two_frames)
@@ -490,6 +493,12 @@ def _train_cases(ref, one_frame, two_frames):
     train_case(ref, "analytic_layernorm", make_ref_config(ref, layer_norm_on=True, numerical_grad=False), one_frame, [0.0], 2048, 2, 26)
     train_case(ref, "numerical_frozen", make_ref_config(ref), one_frame, [0.0], 2048, 2, 27, freeze_decoder=True)
     train_case(ref, "analytic_unweighted", make_ref_config(ref, numerical_grad=False, loss_weight_on=False), one_frame, [0.0], 1024, 2, 28)
+
+
+def _train_width_cases(ref, one_frame):
+    """One hidden level at the other widths the fused kernels are compiled for (H = 32, 128)."""
+    train_case(ref, "analytic_l1h32", make_ref_config(ref, numerical_grad=False, geo_mlp_hidden_dim=32), one_frame, [0.0], 2048, 2, 29)
+    train_case(ref, "numerical_l1h128", make_ref_config(ref, geo_mlp_hidden_dim=128), one_frame, [0.0], 2048, 2, 30)
 
 
 def _map_cases(ref, two_frames):
