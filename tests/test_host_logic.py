@@ -263,3 +263,23 @@ def test_neighbour_exchange_with_three_gloo_ranks():
         private = (owner == r) & ~in_band
         private[-1] = False
         assert torch.all(outs[r]["grad"][private] == float(r + 1))
+
+
+def test_spatial_shards_bands_and_pairwise_flag():
+    """Band rows partition correctly; slabs narrower than two bands switch the exchange to the flat all-reduce."""
+    pts = torch.stack((torch.arange(80, dtype=torch.float32) + 0.5, torch.zeros(80), torch.zeros(80)), 1)
+    wide = cdist.SpatialShards(pts, 1.0, reach=2, world_size=4, axis=0)
+    assert wide.pairwise and len(wide.band_rows) == 3
+    union = torch.cat(wide.band_rows).sort().values
+    assert torch.equal(union, wide.shared_rows[wide.shared_rows < 80])  # the padding row is never shared
+    for j, rows in enumerate(wide.band_rows):  # band j hugs boundary j: reach + margin = 3 cells either side
+        b = int(wide.boundaries[j])
+        assert rows.tolist() == list(range(b - 3, b + 3))
+    left, right = wide.neighbour_rows(0)
+    assert left is None and torch.equal(right, wide.band_rows[0])
+    left, right = wide.neighbour_rows(3)
+    assert right is None and torch.equal(left, wide.band_rows[2])
+    narrow = cdist.SpatialShards(pts, 1.0, reach=2, world_size=20, axis=0)  # 4-cell slabs, 6-cell bands
+    assert not narrow.pairwise
+    with pytest.raises(ValueError):
+        cdist.NeighbourExchange(narrow, 1, torch.zeros(81, 8))
