@@ -25,14 +25,13 @@ TIME_FILTER = 1 << 2
 LAYER_NORM = 1 << 3
 LEAKY_RELU = 1 << 4
 USE_BRICKS = 1 << 5
-TILE_KERNELS = 1 << 6
 
 _f32p = C.c_void_p  # device pointers travel as plain addresses
 
 
 class ClidBricks(C.Structure):
     _fields_ = [
-        ("headers", C.c_void_p), ("records", C.c_void_p), ("stencil", C.c_void_p),
+        ("headers", C.c_void_p), ("hood", C.c_void_p), ("records", C.c_void_p), ("stencil", C.c_void_p),
         ("origin", C.c_int32 * 3), ("dims", C.c_int32 * 3), ("span", C.c_int32), ("reach", C.c_int32),
         ("n_records", C.c_int32), ("apron", C.c_int32),
     ]

@@ -11,7 +11,7 @@
 #include "query_bwd.cuh"
 #include "query_fwd.cuh"
 #include "train.cuh"
-#include "tile_kernel.cuh"
+#include "decoder_grad.cuh"
 #include "train_fused.cuh"
 
 namespace clid {
@@ -59,7 +59,7 @@ static int check_map(const ClidMap* m, uint32_t flags) {
   if (m->knn < 1 || m->knn > CLID_MAX_KNN) return set_error(CLID_EINVAL, "knn %d outside 1..%d", m->knn, CLID_MAX_KNN);
   if (!(m->resolution > 0.f)) return set_error(CLID_EINVAL, "resolution must be positive");
   if (!m->gather_points || !m->gather_features) return set_error(CLID_EINVAL, "gather arrays are NULL");
-  if (!aligned16(m->gather_features)) return set_error(CLID_EINVAL, "gather_features must be 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(m->gather_features) & 31u) return set_error(CLID_EINVAL, "gather_features must be 32-byte aligned (rows are read with 256-bit loads)");
   if (flags & CLID_USE_BRICKS) {
     if (!m->bricks) return set_error(CLID_EINVAL, "CLID_USE_BRICKS without ClidMap.bricks");
     const ClidBricks* b = m->bricks;
@@ -68,6 +68,7 @@ static int check_map(const ClidMap* m, uint32_t flags) {
       return set_error(CLID_EUNSUPPORTED, "brick index must have span 2, a one-brick apron and reach <= 2 (span %d, apron %d, reach %d)",
                        b->span, b->apron, b->reach);
     if (!aligned16(b->headers) || !aligned16(b->records)) return set_error(CLID_EINVAL, "brick arrays must be 16-byte aligned");
+    if (b->hood && (reinterpret_cast<uintptr_t>(b->hood) & 127u)) return set_error(CLID_EINVAL, "ClidBricks.hood must be 128-byte aligned");
   } else {
     if (m->kc < 1 || m->kc > CLID_MAX_KC) return set_error(CLID_EINVAL, "kc %d outside 1..%d", m->kc, CLID_MAX_KC);
     if (!m->buffer_pt_index || m->buffer_size <= 0 || !m->neighbor_dx) return set_error(CLID_EINVAL, "hash table arguments are NULL/empty");
@@ -146,17 +147,6 @@ int clid_query_forward(const ClidMap* map, const ClidDecoder* dec, const float* 
   p.ts = ts;
   p.n = n;
   p.flags = flags;
-  // brick index with an apron, one-level decoder, plain inference outputs: phase-parked tile kernel
-  if ((flags & CLID_TILE_KERNELS) && (flags & CLID_USE_BRICKS) && dec && !(flags & CLID_TRAINING_MODE) && !out->z && !out->weights && !out->knn_idx &&
-      tile_supported(*map, *dec, *map->bricks)) {
-    TileParams t;
-    memset(&t, 0, sizeof(t));
-    t.map = *map; t.dec = *dec; t.bricks = *map->bricks;
-    t.x = x; t.ts = ts;
-    t.sdf_out = out->sdf; t.grad_out = out->grad; t.nn_count = out->nn_count; t.certainty = out->certainty;
-    t.n = n; t.flags = flags;
-    return launch_tile(t, kTileInfer, static_cast<cudaStream_t>(stream));
-  }
   return (flags & CLID_USE_BRICKS) ? dispatch_query_bricks(p, dec != nullptr, static_cast<cudaStream_t>(stream))
                                    : dispatch_query_hashed(p, dec != nullptr, static_cast<cudaStream_t>(stream));
 }
@@ -221,7 +211,7 @@ int clid_train_backward(const ClidMap* map, const ClidDecoder* dec, const float*
 
 size_t clid_train_fused_scratch_bytes(int64_t n, int32_t numerical) {
   if (n <= 0) return 0;
-  const int64_t per_tile = numerical ? kNumTile : 32;
+  const int64_t per_tile = numerical ? kNumTileSamples : 32;
   const int64_t tiles = (n + per_tile - 1) / per_tile;
   return (size_t)tiles * 32 * kFoldRow * sizeof(float);
 }
@@ -253,18 +243,6 @@ int clid_train_fused(const ClidMap* map, const ClidDecoder* dec, const ClidTrain
   }
   const bool have_scratch = a->scratch && a->scratch_bytes >= clid_train_fused_scratch_bytes(a->n, a->numerical);
   if (a->scratch && (reinterpret_cast<uintptr_t>(a->scratch) & 15u)) return set_error(CLID_EINVAL, "scratch must be 16-byte aligned");
-  if ((flags & CLID_TILE_KERNELS) && (flags & CLID_USE_BRICKS) && tile_supported(*map, *dec, *map->bricks) &&
-      (!a->dec_grad || have_scratch)) {
-    TileParams t;
-    memset(&t, 0, sizeof(t));
-    t.map = *map; t.dec = *dec; t.bricks = *map->bricks;
-    t.x = p.x; t.ts = p.ts; t.label = p.label; t.weight = p.weight;
-    t.sdf_out = p.sdf_out; t.gfeat = p.gfeat; t.touched = p.touched; t.loss = p.loss;
-    t.fold_rows = p.dec_grad ? static_cast<float*>(a->scratch) : nullptr;
-    t.n = p.n; t.n_norm = p.n_norm; t.nd_norm = p.nd_norm;
-    t.weight_e = p.weight_e; t.num_eps = p.num_eps; t.weighted = p.weighted; t.flags = flags;
-    return launch_tile(t, a->numerical ? kTileTrainNumerical : kTileTrainAnalytic, static_cast<cudaStream_t>(stream));
-  }
   if (p.dec_grad && have_scratch) {
     // decoder-gradient rows go to scratch; a dense reduction kernel folds them afterwards
     p.fold_rows = static_cast<float*>(a->scratch);

@@ -85,9 +85,15 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 }
 
 // ---- decoder weights staged in shared memory --------------------------------------
-// layout (floats): W0[H][kInPad] | b0[H] | {Wl[H][H] | bl[H]} (levels-1) | wout[H] | bout | pad
+// layout (floats): W0 (H * kInPad) | b0[H] | {Wl[H][H] | bl[H]} (levels-1) | wout[H] | bout | pad
+// W0 of a one-level decoder is stored UNIT-PAIR interleaved for mlp_l1_pairs: element (j, i) sits at
+// (j / 2) * 2 kInPad + 2 i + (j & 1), i.e. pair p holds (W[2p][i], W[2p+1][i]) for i = 0..11 (i = 11 is
+// zero padding); deeper decoders keep row-major rows [H][kInPad].
 template <int H, int L>
 struct MlpLayout {
+  __host__ __device__ static constexpr int w0_index(int j, int i) {
+    return L == 1 ? (j >> 1) * (2 * kInPad) + 2 * i + (j & 1) : j * kInPad + i;
+  }
   static constexpr int kW0 = 0;
   static constexpr int kB0 = kW0 + H * kInPad;
   static constexpr int kHidden = kB0 + H;  // start of level-1.. blocks
@@ -119,10 +125,10 @@ __device__ __forceinline__ void stage_decoder(float* sm, const ClidDecoder& dec)
     const int i = threadIdx.x + r * blockDim.x;
     if (i < kW) {
       const int j = i / kIn, c = i - j * kIn;
-      sm[Lay::kW0 + j * kInPad + c] = v[r];
+      sm[Lay::kW0 + Lay::w0_index(j, c)] = v[r];
     }
   }
-  for (int j = threadIdx.x; j < H; j += blockDim.x) sm[Lay::kW0 + j * kInPad + kIn] = 0.f;  // padding column
+  for (int j = threadIdx.x; j < H; j += blockDim.x) sm[Lay::kW0 + Lay::w0_index(j, kIn)] = 0.f;  // padding column
   if (threadIdx.x < H) {
     sm[Lay::kB0 + threadIdx.x] = b;
     sm[Lay::kWout + threadIdx.x] = wo;
@@ -142,58 +148,59 @@ __device__ __forceinline__ void stage_decoder(float* sm, const ClidDecoder& dec)
   if (threadIdx.x == 0) sm[Lay::kBout] = dec.out_bias ? dec.out_bias[0] : 0.f;
 }
 
-// One-hidden-level decoder with Blackwell's packed fp32 FMA (FFMA2, `fma.rn.f32x2`, sm_100+): the
-// 11-wide dot product and the 11-wide a += c_j W0[j] update are each 6 two-lane FMAs on register
-// pairs instead of 11 scalar ones, which halves the FMA-pipe instruction count of the decoder (the
-// largest block of issued instructions in the fused kernels).  Weights come from shared memory as
-// three broadcast LDS.128 per hidden unit.  Optionally records the activation pattern as bit
-// masks (unit j -> bit j % 32 of word j / 32) for the backward's decoder-gradient fold.
+// One-hidden-level decoder with Blackwell's packed fp32 FMA (FFMA2, `fma.rn.f32x2`, sm_100+), two hidden
+// units per instruction: with the unit-pair interleaved W0 (MlpLayout) the pre-activations of units
+// (2p, 2p+1) are one chain of packed FMAs over the 11 inputs against (z_i, z_i) -- no horizontal adds, no
+// register shuffling, the LDS.128 results are the FFMA2 operands -- and a = d out / d z accumulates as
+// (even-unit, odd-unit) partial sums, 11 packed FMAs per pair, folded once at the end.  Per unit: 11 FFMA2
+// instead of 12 FFMA2 + 3 FADD + pairing MOVs, and 4 LDS instead of 5.  Optionally records the activation
+// pattern as bit masks (unit j -> bit j % 32 of word j / 32) for the backward's decoder-gradient fold.
 template <int H, bool kMask>
-__device__ __forceinline__ void mlp_l1_ffma2(const float* __restrict__ sm, const float (&z)[kIn], float slope,
+__device__ __forceinline__ void mlp_l1_pairs(const float* __restrict__ sm, const float (&z)[kIn], float slope,
                                              float& out, float (&a)[kIn], uint32_t* __restrict__ mask) {
   using Lay = MlpLayout<H, 1>;
-  const float4* w0 = reinterpret_cast<const float4*>(sm + Lay::kW0);
-  float2 zp[6], ap[6];
+  const float4* w = reinterpret_cast<const float4*>(sm + Lay::kW0);  // pair p: float4 6p .. 6p+5
+  const float2* b2 = reinterpret_cast<const float2*>(sm + Lay::kB0);
+  const float2* wo2 = reinterpret_cast<const float2*>(sm + Lay::kWout);
+  float2 zz[kIn], acc[kIn];
 #pragma unroll
-  for (int i = 0; i < 5; ++i) zp[i] = make_float2(z[2 * i], z[2 * i + 1]);
-  zp[5] = make_float2(z[10], 0.f);
-#pragma unroll
-  for (int i = 0; i < 6; ++i) ap[i] = make_float2(0.f, 0.f);
-  out = sm[Lay::kBout];
+  for (int i = 0; i < kIn; ++i) { zz[i] = make_float2(z[i], z[i]); acc[i] = make_float2(0.f, 0.f); }
+  float2 o2 = make_float2(sm[Lay::kBout], 0.f);
+  const float2 sl2 = make_float2(slope, slope);
 #pragma unroll
   for (int jw = 0; jw < H / 32; ++jw) {
     uint32_t bits = 0u;
-#pragma unroll 8
-    for (int jj = 0; jj < 32; ++jj) {
-      const int j = jw * 32 + jj;
-      const float4 r0 = w0[j * 3 + 0], r1 = w0[j * 3 + 1], r2 = w0[j * 3 + 2];
-      // two independent chains of three packed FMAs
-      float2 p0 = make_float2(sm[Lay::kB0 + j], 0.f);
-      float2 p1 = make_float2(0.f, 0.f);
-      p0 = __ffma2_rn(make_float2(r0.x, r0.y), zp[0], p0);
-      p1 = __ffma2_rn(make_float2(r0.z, r0.w), zp[1], p1);
-      p0 = __ffma2_rn(make_float2(r1.x, r1.y), zp[2], p0);
-      p1 = __ffma2_rn(make_float2(r1.z, r1.w), zp[3], p1);
-      p0 = __ffma2_rn(make_float2(r2.x, r2.y), zp[4], p0);
-      p1 = __ffma2_rn(make_float2(r2.z, r2.w), zp[5], p1);  // r2.w is the zero padding
-      const float pre = (p0.x + p0.y) + (p1.x + p1.y);
-      const bool on = pre > 0.f;
-      if (kMask) bits = (bits >> 1) | (on ? 0x80000000u : 0u);  // after 32 steps unit jj sits at bit jj
-      const float cj = sm[Lay::kWout + j] * (on ? 1.f : slope);
-      out = fmaf(cj, pre, out);
-      const float2 cc = make_float2(cj, cj);
-      ap[0] = __ffma2_rn(make_float2(r0.x, r0.y), cc, ap[0]);
-      ap[1] = __ffma2_rn(make_float2(r0.z, r0.w), cc, ap[1]);
-      ap[2] = __ffma2_rn(make_float2(r1.x, r1.y), cc, ap[2]);
-      ap[3] = __ffma2_rn(make_float2(r1.z, r1.w), cc, ap[3]);
-      ap[4] = __ffma2_rn(make_float2(r2.x, r2.y), cc, ap[4]);
-      ap[5] = __ffma2_rn(make_float2(r2.z, r2.w), cc, ap[5]);
+#pragma unroll 4
+    for (int pp = 0; pp < 16; ++pp) {
+      const int p = jw * 16 + pp;
+      const float4 r0 = w[p * 6 + 0], r1 = w[p * 6 + 1], r2 = w[p * 6 + 2];
+      const float4 r3 = w[p * 6 + 3], r4 = w[p * 6 + 4], r5 = w[p * 6 + 5];
+      float2 e = b2[p], o = make_float2(0.f, 0.f);  // two independent chains over even / odd inputs
+      e = __ffma2_rn(make_float2(r0.x, r0.y), zz[0], e);  o = __ffma2_rn(make_float2(r0.z, r0.w), zz[1], o);
+      e = __ffma2_rn(make_float2(r1.x, r1.y), zz[2], e);  o = __ffma2_rn(make_float2(r1.z, r1.w), zz[3], o);
+      e = __ffma2_rn(make_float2(r2.x, r2.y), zz[4], e);  o = __ffma2_rn(make_float2(r2.z, r2.w), zz[5], o);
+      e = __ffma2_rn(make_float2(r3.x, r3.y), zz[6], e);  o = __ffma2_rn(make_float2(r3.z, r3.w), zz[7], o);
+      e = __ffma2_rn(make_float2(r4.x, r4.y), zz[8], e);  o = __ffma2_rn(make_float2(r4.z, r4.w), zz[9], o);
+      e = __ffma2_rn(make_float2(r5.x, r5.y), zz[10], e);
+      const float2 pre = __fadd2_rn(e, o);
+      const bool on0 = pre.x > 0.f, on1 = pre.y > 0.f;
+      if (kMask) bits = (bits >> 2) | (on0 ? 0x40000000u : 0u) | (on1 ? 0x80000000u : 0u);  // unit jj ends at bit jj
+      const float2 wo = wo2[p];
+      const float2 ws = __fmul2_rn(wo, sl2);
+      const float2 c = make_float2(on0 ? wo.x : ws.x, on1 ? wo.y : ws.y);
+      o2 = __ffma2_rn(c, pre, o2);
+      acc[0] = __ffma2_rn(make_float2(r0.x, r0.y), c, acc[0]);  acc[1] = __ffma2_rn(make_float2(r0.z, r0.w), c, acc[1]);
+      acc[2] = __ffma2_rn(make_float2(r1.x, r1.y), c, acc[2]);  acc[3] = __ffma2_rn(make_float2(r1.z, r1.w), c, acc[3]);
+      acc[4] = __ffma2_rn(make_float2(r2.x, r2.y), c, acc[4]);  acc[5] = __ffma2_rn(make_float2(r2.z, r2.w), c, acc[5]);
+      acc[6] = __ffma2_rn(make_float2(r3.x, r3.y), c, acc[6]);  acc[7] = __ffma2_rn(make_float2(r3.z, r3.w), c, acc[7]);
+      acc[8] = __ffma2_rn(make_float2(r4.x, r4.y), c, acc[8]);  acc[9] = __ffma2_rn(make_float2(r4.z, r4.w), c, acc[9]);
+      acc[10] = __ffma2_rn(make_float2(r5.x, r5.y), c, acc[10]);
     }
     if (kMask) mask[jw] = bits;
   }
+  out = o2.x + o2.y;
 #pragma unroll
-  for (int i = 0; i < 5; ++i) { a[2 * i] = ap[i].x; a[2 * i + 1] = ap[i].y; }
-  a[10] = ap[5].x;
+  for (int i = 0; i < kIn; ++i) a[i] = acc[i].x + acc[i].y;
 }
 
 // Forward of the MLP plus a = d out / d z (back-propagated through the activation masks).
@@ -207,7 +214,7 @@ __device__ __forceinline__ void mlp_value_and_input_grad(const float* __restrict
 #pragma unroll
   for (int i = 0; i < kIn; ++i) a[i] = 0.f;
   if constexpr (L == 1) {
-    mlp_l1_ffma2<H, false>(sm, z, slope, out, a, nullptr);
+    mlp_l1_pairs<H, false>(sm, z, slope, out, a, nullptr);
   } else {
     // level 0
     float h[H], dact[H];
@@ -267,6 +274,14 @@ __device__ __forceinline__ void load_feature_row(const float* __restrict__ feats
   const float4* row = reinterpret_cast<const float4*>(feats + (int64_t)id * kFeat);
   float4 a = __ldg(row), b = __ldg(row + 1);
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// one 32-byte feature row with a single 256-bit load (LDG.E.256, sm_100+)
+__device__ __forceinline__ void load_feature_row256(const float* __restrict__ feats, int id, float (&f)[kFeat]) {
+  const float* row = feats + (int64_t)id * kFeat;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7])
+               : "l"(row));
 }
 
 // Second moments of a query's neighbourhood.  With t_k = -2 u_k^2 (d u_k / d x = t_k v_k):

@@ -13,7 +13,6 @@ struct QueryParams;
 struct TrainBwdParams;
 struct TrainFusedParams;
 struct QueryBwdParams;
-struct TileParams;
 struct DecoderGradParams;
 
 int set_error(int code, const char* fmt, ...);
@@ -26,7 +25,7 @@ int device_info(DeviceInfo* info);
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// inst_query_bricks.cu / inst_query_hashed.cu
+// inst_query_{bricks,hashed}.cu
 int dispatch_query_bricks(const QueryParams& p, bool has_dec, cudaStream_t stream);
 int dispatch_query_hashed(const QueryParams& p, bool has_dec, cudaStream_t stream);
 // inst_query_bwd.cu
@@ -34,13 +33,11 @@ int launch_query_backward_first(const QueryBwdParams& p, int grid, cudaStream_t 
 int launch_query_backward_second(const QueryBwdParams& p, int grid, cudaStream_t stream);
 // inst_train_bwd.cu
 int dispatch_train_backward(const TrainBwdParams& p, cudaStream_t stream);
-// inst_fused_bricks.cu / inst_fused_hashed.cu
+// inst_fused_{bricks,hashed}.cu
 int dispatch_train_fused_bricks(const TrainFusedParams& p, cudaStream_t stream);
 int dispatch_train_fused_hashed(const TrainFusedParams& p, cudaStream_t stream);
 
-// inst_tile.cu: phase-parked tile kernels (mode: TileMode) and the decoder-gradient reduction
-bool tile_supported(const ClidMap& map, const ClidDecoder& dec, const ClidBricks& bricks);
-int launch_tile(TileParams& p, int mode, cudaStream_t stream);
+// inst_decoder_grad.cu
 int launch_decoder_grad(const DecoderGradParams& p, cudaStream_t stream);
 
 }  // namespace clid

@@ -7,17 +7,9 @@
 //   utils/tools.py:298-311          get_gradient
 #pragma once
 #include "common.cuh"
+#include "search.cuh"
 
 namespace clid {
-
-#ifndef CLID_QUERY_MIN_BLOCKS
-#define CLID_QUERY_MIN_BLOCKS 4  // resident CTAs per SM the forward kernel is register-budgeted for
-#endif
-#ifndef CLID_QUERY_THREADS
-#define CLID_QUERY_THREADS 128
-#endif
-constexpr int kQueryThreads = CLID_QUERY_THREADS;
-constexpr int kBrickSlots = 8;  // span 2: a neighbourhood touches at most 2x2x2 bricks
 
 struct QueryParams {
   ClidMap map;
@@ -30,204 +22,20 @@ struct QueryParams {
   uint32_t flags;
 };
 
-// Ascending top-K by squared distance with an integer payload; ties keep the earlier candidate.
-template <int K>
-struct TopK {
-  float d[K];
-  int id[K];
-  __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int k = 0; k < K; ++k) { d[k] = __int_as_float(0x7f800000); id[k] = -1; }
-  }
-  __device__ __forceinline__ void insert(float dc, int ic) {
-    if (!(dc < d[K - 1])) return;
-    // one pass of compare-exchange from the front: the carried element is always the larger one
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const bool lt = dc < d[k];
-      const float dk = d[k];
-      const int ik = id[k];
-      d[k] = lt ? dc : dk;
-      id[k] = lt ? ic : ik;
-      dc = lt ? dk : dc;
-      ic = lt ? ik : ic;
-    }
-  }
-};
 
-// ---- candidate enumeration through the reference's hash table ----------------------------
-// Payload of the top-K: gather row (local row with CLID_QUERY_LOCALLY, else global id).
-template <int K>
-__device__ __forceinline__ int search_hashed(const ClidMap& m, const int64_t* __restrict__ cell_mod, float px,
-                                             float py, float pz, const bool local, const bool time_filter,
-                                             TopK<K>& top) {
-  constexpr int U = 9;
-  const int gx = cell_of(px, m.resolution), gy = cell_of(py, m.resolution), gz = cell_of(pz, m.resolution);
-  const int64_t B = m.buffer_size;
-  const int64_t m0 = floor_mod((int64_t)gx * m.primes[0] + (int64_t)gy * m.primes[1] + (int64_t)gz * m.primes[2], B);
-  float td_cur = 0.f;
-  if (time_filter) td_cur = m.travel_dist[m.cur_ts];
-  int count = 0;
-  for (int c0 = 0; c0 < m.kc; c0 += U) {
-    int gi[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      int c = c0 + u;
-      int64_t v = -1;
-      if (c < m.kc) {
-        int64_t slot = m0 + cell_mod[c];
-        slot = slot >= B ? slot - B : slot;
-        v = __ldg(m.buffer_pt_index + slot);
-      }
-      gi[u] = (int)v;
-    }
-    float cx[U], cy[U], cz[U];
-    int li[U];
-    int tsc[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      int g = gi[u] < 0 ? 0 : gi[u];  // invalid lanes read row 0 (always mapped); result discarded
-      const float* p = m.neural_points + 3 * (int64_t)g;
-      cx[u] = __ldg(p); cy[u] = __ldg(p + 1); cz[u] = __ldg(p + 2);
-      li[u] = local ? (int)__ldg(m.global2local + g) : g;
-      tsc[u] = time_filter ? __ldg(m.point_ts_create + g) : 0;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      bool ok = gi[u] >= 0;
-      if (time_filter) {
-        float gap = fabsf(td_cur - __ldg(m.travel_dist + tsc[u]));
-        ok = ok && (gap < m.diff_travel_dist_local);
-      }
-      float d2 = dist2_torch(cx[u] - px, cy[u] - py, cz[u] - pz);  // neighbour - query, as the reference
-      ok = ok && !(d2 > m.max_valid_dist2) && li[u] >= 0;
-      if (ok) {
-        ++count;
-        top.insert(d2, li[u]);
-      }
-    }
-  }
-  return count;
+
+// kSearch: how the candidates of a query are enumerated (search.cuh)
+enum SearchKind { kSearchHashed = 0, kSearchBricks = 1 };
+
+// dynamic shared memory of the search phase behind the decoder weights, in floats
+template <int kSearch>
+constexpr int search_smem_floats() {
+  return kSearch == kSearchHashed ? 2 * CLID_MAX_KC : 2 * 64 * kBrickSlots + (int)(sizeof(BrickScratch) / sizeof(float));
 }
 
-// ---- candidate enumeration through the brick index ---------------------------------------
-// Payload of the top-K: record index.  A 64-cell brick is walked as two 32-cell halves (z < 2,
-// z >= 2) so every bit operation is a single 32-bit instruction.  The grid carries a one-brick
-// empty apron (ClidBricks.apron) and a neighbourhood spans 2 x 2 x 2 bricks (span == 2): a query is
-// range-tested once, the eight header addresses follow by constant strides.
-// Phase 1: load the 8 brick headers, AND with the stencil, compact the non-empty (want, occupancy,
-// first-record) half-brick triples into this lane's scratch column (word s of the column is
-// col[s * kStride]: want in slots 0..11, occupancy in 12..23, first record in 24..35).
-// Phase 2 (warp-converged): every lane pops up to kWalkBatch candidates, issues their record loads
-// together, then ranks them; a warp iterates ceil(max-over-lanes(candidates) / kWalkBatch) times
-// instead of diverging inside nested loops.
-// A neighbourhood is at most 5 cells wide (reach <= 2): 5 consecutive z cells touch at most 3 of the
-// 2-cell z halves, so at most 3 x 2 x 2 half-bricks can be non-empty.
-constexpr int kHalfSlots = 12;
-#ifndef CLID_WALK_BATCH
-#define CLID_WALK_BATCH 6   // measured 2 / 4 / 6 / 8: 61.5 / 58.4 / 57.4 / 57.4 us (forward, 131072 queries, cold L2)
-#endif
-constexpr int kWalkBatch = CLID_WALK_BATCH;
-#ifndef CLID_PF_RECORDS
-#define CLID_PF_RECORDS 0   // L2 prefetch of the record lines of every non-empty half-brick: paid off with
-                            // 16-B-per-iteration walks, no longer with 6 record loads in flight per lane
-#endif
-#ifndef CLID_PF_FEATURES
-#define CLID_PF_FEATURES 1  // L2 prefetch of the feature row of every candidate that enters the top-K
-#endif
-
-struct BrickScratch {  // [slot][thread] columns of a 128-thread CTA
-  uint32_t want[kHalfSlots][kQueryThreads];
-  uint32_t occ[kHalfSlots][kQueryThreads];
-  int base[kHalfSlots][kQueryThreads];
-};
-
-template <int K, int kStride>
-__device__ __forceinline__ int search_bricks(const ClidMap& m, const ClidBricks& b, const uint64_t* stencil,
-                                           uint32_t* col, bool live, float px, float py, float pz,
-                                           TopK<K>& top) {
-  const int rx = cell_of(px, m.resolution) - b.origin[0] - b.reach;
-  const int ry = cell_of(py, m.resolution) - b.origin[1] - b.reach;
-  const int rz = cell_of(pz, m.resolution) - b.origin[2] - b.reach;
-  const int bx0 = rx >> 2, by0 = ry >> 2, bz0 = rz >> 2;
-  const int D0 = b.dims[0], D1 = b.dims[1];
-  const bool in = live && (unsigned)bx0 < (unsigned)(D0 - 1) && (unsigned)by0 < (unsigned)(D1 - 1) &&
-                  (unsigned)bz0 < (unsigned)(b.dims[2] - 1);
-  const float4* records = reinterpret_cast<const float4*>(b.records);
-  int nfill = 0;
-  if (in) {
-    const uint2* st = reinterpret_cast<const uint2*>(stencil) + (((rz & 3) * 4 + (ry & 3)) * 4 + (rx & 3)) * 8;
-    const uint4* h0 = reinterpret_cast<const uint4*>(b.headers) + ((int64_t)bz0 * D1 + by0) * D0 + bx0;
-    const int sy = D0, sz = D0 * D1;
-    uint4 h[8];
-#pragma unroll
-    for (int s = 0; s < 8; ++s) h[s] = __ldg(h0 + (s & 1) + ((s >> 1) & 1) * sy + (s >> 2) * sz);
-#pragma unroll
-    for (int s = 0; s < 8; ++s) {
-      const uint2 sten = st[s];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const uint32_t occ = half ? h[s].y : h[s].x;
-        const uint32_t want = occ & (half ? sten.y : sten.x);
-        if (want) {
-          const int base = (int)h[s].z + (half ? __popc(h[s].x) : 0);
-          col[nfill * kStride] = want;
-          col[(kHalfSlots + nfill) * kStride] = occ;
-          col[(2 * kHalfSlots + nfill) * kStride] = (uint32_t)base;
-          ++nfill;
-          // the records of a half-brick are contiguous: pull their first and last line towards L2
-#if CLID_PF_RECORDS
-          prefetch_l2(records + base);
-          prefetch_l2(records + base + __popc(occ) - 1);
-#endif
-        }
-      }
-    }
-  }
-  // cursor over the filled slots: a pointer into the lane's column and the number of slots left
-  int count = 0, left = nfill;
-  const uint32_t* sp = col;
-  uint32_t w = 0, occ = 0;
-  int base = 0;
-  if (nfill > 0) { w = sp[0]; occ = sp[kHalfSlots * kStride]; base = (int)sp[2 * kHalfSlots * kStride]; }
-  while (__any_sync(0xffffffffu, w != 0)) {
-    int rec[kWalkBatch];
-#pragma unroll
-    for (int j = 0; j < kWalkBatch; ++j) {
-      rec[j] = -1;
-      if (w) {
-        const int bit = __ffs(w) - 1;
-        w &= w - 1;
-        rec[j] = base + __popc(occ & ((1u << bit) - 1u));
-        if (w == 0 && left > 1) {
-          --left;
-          sp += kStride;
-          w = sp[0]; occ = sp[kHalfSlots * kStride]; base = (int)sp[2 * kHalfSlots * kStride];
-        }
-      }
-    }
-    float4 r[kWalkBatch];
-#pragma unroll
-    for (int j = 0; j < kWalkBatch; ++j) r[j] = __ldg(records + (rec[j] < 0 ? 0 : rec[j]));
-#pragma unroll
-    for (int j = 0; j < kWalkBatch; ++j) {
-      const float d2 = dist2_torch(r[j].x - px, r[j].y - py, r[j].z - pz);
-      if (rec[j] >= 0 && !(d2 > m.max_valid_dist2)) {
-        ++count;
-        if (d2 < top.d[K - 1]) {
-#if CLID_PF_FEATURES
-          prefetch_l2(m.gather_features + (int64_t)__float_as_int(r[j].w) * kFeat);  // likely neighbour
-#endif
-          top.insert(d2, rec[j]);
-        }
-      }
-    }
-  }
-  return count;
-}
-
-template <int H, int L, int K, bool kBricks>
+template <int H, int L, int K, int kSearch>
 __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_forward_kernel(const __grid_constant__ QueryParams p) {
+  constexpr bool kBricks = kSearch != kSearchHashed;  // the top-K payload is a record index
   extern __shared__ __align__(16) float smem[];
   float* sm_dec = smem;
   constexpr int kDecFloats = H > 0 ? MlpLayout<(H > 0 ? H : 4), (H > 0 ? L : 1)>::kFloats : 0;
@@ -268,33 +76,38 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
     TopK<K> top;
     top.init();
     int count = 0;
-    if constexpr (kBricks) count = search_bricks<K, kQueryThreads>(m, p.bricks, stencil, &scratch.want[0][threadIdx.x], live, px, py, pz, top);
+    if constexpr (kSearch == kSearchBricks) count = search_bricks<K, kQueryThreads>(m, p.bricks, stencil, &scratch.want[0][threadIdx.x], live, px, py, pz, top);
     else if (live) count = search_hashed<K>(m, cell_mod, px, py, pz, local, time_filter, top);
     if (!live) continue;
 
     // ---- neighbour rows, offsets and inverse-distance weights (neural_points.py:653-706)
+    // All K record loads are issued before the first one is used, then the feature rows in batches of
+    // three: per-neighbour `if (valid) { load; use }` blocks compile to one global round trip per
+    // neighbour (12 exposed round trips per tile, profiles/r2a_*), these to three.
     int row[K];
     float vx[K], vy[K], vz[K], w[K], u[K];
     float S = 0.f;
+    if constexpr (kBricks) {
+      float4 rec[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const bool valid = k < knn && top.id[k] >= 0;
-      row[k] = -1;
-      vx[k] = vy[k] = vz[k] = 0.f;
-      u[k] = 0.f;
-      if (valid) {
-        float qx, qy, qz;
-        if constexpr (kBricks) {
-          const float4 r = __ldg(reinterpret_cast<const float4*>(p.bricks.records) + top.id[k]);
-          qx = r.x; qy = r.y; qz = r.z;
-          row[k] = __float_as_int(r.w);
-        } else {
-          row[k] = top.id[k];
-          const float* g = m.gather_points + 3 * (int64_t)row[k];
-          qx = __ldg(g); qy = __ldg(g + 1); qz = __ldg(g + 2);
-        }
-        vx[k] = px - qx; vy[k] = py - qy; vz[k] = pz - qz;
-        u[k] = 1.0f / (top.d[k] + kIdwEps);
+      for (int k = 0; k < K; ++k) rec[k] = __ldg(reinterpret_cast<const float4*>(p.bricks.records) + (top.id[k] < 0 ? 0 : top.id[k]));
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const bool valid = k < knn && top.id[k] >= 0;
+        row[k] = valid ? __float_as_int(rec[k].w) : -1;
+        vx[k] = valid ? px - rec[k].x : 0.f; vy[k] = valid ? py - rec[k].y : 0.f; vz[k] = valid ? pz - rec[k].z : 0.f;
+        u[k] = valid ? 1.0f / (top.d[k] + kIdwEps) : 0.f;
+        S += u[k];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const bool valid = k < knn && top.id[k] >= 0;
+        row[k] = valid ? top.id[k] : -1;
+        const float* g = m.gather_points + 3 * (int64_t)(valid ? row[k] : 0);
+        const float qx = __ldg(g), qy = __ldg(g + 1), qz = __ldg(g + 2);
+        vx[k] = valid ? px - qx : 0.f; vy[k] = valid ? py - qy : 0.f; vz[k] = valid ? pz - qz : 0.f;
+        u[k] = valid ? 1.0f / (top.d[k] + kIdwEps) : 0.f;
         S += u[k];
       }
     }
@@ -310,18 +123,30 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
     Moments mom;
     mom.clear();
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      if (row[k] >= 0) {
-        float f[kFeat];
-        load_feature_row(m.gather_features, row[k], f);
-        if (layer_norm) { float mu, rs; layer_norm8(f, mu, rs); }
-        if (p.out.certainty) cert = fmaf(__ldg(m.gather_certainties + row[k]), w[k], cert);
+    for (int k0 = 0; k0 < K; k0 += 3) {
+      float fb[3][kFeat], cb[3];
 #pragma unroll
-        for (int i = 0; i < kFeat; ++i) z[i] = fmaf(w[k], f[i], z[i]);
-        z[8] = fmaf(w[k], vx[k], z[8]);
-        z[9] = fmaf(w[k], vy[k], z[9]);
-        z[10] = fmaf(w[k], vz[k], z[10]);
-        if (want_grad) mom.add(f, u[k], vx[k], vy[k], vz[k]);  // the only pass over the feature rows
+      for (int j = 0; j < 3; ++j) {
+        if (k0 + j < K) {
+          const int rr = row[k0 + j] < 0 ? 0 : row[k0 + j];  // invalid neighbours read row 0; the result is discarded
+          load_feature_row256(m.gather_features, rr, fb[j]);
+          cb[j] = p.out.certainty ? __ldg(m.gather_certainties + rr) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int k = k0 + j;
+        if (k < K && row[k] >= 0) {
+          float (&f)[kFeat] = fb[j];
+          if (layer_norm) { float mu, rs; layer_norm8(f, mu, rs); }
+          cert = fmaf(cb[j], w[k], cert);
+#pragma unroll
+          for (int i = 0; i < kFeat; ++i) z[i] = fmaf(w[k], f[i], z[i]);
+          z[8] = fmaf(w[k], vx[k], z[8]);
+          z[9] = fmaf(w[k], vy[k], z[9]);
+          z[10] = fmaf(w[k], vz[k], z[10]);
+          if (want_grad) mom.add(f, u[k], vx[k], vy[k], vz[k]);  // the only pass over the feature rows
+        }
       }
     }
 

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kBwdThreads) train_backward_l1_kernel(const __
 
       // decoder forward for the activation pattern and a = d logit / d z
       float logit_unused, a[kIn];
-      mlp_l1_ffma2<H, true>(sm_dec, z, slope, logit_unused, a, mask);
+      mlp_l1_pairs<H, true>(sm_dec, z, slope, logit_unused, a, mask);
 
       // c' = [delta z + s tau ; delta]
 #pragma unroll
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kBwdThreads) train_backward_l1_kernel(const __
 #pragma unroll
     for (int i = 0; i < kIn; ++i) {
       atomicAdd(gW0 + j * kIn + i, wout * g[i]);
-      dw = fmaf(sm_dec[Lay::kW0 + j * kInPad + i], g[i], dw);
+      dw = fmaf(sm_dec[Lay::kW0 + Lay::w0_index(j, i)], g[i], dw);
     }
     if (p.dec.bias[0]) atomicAdd(gb0 + j, wout * g[kIn]);
     atomicAdd(gwout + j, dw);

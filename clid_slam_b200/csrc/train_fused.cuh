@@ -56,7 +56,7 @@ constexpr int kNumTileSamples = 20;  // base samples per warp tile in numerical 
 // its 64-byte row [c'(12) | activation bits | pad] to global memory and decoder_grad_kernel
 // (tile_kernel.cuh) reduces all rows afterwards.  The warp-serial fold costs ~28 % of this kernel's
 // time (profiles/), as a separate dense reduction it is a few microseconds.
-template <int H, int K, bool kBricks, bool kNumerical, bool kFoldOut>
+template <int H, int K, int kSearch, bool kNumerical, bool kFoldOut>
 __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fused_l1_kernel(const __grid_constant__ TrainFusedParams p) {
   using Lay = MlpLayout<H, 1>;
   constexpr int kRows = H / 32;
@@ -66,8 +66,8 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
   extern __shared__ __align__(16) float smem[];
   float* sm_dec = smem;
   // search scratch (hash residues or stencil + brick cursor columns), then the fold staging
-  constexpr int kSearchFloats = kBricks ? (2 * 64 * kBrickSlots + (int)(sizeof(BrickScratch) / sizeof(float)))
-                                        : 2 * CLID_MAX_KC;
+  constexpr bool kBricks = kSearch != kSearchHashed;
+  constexpr int kSearchFloats = search_smem_floats<kSearch>();
   int64_t* cell_mod = reinterpret_cast<int64_t*>(smem + Lay::kFloats);
   uint64_t* stencil = reinterpret_cast<uint64_t*>(smem + Lay::kFloats);
   BrickScratch& scratch = *reinterpret_cast<BrickScratch*>(smem + Lay::kFloats + 2 * 64 * kBrickSlots);
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
     TopK<K> top;
     top.init();
     int count = 0;
-    if constexpr (kBricks) count = search_bricks<K, kQueryThreads>(m, p.bricks, stencil, &scratch.want[0][threadIdx.x], live, px, py, pz, top);
+    if constexpr (kSearch == kSearchBricks) count = search_bricks<K, kQueryThreads>(m, p.bricks, stencil, &scratch.want[0][threadIdx.x], live, px, py, pz, top);
     else if (live) count = search_hashed<K>(m, cell_mod, px, py, pz, local, time_filter, top);
 
     float c[kInPad];
@@ -168,21 +168,28 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
 #pragma unroll
     for (int k = 0; k < K; ++k) { row[k] = -1; vx[k] = vy[k] = vz[k] = 0.f; u[k] = 0.f; w[k] = 0.f; }
     if (live) {
+      // all K record loads before the first use, feature rows in batches of three (see query_forward_kernel)
+      if constexpr (kBricks) {
+        float4 rec[K];
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        if (k < knn && top.id[k] >= 0) {
-          float qx, qy, qz;
-          if constexpr (kBricks) {
-            const float4 r = __ldg(reinterpret_cast<const float4*>(p.bricks.records) + top.id[k]);
-            qx = r.x; qy = r.y; qz = r.z;
-            row[k] = __float_as_int(r.w);
-          } else {
-            row[k] = top.id[k];
-            const float* g = m.gather_points + 3 * (int64_t)row[k];
-            qx = __ldg(g); qy = __ldg(g + 1); qz = __ldg(g + 2);
-          }
-          vx[k] = px - qx; vy[k] = py - qy; vz[k] = pz - qz;
-          u[k] = 1.0f / (top.d[k] + kIdwEps);
+        for (int k = 0; k < K; ++k) rec[k] = __ldg(reinterpret_cast<const float4*>(p.bricks.records) + (top.id[k] < 0 ? 0 : top.id[k]));
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const bool valid = k < knn && top.id[k] >= 0;
+          row[k] = valid ? __float_as_int(rec[k].w) : -1;
+          vx[k] = valid ? px - rec[k].x : 0.f; vy[k] = valid ? py - rec[k].y : 0.f; vz[k] = valid ? pz - rec[k].z : 0.f;
+          u[k] = valid ? 1.0f / (top.d[k] + kIdwEps) : 0.f;
+          S += u[k];
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const bool valid = k < knn && top.id[k] >= 0;
+          row[k] = valid ? top.id[k] : -1;
+          const float* g = m.gather_points + 3 * (int64_t)(valid ? row[k] : 0);
+          const float qx = __ldg(g), qy = __ldg(g + 1), qz = __ldg(g + 2);
+          vx[k] = valid ? px - qx : 0.f; vy[k] = valid ? py - qy : 0.f; vz[k] = valid ? pz - qz : 0.f;
+          u[k] = valid ? 1.0f / (top.d[k] + kIdwEps) : 0.f;
           S += u[k];
         }
       }
@@ -193,15 +200,22 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
       // the analytic spatial gradient and the tangent input tau0 = s J r are linear in)
       if constexpr (!kNumerical) mom.clear();
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        if (row[k] >= 0) {
-          float f[kFeat];
-          load_feature_row(m.gather_features, row[k], f);
-          if (layer_norm) { float mu, rs; layer_norm8(f, mu, rs); }
+      for (int k0 = 0; k0 < K; k0 += 3) {
+        float fb[3][kFeat];
 #pragma unroll
-          for (int i = 0; i < kFeat; ++i) z[i] = fmaf(w[k], f[i], z[i]);
-          z[8] = fmaf(w[k], vx[k], z[8]); z[9] = fmaf(w[k], vy[k], z[9]); z[10] = fmaf(w[k], vz[k], z[10]);
-          if constexpr (!kNumerical) mom.add(f, u[k], vx[k], vy[k], vz[k]);
+        for (int j = 0; j < 3; ++j)
+          if (k0 + j < K) load_feature_row256(m.gather_features, row[k0 + j] < 0 ? 0 : row[k0 + j], fb[j]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int k = k0 + j;
+          if (k < K && row[k] >= 0) {
+            float (&f)[kFeat] = fb[j];
+            if (layer_norm) { float mu, rs; layer_norm8(f, mu, rs); }
+#pragma unroll
+            for (int i = 0; i < kFeat; ++i) z[i] = fmaf(w[k], f[i], z[i]);
+            z[8] = fmaf(w[k], vx[k], z[8]); z[9] = fmaf(w[k], vy[k], z[9]); z[10] = fmaf(w[k], vz[k], z[10]);
+            if constexpr (!kNumerical) mom.add(f, u[k], vx[k], vy[k], vz[k]);
+          }
         }
       }
 
@@ -216,7 +230,7 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
       }
 
       float out;
-      mlp_l1_ffma2<H, true>(sm_dec, z, slope, out, a, mask);
+      mlp_l1_pairs<H, true>(sm_dec, z, slope, out, a, mask);
       sdf = out * s;
       if (p.sdf_out && role_variant == 0) p.sdf_out[q] = sdf;
 #pragma unroll
@@ -406,7 +420,7 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
 #pragma unroll
     for (int i = 0; i < kIn; ++i) {
       atomicAdd(gW0 + j * kIn + i, wout * g[i]);
-      dw = fmaf(sm_dec[Lay::kW0 + j * kInPad + i], g[i], dw);
+      dw = fmaf(sm_dec[Lay::kW0 + Lay::w0_index(j, i)], g[i], dw);
     }
     if (p.dec.bias[0]) atomicAdd(gb0 + j, wout * g[kIn]);
     atomicAdd(gwout + j, dw);

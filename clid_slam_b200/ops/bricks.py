@@ -17,6 +17,7 @@ The index is rebuilt lazily whenever the map changes (per frame), with torch ops
 from __future__ import annotations
 
 import math
+import os
 from functools import lru_cache
 from typing import Optional
 
@@ -81,10 +82,11 @@ def _make_stencil_table(offsets_cpu: torch.Tensor, reach: int, span: int) -> tor
 class BrickIndex:
     """Device tensors of one index plus the ClidBricks struct that points at them."""
 
-    def __init__(self, headers, records, stencil, origin, dims, span, reach, apron=0):
-        self.headers, self.records, self.stencil = headers, records, stencil
+    def __init__(self, headers, records, stencil, origin, dims, span, reach, apron=0, hood=None):
+        self.headers, self.records, self.stencil, self.hood = headers, records, stencil, hood
         s = _lib.ClidBricks()
         s.headers = headers.data_ptr()
+        s.hood = None if hood is None else hood.data_ptr()
         s.records = records.data_ptr()
         s.stencil = stencil.data_ptr()
         for i in range(3):
@@ -96,7 +98,8 @@ class BrickIndex:
         self.n_bricks = int(dims[0]) * int(dims[1]) * int(dims[2])
 
     def nbytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in (self.headers, self.records, self.stencil))
+        return sum(t.numel() * t.element_size() for t in (self.headers, self.records, self.stencil, self.hood)
+                   if t is not None)
 
 
 def build(npm, query_locally: bool) -> Optional[BrickIndex]:
@@ -166,4 +169,25 @@ def build(npm, query_locally: bool) -> Optional[BrickIndex]:
     headers[:, 3] = count.to(torch.int32)
 
     stencil = _stencil_table(offsets_cpu, reach, span).to(dev)
-    return BrickIndex(headers, records, stencil, lo_c.tolist(), dims, span, reach, apron=1)
+    hood = _hood_lines(headers, dims) if USE_HOOD and n_bricks <= MAX_HOOD_BRICKS else None
+    return BrickIndex(headers, records, stencil, lo_c.tolist(), dims, span, reach, apron=1, hood=hood)
+
+
+MAX_HOOD_BRICKS = 1 << 24  # 128 B per brick: 2 GiB of neighbourhood lines at most
+USE_HOOD = os.environ.get("CLID_HOOD", "1") != "0"  # False: the kernels read the eight 16-byte headers (tests run both)
+
+
+def _hood_lines(headers: torch.Tensor, dims) -> torch.Tensor:
+    """ClidBricks.hood: line b = the (mask lo, mask hi) pairs and first-record indices of the 2 x 2 x 2 bricks
+    whose lower corner is brick b, so that a query reads its whole neighbourhood directory from ONE 128-byte
+    line (coop_search.cuh) instead of eight 16-byte headers in eight different lines.  Bricks past the upper
+    faces read as empty; the apron keeps every query's lower-corner brick inside [0, dims - 2]."""
+    d0, d1, d2 = dims
+    hdr = headers.view(d2, d1, d0, 4)
+    hood = torch.zeros(d2, d1, d0, 32, dtype=torch.int32, device=headers.device)
+    for s in range(8):
+        dx, dy, dz = s & 1, (s >> 1) & 1, s >> 2
+        src = hdr[dz:, dy:, dx:]
+        hood[: d2 - dz, : d1 - dy, : d0 - dx, 2 * s:2 * s + 2] = src[..., 0:2]
+        hood[: d2 - dz, : d1 - dy, : d0 - dx, 16 + s] = src[..., 2]
+    return hood.view(-1, 32)

@@ -21,10 +21,9 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
         )
 
 
-# Kernel family of the brick-index fast path: False = register-resident kernels (16 warps/SM, two
-# waves; the default -- faster at the bench sizes), True = phase-parked tile
-# kernels (28 warps/SM, one wave).  Same results; tests run both.
-USE_TILE_KERNELS = os.environ.get("CLID_TILE_KERNELS", "0") == "1"
+def brick_flags(bricks) -> int:
+    """Flag bits that select the brick-index kernels for `bricks` (a BrickIndex)."""
+    return _lib.USE_BRICKS
 
 _COUNTERS = {}
 
@@ -144,9 +143,7 @@ def forward(npm, decoder, x: torch.Tensor, ts: Optional[torch.Tensor], training_
         bricks = None
     if bricks is not None:
         m.bricks = C.pointer(bricks.struct)
-        flags |= _lib.USE_BRICKS
-        if USE_TILE_KERNELS:
-            flags |= _lib.TILE_KERNELS
+        flags |= brick_flags(bricks)
     dec_struct = None
     if decoder is not None:
         dec_struct = decoder.abi_struct()

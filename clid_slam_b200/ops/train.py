@@ -229,9 +229,7 @@ class FusedTrainer:
         bricks = npm.brick_index(True) if os.environ.get("CLID_DISABLE_BRICKS", "0") != "1" else None
         if bricks is not None:
             m.bricks = C.pointer(bricks.struct)
-            flags |= _lib.USE_BRICKS
-            if _q.USE_TILE_KERNELS:
-                flags |= _lib.TILE_KERNELS
+            flags |= _q.brick_flags(bricks)
         if dec.use_leaky_relu:
             flags |= _lib.LEAKY_RELU
         ds = dec.abi_struct()

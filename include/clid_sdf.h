@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CLID_ABI_VERSION 2
+#define CLID_ABI_VERSION 3
 #define CLID_MAX_LEVELS 3   /* hidden layers of the decoder MLP */
 #define CLID_MAX_KNN 8      /* query_nn_k */
 #define CLID_MAX_KC 256     /* probed cells per query */
@@ -49,10 +49,7 @@ enum ClidFlags {
   CLID_TIME_FILTER = 1 << 2,   /* travel-distance window on point_ts_create (:1003-1009) */
   CLID_LAYER_NORM = 1 << 3,    /* F.layer_norm over the feature dim, no affine, eps 1e-5 (:632-633) */
   CLID_LEAKY_RELU = 1 << 4,    /* decoder.py:66-74, slope 0.01 */
-  CLID_USE_BRICKS = 1 << 5,    /* probe through ClidMap.bricks instead of the hash table */
-  CLID_TILE_KERNELS = 1 << 6   /* with an aproned span-2 brick index and a one-level decoder: run the
-                                  phase-parked 28-warps/SM tile kernel instead of the register-resident
-                                  one (same results; DESIGN.md section 4 compares them)               */
+  CLID_USE_BRICKS = 1 << 5     /* probe through ClidMap.bricks instead of the hash table */
 };
 
 /* Brick index: a compact, per-frame restatement of "which neural point does the voxel hash
@@ -72,6 +69,12 @@ typedef struct ClidBrickHeader {
 
 typedef struct ClidBricks {
   const ClidBrickHeader* headers; /* [dims[0]*dims[1]*dims[2]], x fastest                      */
+  const uint32_t* hood;           /* [dims[0]*dims[1]*dims[2]][32] or NULL: entry b packs the headers of the
+                                     2x2x2 bricks whose lower corner is b into ONE 128-byte line --
+                                     words 0..15 occupancy masks (lo, hi) of bricks s = dx + 2 dy + 4 dz,
+                                     words 16..23 their first-record indices, 24..31 unused -- so a query
+                                     reads its whole neighbourhood directory from a single line
+                                     (used when not NULL, else the eight headers are read)       */
   const float* records;           /* [n_records,4] = (px, py, pz, bit-cast int32 gather row)   */
   const uint64_t* stencil;        /* [64][span^3] neighbourhood masks by in-brick position of
                                      the neighbourhood's lower corner, then brick offset      */
@@ -80,9 +83,8 @@ typedef struct ClidBricks {
   int32_t span;                   /* bricks per axis one neighbourhood can touch               */
   int32_t reach;                  /* num_nei_cells: the neighbourhood is [-reach, reach]^3     */
   int32_t n_records;
-  int32_t apron;                  /* empty bricks surrounding the indexed bricks on every side (0 or 1).
-                                     With apron >= 1 and span == 2 the phase-parked tile kernels are used
-                                     (one range test per query instead of one per brick).             */
+  int32_t apron;                  /* empty bricks surrounding the indexed bricks on every side; the
+                                     kernels need 1 (a query is range-tested once, not per brick) */
 } ClidBricks;
 
 /* Neural-point map state read by a query.  model/neural_points.py:79-133 */

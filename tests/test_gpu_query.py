@@ -49,15 +49,15 @@ def test_query_feature_matches_reference_fixture(name):
 
 
 def _kernel_family(monkeypatch, family):
-    """hashed: reference hash table; bricks: brick index, register-resident kernels; tiles: brick
-    index, phase-parked tile kernels.  Returns the use_bricks argument."""
-    from clid_slam_b200.ops import query as q
+    """hashed: reference hash table; bricks: brick index with the 128-byte neighbourhood lines (the
+    default); headers: brick index read through its eight 16-byte headers.  Returns the use_bricks argument."""
+    from clid_slam_b200.ops import bricks as b
 
-    monkeypatch.setattr(q, "USE_TILE_KERNELS", family == "tiles")
+    monkeypatch.setattr(b, "USE_HOOD", family != "headers")
     return family != "hashed"
 
 
-FAMILIES = ["hashed", "bricks", "tiles"]
+FAMILIES = ["hashed", "bricks", "headers"]
 
 
 @pytest.mark.parametrize("family", FAMILIES)

@@ -50,14 +50,14 @@ def _check_final_state(fx, npm, dec):
 
 
 # rows: decoder-gradient rows to scratch + reduction kernel (default); infold: the warps fold them inside
-# the one kernel; tiles: phase-parked tile kernels; three-kernels: forward / loss / backward launches
-@pytest.mark.parametrize("variant", ["rows", "infold", "tiles", "three-kernels"])
+# the one kernel; headers: brick index without the neighbourhood lines; three-kernels: forward / loss / backward launches
+@pytest.mark.parametrize("variant", ["rows", "infold", "headers", "three-kernels"])
 @pytest.mark.parametrize("name", L1_CASES)
 def test_fused_training_matches_reference(name, variant, monkeypatch):
-    from clid_slam_b200.ops import query as q
+    from clid_slam_b200.ops import bricks as bk
     from clid_slam_b200.ops.train import FusedTrainer
 
-    monkeypatch.setattr(q, "USE_TILE_KERNELS", variant == "tiles")
+    monkeypatch.setattr(bk, "USE_HOOD", variant != "headers")
     fx, m, cfg, npm, dec, frozen = _setup(name)
     trainer = FusedTrainer(cfg, npm, dec)
     trainer.single_kernel = variant != "three-kernels"
@@ -178,17 +178,17 @@ def test_decoder_grad_reduce_matches_infold():
     gio.assert_close(grads[0][1], grads[1][1], 1e-4, 1e-9, "feature gradients")
 
 
-@pytest.mark.parametrize("variant", ["rows", "tiles"])
+@pytest.mark.parametrize("variant", ["rows", "headers"])
 @pytest.mark.parametrize("hidden,numerical,leaky", [(32, False, False), (128, False, False), (32, True, False),
                                                      (128, True, True), (64, False, True)])
 def test_training_gradients_match_oracle_other_widths(hidden, numerical, leaky, variant, monkeypatch):
     """Decoder widths / activation the reference fixtures do not cover: loss, dL/dfeatures and dL/ddecoder of
     one iteration against torch autograd through the oracle (double backward in analytic mode)."""
     import oracle.sdf_oracle as oc
-    from clid_slam_b200.ops import query as q
+    from clid_slam_b200.ops import bricks as bk
     from clid_slam_b200.ops.train import FusedTrainer
 
-    monkeypatch.setattr(q, "USE_TILE_KERNELS", variant == "tiles")
+    monkeypatch.setattr(bk, "USE_HOOD", variant != "headers")
     cfg_o = oc.OracleConfig(buffer_size=2_000_003, local_map_radius=80.0, geo_mlp_hidden_dim=hidden,
                             numerical_grad=numerical, gradient_decimation=10 if numerical else 1, mlp_leaky_relu=leaky)
     mo, params, gen = hp.build_oracle_world(120, 2, seed=7, cfg=cfg_o)
