@@ -21,6 +21,9 @@ __device__ __forceinline__ void ldg256(const void* p, uint32_t (&v)[8]) {  // LD
                : "l"(p));
 }
 
+#ifndef CLID_TOPK_PARALLEL
+#define CLID_TOPK_PARALLEL 1
+#endif
 // Ascending top-K by squared distance with an integer payload; ties keep the earlier candidate.
 template <int K>
 struct TopK {
@@ -32,6 +35,21 @@ struct TopK {
   }
   __device__ __forceinline__ void insert(float dc, int ic) {
     if (!(dc < d[K - 1])) return;
+#if CLID_TOPK_PARALLEL
+    // all K comparisons are independent, every slot then takes {itself, its left neighbour, the candidate}
+    // from the OLD values: dependency depth 3 instead of a K-long compare-exchange chain (the list is
+    // ascending, so lt[k-1] implies lt[k]); ties keep the earlier candidate as before
+    bool lt[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) lt[k] = dc < d[k];
+#pragma unroll
+    for (int k = K - 1; k > 0; --k) {
+      d[k] = lt[k] ? (lt[k - 1] ? d[k - 1] : dc) : d[k];
+      id[k] = lt[k] ? (lt[k - 1] ? id[k - 1] : ic) : id[k];
+    }
+    d[0] = lt[0] ? dc : d[0];
+    id[0] = lt[0] ? ic : id[0];
+#else
     // one pass of compare-exchange from the front: the carried element is always the larger one
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -43,6 +61,7 @@ struct TopK {
       dc = lt ? dk : dc;
       ic = lt ? ik : ic;
     }
+#endif
   }
 };
 
