@@ -50,7 +50,8 @@ def parse_args():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--mode", default="analytic", choices=["analytic", "numerical"],
                     help="eikonal gradient mode of the training step")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference legs (CPU and eager CUDA)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity gate against the oracle")
     ap.add_argument("--sharding", default="spatial", choices=["spatial", "replicated"],
                     help="N > 1: slab-partitioned samples and neural points with a neighbour exchange of the band "
                          "gradients (default) or any-sample-anywhere with a dense feature-gradient all-reduce")
@@ -142,6 +143,11 @@ def build_world(device, mode):
     return cfg, dec, npm
 
 
+def _xlwt(batch):
+    x, label, weight, ts = batch
+    return x, label, weight, ts
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -215,6 +221,14 @@ def run_native(args):
             flush_sink.copy_(flush_r.sum())
 
     flush = _Flush()
+
+    # ---- untimed parity gate at the benchmark configuration: forward + gradient and one training
+    # iteration of the CUDA path against the CPU oracle on a 16384-sample slice of batch 0, on this very world
+    parity = None
+    if world == 1 and not args.no_parity:
+        from oracle.bridge import parity_gate  # checker only: never timed, never on the product path
+
+        parity = parity_gate(npm, dec, cfg, *_xlwt(batches[0]))
 
     trainer = FusedTrainer(cfg, npm, dec)
     n_global = BATCH * world
@@ -331,8 +345,17 @@ def run_native(args):
     torch.cuda.synchronize()
     wall_e2e_ms = (time.perf_counter() - wall1) * 1e3
     sync_all()
-    e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_events)
+    e2e_events_ms = sum(a.elapsed_time(b) for a, b in e2e_events)
     clocks = sampler.stop() if rank == 0 else None
+    # the end-to-end time is the host wall clock of that loop (copies, launches, loss reads, everything) minus the
+    # untimed L2 flushes, whose wall time is measured by running the same number of flushes alone
+    sync_all()
+    wall2 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()
+    torch.cuda.synchronize()
+    wall_flush_ms = (time.perf_counter() - wall2) * 1e3
+    e2e_ms = max(wall_e2e_ms - wall_flush_ms, e2e_events_ms)
 
     # ---- kernel-only timing for the roofline: the same step launched call by call (no graph) with
     # CUDA events around the dominant kernel, same L2 hygiene
@@ -362,6 +385,35 @@ def run_native(args):
     torch.cuda.synchronize()
     inf_ms = statistics.median(a.elapsed_time(b) for a, b in inf_events)
     mean_nn = float(nn_count.float().mean().item())
+
+    # ---- the shipped default of every run file is the NUMERICAL eikonal gradient (config.py:204-206): second value,
+    # same map, same batches, its own trainer and graphs (N = 1 only; `--mode numerical` makes it the headline)
+    numerical_line = None
+    if world == 1 and graphed and args.mode == "analytic":
+        import copy
+
+        cfg_n = copy.copy(cfg)
+        cfg_n.numerical_grad, cfg_n.gradient_decimation = True, 10
+        trainer_n = FusedTrainer(cfg_n, npm, dec)
+        nd_n = (BATCH + 9) // 10
+        pipe_n = StepPipeline(trainer_n, BATCH, buffers=batches, n_global=BATCH, nd_global=nd_n)
+        for i in range(3):
+            flush.zero_()
+            pipe_n.run(i % n_batches)
+        ev = []
+        for i in range(min(args.steps, 30)):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pipe_n.run(i % n_batches)
+            e1.record()
+            ev.append((e0, e1))
+        torch.cuda.synchronize()
+        ms_n = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+        numerical_line = {"value": BATCH / (ms_n * 1e-3), "unit": "samples/s", "ms_per_step": ms_n, "steps": len(ev),
+                          "evaluations_per_step": BATCH + 6 * nd_n,
+                          "note": "same step with get_numerical_gradient (6 shifted evaluations of every 10th sample)"}
+        del pipe_n, trainer_n
 
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=device)
     if world > 1:
@@ -441,9 +493,21 @@ def run_native(args):
             "clocks": clocks,
             "final_loss": [float(v) for v in loss_host.tolist()],
         }
+        if parity is not None:
+            line["parity"] = parity
+        if numerical_line is not None:
+            line["numerical_mode"] = numerical_line
         if world == 1 and not args.no_cpu_baseline:
+            # free the benchmark's device memory before the reference builds its own world on the same GPU
             line["cpu_baseline"] = cpu_reference(args.mode, steps=3, warmup=1, n=BATCH)
+            line["eager_cuda_baseline"] = eager_cuda_reference(args.mode, device, steps=5, warmup=2, n=BATCH)
+            if line["eager_cuda_baseline"].get("value"):
+                line["speedup_over_eager_cuda"] = {"step": value / line["eager_cuda_baseline"]["value"],
+                                                   "inference_forward": (BATCH / (inf_ms * 1e-3)) /
+                                                   line["eager_cuda_baseline"]["inference_forward"]["value"]}
         print(json.dumps(line), flush=True)
+        if parity is not None and not parity["ok"]:
+            raise SystemExit("parity gate FAILED: " + json.dumps(parity))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -451,13 +515,24 @@ def run_native(args):
 
 # ------------------------------------------------------------------------------------------ reference arm
 def cpu_reference(mode, steps, warmup, n):
-    """The reference's algorithm for the same step on the host cores: the oracle port (torch CPU
-    ops, oracle/sdf_oracle.py -- the reference itself is pure PyTorch and is not on this box)."""
+    """The reference's own implementation of the step on the host cores: the UNMODIFIED reference shipped under
+    baseline/_ref (baseline/ref_runner.py: NeuralPoints.update, Mapper.mapping with its stock get_batch) when it is
+    there, else the oracle port (torch CPU restatement, oracle/sdf_oracle.py)."""
     import torch
 
+    threads = os.cpu_count() or 1
+    from baseline import ref_runner
+
+    if ref_runner.available():
+        r = ref_runner.run("cpu", mode, n, SIDE, SHEETS, steps=steps, warmup=warmup, threads=threads)
+        return {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["threads"], "kind": "reference",
+                "sample": f"Mapper.mapping({steps}) of the unmodified reference (baseline/_ref) with {n}-sample batches drawn by its "
+                          f"stock get_batch from a {4 * n}-sample pool, 1.08M-point world ({mode} gradient), after mapping({warmup})",
+                "ms_per_step": r["ms_per_step"],
+                "inference_forward": {"value": r["inference_samples_per_s"], "unit": "samples/s",
+                                      "sample": f"query_feature + Decoder.sdf + get_gradient on {n} queries, mean of 2 after 1 warm-up"}}
     from oracle import sdf_oracle as oc
 
-    threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     cfg = oc.OracleConfig(local_map_radius=1.0e4, numerical_grad=(mode == "numerical"),
                           gradient_decimation=10 if mode == "numerical" else 1)
@@ -477,7 +552,6 @@ def cpu_reference(mode, steps, warmup, n):
         if i >= warmup:
             times.append(dt)
     total = sum(times)
-    # the inference variant beside it (workload i): query_feature -> Decoder.sdf -> get_gradient
     fwd_times = []
     for i in range(3):
         x = batches[i % 2][0].clone().requires_grad_(True)
@@ -493,6 +567,25 @@ def cpu_reference(mode, steps, warmup, n):
                                   "sample": f"{len(fwd_times)} forward + gradient passes of {n} queries, after 1 warm-up"}}
 
 
+def eager_cuda_reference(mode, device, steps, warmup, n):
+    """The unmodified reference on the SAME B200 with device="cuda": its eager PyTorch path (what the reference
+    actually deploys, README.md:33), the meaningful baseline for the speed-up."""
+    import torch
+
+    from baseline import ref_runner
+
+    if not ref_runner.available():
+        return {"unavailable": "baseline/_ref is missing (python -m baseline.install_ref in the build container)"}
+    try:
+        torch.cuda.empty_cache()
+        r = ref_runner.run(device, mode, n, SIDE, SHEETS, steps=steps, warmup=warmup)
+    except Exception as exc:  # the baseline must never take the benchmark line down
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
+    return {"value": r["samples_per_s"], "unit": "samples/s", "kind": "reference-eager-cuda", "ms_per_step": r["ms_per_step"],
+            "sample": f"Mapper.mapping({steps}) of the unmodified reference with device={device}, {n}-sample batches, after mapping({warmup})",
+            "inference_forward": {"value": r["inference_samples_per_s"], "unit": "samples/s", "ms": r["inference_ms"]}}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -500,6 +593,7 @@ def run_reference(args):
     steps = max(1, min(args.steps, 5))
     warmup = max(1, min(args.warmup, 2))
     base = cpu_reference(args.mode, steps=steps, warmup=warmup, n=BATCH)
+    kind = "the unmodified reference (baseline/_ref)" if base["kind"] == "reference" else "reference algorithm (oracle port, torch CPU)"
     line = {
         "impl": "reference",
         "metric": "sampled-points/sec through SDF decoder+grad+loss (train step: fused gather+MLP+grad forward, "
@@ -508,7 +602,7 @@ def run_reference(args):
         "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BASELINE configs[2]: 131072 samples/batch, 1.08M neural points, ncd128 decoder, "
-                               f"{args.mode} eikonal gradient; reference algorithm (oracle port, torch CPU) on host cores"},
+                               f"{args.mode} eikonal gradient; {kind} on host cores"},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

@@ -50,36 +50,8 @@ def make_ref_config(ref, **over):
     return cfg
 
 
-def oracle_cfg_from_ref(cfg) -> oc.OracleConfig:
-    o = oc.OracleConfig()
-    for name in o.__dataclass_fields__:
-        if hasattr(cfg, name):
-            setattr(o, name, getattr(cfg, name))
-    return o
-
-
-def oracle_map_from_ref(npm, ocfg) -> oc.OracleMap:
-    m = oc.OracleMap(
-        cfg=ocfg,
-        table=npm.buffer_pt_index.clone(),
-        points=npm.neural_points.clone(),
-        ts_create=npm.point_ts_create.clone(),
-        ts_update=npm.point_ts_update.clone(),
-        certainties=npm.point_certainties.clone(),
-        features=npm.geo_features.clone(),
-        travel_dist=npm.travel_dist.clone(),
-        cur_ts=int(npm.cur_ts),
-        reboot_ts=int(npm.reboot_ts),
-    )
-    m.offsets = npm.neighbor_dx.clone()
-    m.max_valid_dist2 = float(npm.max_valid_dist2)
-    m.local_points = npm.local_neural_points.clone()
-    m.local_features = npm.local_geo_features.detach().clone().requires_grad_(True)
-    m.local_certainties = npm.local_point_certainties.clone()
-    m.local_ts_update = npm.local_point_ts_update.clone()
-    m.local_mask = npm.local_mask.clone()
-    m.global2local = npm.global2local.clone()
-    return m
+from oracle.bridge import oracle_config_from as oracle_cfg_from_ref  # noqa: E402
+from oracle.bridge import oracle_map_from as oracle_map_from_ref  # noqa: E402
 
 
 def map_state_arrays(npm, prefix="map_"):
