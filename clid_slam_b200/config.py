@@ -97,9 +97,12 @@ class Config:
         self.new_certainty_thre: float = 1.0
         self.pool_capacity: int = int(1e7)
         # tracking / pgo switches the mapper looks at
-        self.track_on: bool = False
+        self.track_on: bool = True          # utils/config.py:254; load() keeps it only if the run file has a tracker section
         self.pgo_on: bool = False
-        self.use_pin_mapper: bool = True
+        self.use_pin_mapper: bool = False   # utils/config.py:18: CLID-SLAM's region-specific sampler is the default
+        self.consistency_count: int = 1000  # utils/config.py:218-219 (consistency loss; not on the fused path)
+        self.consistency_range: float = 0.05
+        self.lr_pose: float = 1e-4          # utils/config.py:235 (bundle adjustment; no caller)
         self.dynamic_certainty_thre: float = 0.5
         self.dynamic_sdf_ratio_thre: float = 1.5
         self.dynamic_min_grad_norm_thre: float = 0.25
@@ -115,6 +118,10 @@ class Config:
 
         with open(path, "r") as fh:
             args = yaml.safe_load(fh)
+        setting = args.get("setting", {}) or {}
+        self.use_pin_mapper = bool(setting.get("use_pin_mapper", False))      # utils/config.py:415
+        self.track_on = bool(args.get("tracker", False))                      # utils/config.py:676: on only if indicated
+        self.pgo_on = bool(args.get("pgo", False)) if self.track_on else False  # utils/config.py:742-743
         proc = args.get("process", {})
         self.min_range = proc.get("min_range_m", self.min_range)
         self.max_range = proc.get("max_range_m", self.max_range)
@@ -164,7 +171,9 @@ class Config:
         self.lr = float(opt.get("learning_rate", self.lr))
         self.weight_decay = float(opt.get("weight_decay", self.weight_decay))
         self.adaptive_iters = opt.get("adaptive_iters", self.adaptive_iters)
+        self.lr_pose = float(opt.get("lr_pose_ba", self.lr_pose))
         self._derive()
+        self.consistency_count = int(self.bs / 4)  # utils/config.py:904
 
 
 def ncd128() -> Config:

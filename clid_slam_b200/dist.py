@@ -126,7 +126,13 @@ class SpatialShards:
                 q = torch.arange(1, world_size, device=dev, dtype=torch.float32) / world_size
                 srt = torch.sort(cell).values
                 pick = (q * (srt.numel() - 1)).long()
-                boundaries = torch.unique(srt[pick])  # equal point counts per slab
+                # equal point counts per slab; a clustered map can repeat a quantile: keep exactly world-1 strictly
+                # increasing boundaries by bumping repeats (the slabs in between are then empty, which is valid)
+                bnd = srt[pick].tolist()
+                for i in range(1, len(bnd)):
+                    if bnd[i] <= bnd[i - 1]:
+                        bnd[i] = bnd[i - 1] + 1
+                boundaries = torch.tensor(bnd, dtype=torch.int64, device=dev)
             else:
                 boundaries = torch.empty(0, dtype=torch.int64, device=dev)
         self.boundaries = boundaries.to(device=dev, dtype=torch.int64).contiguous()

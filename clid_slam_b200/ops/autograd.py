@@ -25,6 +25,22 @@ from .. import _lib
 from . import query as _q
 
 
+def _state_stamp(npm, query_locally, feats):
+    """What the backward kernels re-read from the LIVE map by pointer: the gather points / features.  If any of it
+    changed since the forward (optimiser step, reset_local_map, update ...) the saved neighbour rows are stale and
+    the gradients would silently belong to another map: torch's own version check cannot see it, so we do."""
+    pts = npm.local_neural_points if query_locally else npm.neural_points
+    return (getattr(npm, "_map_version", 0), feats.data_ptr(), feats._version, tuple(feats.shape), pts.data_ptr())
+
+
+def _check_stamp(ctx, what):
+    feats = ctx.npm.local_geo_features if ctx.query_locally else ctx.npm.geo_features
+    if _state_stamp(ctx.npm, ctx.query_locally, feats) != ctx.stamp:
+        raise RuntimeError(
+            f"{what}: the neural-point map or its feature table was modified between the forward of query_feature "
+            "and this backward (optimizer.step / reset_local_map / update ...); the saved neighbour rows are stale")
+
+
 def _launch_backward(npm, query_locally, x, idx, gz, need_gx, need_gfeat, feat_rows):
     lib = _lib.load()
     m, flags = _q.map_struct(npm, query_locally)
@@ -66,6 +82,7 @@ class QueryFeatureGrad(torch.autograd.Function):
     def forward(ctx, gz, x, feats, idx, npm, query_locally, need_gx, need_gfeat):
         ctx.npm, ctx.query_locally = npm, query_locally
         ctx.feat_rows = feats.shape[0]
+        ctx.stamp = _state_stamp(npm, query_locally, feats)
         ctx.save_for_backward(gz, x, idx)
         ctx.set_materialize_grads(False)
         gx, gfeat = _launch_backward(npm, query_locally, x, idx, gz, need_gx, need_gfeat, feats.shape[0])
@@ -78,6 +95,7 @@ class QueryFeatureGrad(torch.autograd.Function):
         if ggx is None:
             return (None,) * 8
         gz, x, idx = ctx.saved_tensors
+        _check_stamp(ctx, "double backward of query_feature")
         g_gz, g_feats = _launch_backward_backward(
             ctx.npm, ctx.query_locally, x, idx, gz, ggx, ctx.needs_input_grad[2], ctx.feat_rows)
         return g_gz if ctx.needs_input_grad[0] else None, None, g_feats, None, None, None, None, None
@@ -99,6 +117,7 @@ class QueryFeature(torch.autograd.Function):
         if training_mode:
             table.add_(accum)
         ctx.npm, ctx.query_locally = npm, query_locally
+        ctx.stamp = _state_stamp(npm, query_locally, feats)
         ctx.save_for_backward(xd, feats, res["knn_idx"])
         ctx.set_materialize_grads(False)
         nn = res["nn_count"].long()
@@ -110,6 +129,7 @@ class QueryFeature(torch.autograd.Function):
         if gz is None:
             return (None,) * 6
         xd, feats, idx = ctx.saved_tensors
+        _check_stamp(ctx, "backward of query_feature")
         need_gx, need_gfeat = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         gx, gfeat = QueryFeatureGrad.apply(gz, xd, feats, idx, ctx.npm, ctx.query_locally, need_gx, need_gfeat)
         return gx, gfeat, None, None, None, None

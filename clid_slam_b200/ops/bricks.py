@@ -41,6 +41,20 @@ def hash_is_alias_free(buffer_size: int, reach: int) -> bool:
 
 _STENCILS = {}
 
+# why a query could not use the brick index and ran on the (20x slower) probe of the reference's hash table:
+# reason -> number of index builds that gave up.  Each reason warns once per process.
+FALLBACKS: dict = {}
+
+
+def _fallback(reason: str):
+    import warnings
+
+    if reason not in FALLBACKS:
+        warnings.warn(f"clid_slam_b200: brick index unavailable ({reason}); queries fall back to the hash-table probe, "
+                      "which is ~20x slower (DESIGN.md section 3)", RuntimeWarning, stacklevel=3)
+    FALLBACKS[reason] = FALLBACKS.get(reason, 0) + 1
+    return None
+
 
 def _stencil_table(offsets_cpu: torch.Tensor, reach: int, span: int) -> torch.Tensor:
     key = (offsets_cpu.numpy().tobytes(), reach, span)
@@ -108,10 +122,12 @@ def build(npm, query_locally: bool) -> Optional[BrickIndex]:
     offsets_cpu = npm.neighbor_dx.detach().cpu()
     reach = int(offsets_cpu.abs().max().item()) if offsets_cpu.numel() else 0
     span = (2 * reach + 7) // 4
-    if span != 2 or npm.count() == 0:  # the kernels walk exactly 2x2x2 bricks (num_nei_cells 1 or 2)
+    if npm.count() == 0:
         return None
+    if span != 2:  # the kernels walk exactly 2x2x2 bricks (num_nei_cells 1 or 2)
+        return _fallback(f"num_nei_cells = {reach}: a neighbourhood must span 2 bricks per axis") if reach > 2 else None
     if not hash_is_alias_free(int(npm.buffer_size), reach):
-        return None
+        return _fallback(f"hash table of {int(npm.buffer_size)} slots aliases cells inside a neighbourhood")
     dev = npm.neural_points.device
     res = float(npm.resolution)
     primes = npm.primes
@@ -146,7 +162,7 @@ def build(npm, query_locally: bool) -> Optional[BrickIndex]:
     dims = [int((hi_c[i] - lo_c[i]) // 4 + 1) for i in range(3)]
     n_bricks = dims[0] * dims[1] * dims[2]
     if n_bricks > MAX_BRICKS:
-        return None
+        return _fallback(f"bounding box of {dims} bricks exceeds the dense header cap of {MAX_BRICKS}")
     rel = cells - lo
     brick = (rel[:, 0] >> 2) + dims[0] * ((rel[:, 1] >> 2) + dims[1] * (rel[:, 2] >> 2))
     bit = (rel[:, 0] & 3) + 4 * (rel[:, 1] & 3) + 16 * (rel[:, 2] & 3)

@@ -26,15 +26,30 @@ def brick_flags(bricks) -> int:
     return _lib.USE_BRICKS
 
 _COUNTERS = {}
+_COUNTER_POOLS = {}
+_POOL_SLOTS = 256
 
 
 def _work_counter(npm, device: torch.device) -> torch.Tensor:
-    """4 zeroed bytes per (device, stream) for the kernels' dynamic tile scheduler; the kernels
-    leave the counter at zero, so it is allocated and cleared once."""
+    """4 zeroed bytes per (device, stream) for the kernels' dynamic tile scheduler; the kernels leave the
+    counter at zero, so it is cleared once.  Counters are slices of one pre-zeroed pool per device: a stream
+    that is first seen DURING a CUDA-graph capture (the capture stream) must not get a tensor whose
+    allocation and zero-fill would belong to that graph's private pool and memset node."""
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     t = _COUNTERS.get(key)
     if t is None:
-        t = torch.zeros(1, dtype=torch.int32, device=device)
+        pool = _COUNTER_POOLS.get(device.index)
+        if pool is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("the first query on a device must not happen inside a CUDA-graph capture "
+                                   "(run one iteration eagerly first)")
+            pool = [torch.zeros(_POOL_SLOTS * 32, dtype=torch.int32, device=device), 0]  # one 128-byte line per counter
+            torch.cuda.synchronize(device)
+            _COUNTER_POOLS[device.index] = pool
+        if pool[1] >= _POOL_SLOTS:
+            raise RuntimeError("more than 256 distinct CUDA streams launched query kernels on this device")
+        t = pool[0][pool[1] * 32: pool[1] * 32 + 1]
+        pool[1] += 1
         _COUNTERS[key] = t
     return t
 

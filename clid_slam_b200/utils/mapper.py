@@ -7,8 +7,11 @@ an alias for the name BASELINE.json uses).  The loop body runs through the fused
 (``ops.train.FusedTrainer``: three launches per iteration, no host synchronisation; long calls replay
 them as one CUDA graph) whenever the
 configuration is covered -- every shipped run file is -- and otherwise through the unfused CUDA
-path (our ``query_feature`` autograd Function + the torch decoder + torch.optim), which accepts
-every loss the reference implements.  Neither path has a CPU fallback.
+path (our ``query_feature`` autograd Function + the torch decoder + torch.optim), which covers the
+sdf losses (bce / zhong / l1 / l2), projective correction, both eikonal modes and its sub-sets, SGD and
+multi-level decoders.  The consistency loss and the semantic / colour heads (utils/mapper.py:717-743,
+770-830; off in every shipped run file) are NOT implemented: mapping() raises for them instead of
+silently training without those terms.  Neither path has a CPU fallback.
 
 Not mirrored (outside the hot path, no caller in CLID-SLAM): ``bundle_adjustment``,
 ``get_ba_samples``, the Open3D pool export needs open3d at call time.
@@ -303,6 +306,11 @@ class Mapper:
 
     def _mapping_unfused(self, iter_count: int) -> None:
         cfg = self.config
+        missing = [name for name in ("consistency_loss_on", "semantic_on", "color_on") if getattr(cfg, name, False)]
+        if missing:
+            raise NotImplementedError(
+                f"{', '.join(missing)}: the consistency loss and the semantic / colour heads (utils/mapper.py:717-743, "
+                "770-830 of the reference) are outside the neural-SDF hot path and not implemented")
         feat_params = list(self.neural_points.parameters())
         opt = setup_optimizer(
             cfg, feat_params, list(self.geo_mlp.parameters()),

@@ -283,3 +283,54 @@ def test_spatial_shards_bands_and_pairwise_flag():
     assert not narrow.pairwise
     with pytest.raises(ValueError):
         cdist.NeighbourExchange(narrow, 1, torch.zeros(81, 8))
+
+
+@pytest.mark.parametrize("yaml_name", ["run_ncd128.yaml", "run_SubT_MRS.yaml", "run_quad.yaml"])
+def test_config_load_matches_the_reference_loader(yaml_name):
+    """Every attribute our Config carries gets the value the reference's Config.load gives it for the shipped run
+    files (utils/config.py:410-910) -- in particular use_pin_mapper / track_on, which select the sampler and the
+    pose source of Mapper.process_frame."""
+    import os
+
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("reference tree not available")
+    ref = ref_loader.load()
+    from clid_slam_b200.config import Config
+
+    path = os.path.join(ref_loader.REFERENCE_ROOT, "config", yaml_name)
+    theirs = ref.Config()
+    theirs.load(path)
+    ours = Config()
+    ours.load(path)
+    skipped = {"device", "dtype", "tran_dtype", "idx_dtype", "silence"}
+    checked = 0
+    for name, mine in vars(ours).items():
+        if name.startswith("_") or name in skipped or not hasattr(theirs, name):
+            continue
+        want = getattr(theirs, name)
+        if name == "track_on":
+            want = bool(want)  # the reference stores the tracker section itself (truthy), utils/config.py:676
+        if isinstance(mine, float) or isinstance(want, float):
+            assert float(mine) == pytest.approx(float(want), rel=1e-12), name
+        else:
+            assert mine == want, name
+        checked += 1
+    assert checked > 50
+    assert ours.use_pin_mapper is False and ours.track_on is True
+
+
+def test_slab_boundaries_of_a_clustered_map_stay_strictly_increasing():
+    """90 % of the points in one cell: the quantiles repeat, the shards must still have world-1 boundaries and
+    every rank must find its neighbour bands (IndexError on ranks 2 and 3 otherwise)."""
+    from clid_slam_b200.dist import SpatialShards
+
+    gen = torch.Generator().manual_seed(0)
+    pts = torch.cat((torch.rand(900, 3, generator=gen) * 0.3, torch.rand(100, 3, generator=gen) * 40.0))
+    shards = SpatialShards(pts, 0.4, reach=2, world_size=4)
+    b = shards.boundaries.tolist()
+    assert len(b) == 3 and all(b[i] < b[i + 1] for i in range(2))
+    assert len(shards.band_rows) == 3
+    owner = shards.owner_of(pts)
+    assert int(owner.min()) >= 0 and int(owner.max()) <= 3
