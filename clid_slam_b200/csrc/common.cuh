@@ -103,41 +103,132 @@ struct MlpLayout {
   static constexpr int kFloats = ((kBout + 1 + 3) / 4) * 4;
 };
 
+// ---- asynchronous staging (sm_90+ async proxy: TMA bulk copies, cp.async, mbarrier) ---------------------
+// The CTA prologue used to be: load decoder + stencil through registers, store to shared memory,
+// __syncthreads -- one exposed global round trip (~4 % of the forward kernel's stall samples) before the
+// first query could even load its coordinates.  Now thread 0 hands the 4 KB stencil to the TMA engine as ONE
+// bulk copy that completes on an mbarrier, every thread issues its share of the decoder as cp.async element
+// copies (global -> shared, no registers, scattered into the padded / pair-interleaved MlpLayout) that arrive
+// on a second mbarrier, and the warps only wait where the data is first needed: the stencil before the first
+// search, the decoder before the first MLP -- i.e. behind the first tile's whole search.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {  // make the initialised barriers visible to the async proxy
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+}
+// TMA bulk copy global -> shared (bytes: multiple of 16, both addresses 16-byte aligned); completes on `bar`
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+// the mbarrier receives one arrival of this thread once all its cp.async copies issued so far have landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+// Barriers of the asynchronous prologue (static shared memory of the kernels that use it).  Thread 0 initialises
+// them, a __syncthreads publishes them; `decoder` expects two arrivals per thread (its cp.async copies, and an
+// explicit one that releases its plain padding stores).
+struct StageBarriers {
+  uint64_t stencil;
+  uint64_t decoder;
+};
+
+__device__ __forceinline__ void stage_barriers_init(StageBarriers& sb) {
+  if (threadIdx.x == 0) {
+    mbar_init(&sb.stencil, 1);
+    mbar_init(&sb.decoder, 2 * blockDim.x);
+    mbar_fence_init();
+  }
+  __syncthreads();
+}
+
+// stencil: ONE TMA bulk copy (UBLKCP) issued by thread 0
+__device__ __forceinline__ void stage_stencil_async(uint64_t* sm_stencil, const uint64_t* stencil, StageBarriers& sb) {
+  if (threadIdx.x == 0) {
+    constexpr uint32_t kBytes = 64 * 8 * sizeof(uint64_t);
+    mbar_expect_tx(&sb.stencil, kBytes);
+    bulk_copy_g2s(sm_stencil, stencil, kBytes, &sb.stencil);
+  }
+}
+
+// decoder: every thread issues its element copies and arrives; nobody waits here
+template <int H, int L>
+__device__ __forceinline__ void stage_decoder_async(float* sm, const ClidDecoder& dec, StageBarriers& sb) {
+  using Lay = MlpLayout<H, L>;
+  constexpr int kW = H * kIn;
+  for (int i = threadIdx.x; i < kW; i += blockDim.x) {
+    const int j = i / kIn, c = i - j * kIn;
+    cp_async4(sm + Lay::kW0 + Lay::w0_index(j, c), dec.weight[0] + i);
+  }
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    sm[Lay::kW0 + Lay::w0_index(j, kIn)] = 0.f;  // padding column
+    if (dec.bias[0]) cp_async4(sm + Lay::kB0 + j, dec.bias[0] + j);
+    else sm[Lay::kB0 + j] = 0.f;
+    cp_async4(sm + Lay::kWout + j, dec.out_weight + j);
+  }
+#pragma unroll
+  for (int l = 1; l < L; ++l) {
+    float* blk = sm + Lay::kHidden + (l - 1) * Lay::kHiddenStride;
+    if ((reinterpret_cast<uintptr_t>(dec.weight[l]) & 15u) == 0) {
+      for (int i = threadIdx.x * 4; i < H * H; i += blockDim.x * 4) cp_async16(blk + i, dec.weight[l] + i);
+    } else {
+      for (int i = threadIdx.x; i < H * H; i += blockDim.x) cp_async4(blk + i, dec.weight[l] + i);
+    }
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+      if (dec.bias[l]) cp_async4(blk + H * H + i, dec.bias[l] + i);
+      else blk[H * H + i] = 0.f;
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (dec.out_bias) cp_async4(sm + Lay::kBout, dec.out_bias);
+    else sm[Lay::kBout] = 0.f;
+  }
+  cp_async_arrive(&sb.decoder);  // async arrival: when this thread's copies have landed
+  mbar_arrive(&sb.decoder);      // release of this thread's plain stores above
+}
+
+// synchronous variant (kernels whose first use of the weights is immediate)
 template <int H, int L>
 __device__ __forceinline__ void stage_decoder(float* sm, const ClidDecoder& dec) {
   using Lay = MlpLayout<H, L>;
-  // first layer: all loads of a thread are issued before its stores (one global round trip)
   constexpr int kW = H * kIn;
-  constexpr int kMaxPer = (kW + 127) / 128;  // CTAs have at least 128 threads
-  float v[kMaxPer];
-#pragma unroll
-  for (int r = 0; r < kMaxPer; ++r) {
-    const int i = threadIdx.x + r * blockDim.x;
-    v[r] = i < kW ? __ldg(dec.weight[0] + i) : 0.f;
+  for (int i = threadIdx.x; i < kW; i += blockDim.x) {
+    const int j = i / kIn, c = i - j * kIn;
+    sm[Lay::kW0 + Lay::w0_index(j, c)] = __ldg(dec.weight[0] + i);
   }
-  float b = 0.f, wo = 0.f;
-  if (threadIdx.x < H) {
-    b = dec.bias[0] ? __ldg(dec.bias[0] + threadIdx.x) : 0.f;
-    wo = __ldg(dec.out_weight + threadIdx.x);
-  }
-#pragma unroll
-  for (int r = 0; r < kMaxPer; ++r) {
-    const int i = threadIdx.x + r * blockDim.x;
-    if (i < kW) {
-      const int j = i / kIn, c = i - j * kIn;
-      sm[Lay::kW0 + Lay::w0_index(j, c)] = v[r];
-    }
-  }
-  for (int j = threadIdx.x; j < H; j += blockDim.x) sm[Lay::kW0 + Lay::w0_index(j, kIn)] = 0.f;  // padding column
-  if (threadIdx.x < H) {
-    sm[Lay::kB0 + threadIdx.x] = b;
-    sm[Lay::kWout + threadIdx.x] = wo;
-  }
-  if (H > blockDim.x) {
-    for (int i = threadIdx.x + blockDim.x; i < H; i += blockDim.x) {
-      sm[Lay::kB0 + i] = dec.bias[0] ? dec.bias[0][i] : 0.f;
-      sm[Lay::kWout + i] = dec.out_weight[i];
-    }
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    sm[Lay::kW0 + Lay::w0_index(j, kIn)] = 0.f;  // padding column
+    sm[Lay::kB0 + j] = dec.bias[0] ? __ldg(dec.bias[0] + j) : 0.f;
+    sm[Lay::kWout + j] = __ldg(dec.out_weight + j);
   }
 #pragma unroll
   for (int l = 1; l < L; ++l) {

@@ -44,20 +44,21 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
   BrickScratch& scratch = *reinterpret_cast<BrickScratch*>(smem + kDecFloats + 2 * 64 * kBrickSlots);
   const ClidMap& m = p.map;
 
-  if constexpr (H > 0) stage_decoder<H, L>(sm_dec, p.dec);
-  if constexpr (kBricks) {
-    const uint4* st_src = reinterpret_cast<const uint4*>(p.bricks.stencil);
-    uint4* st_dst = reinterpret_cast<uint4*>(stencil);
-#pragma unroll
-    for (int i = threadIdx.x; i < 64 * kBrickSlots / 2; i += kQueryThreads) st_dst[i] = __ldg(st_src + i);
-  } else {
+  // asynchronous prologue (common.cuh): stencil by one TMA bulk copy, decoder by cp.async element copies, both
+  // completing on mbarriers that are only waited on where the data is first used
+  __shared__ StageBarriers stage;
+  stage_barriers_init(stage);
+  if constexpr (kBricks) stage_stencil_async(stencil, p.bricks.stencil, stage);
+  if constexpr (H > 0) stage_decoder_async<H, L>(sm_dec, p.dec, stage);
+  if constexpr (!kBricks) {
     for (int c = threadIdx.x; c < m.kc; c += blockDim.x) {
       int64_t h = m.neighbor_dx[3 * c] * m.primes[0] + m.neighbor_dx[3 * c + 1] * m.primes[1] +
                   m.neighbor_dx[3 * c + 2] * m.primes[2];
       cell_mod[c] = floor_mod(h, m.buffer_size);
     }
+    __syncthreads();
   }
-  __syncthreads();
+  bool stencil_ready = !kBricks, decoder_ready = H == 0;
 
   const bool training = p.flags & CLID_TRAINING_MODE;
   const bool local = p.flags & CLID_QUERY_LOCALLY;
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
     TopK<K> top;
     top.init();
     int count = 0;
+    if (!stencil_ready) { mbar_wait(&stage.stencil, 0); stencil_ready = true; }
     if constexpr (kSearch == kSearchBricks) count = search_bricks<K, kQueryThreads>(m, p.bricks, stencil, &scratch.want[0][threadIdx.x], live, px, py, pz, top);
     else if (live) count = search_hashed<K>(m, cell_mod, px, py, pz, local, time_filter, top);
     if (!live) continue;
@@ -182,6 +184,7 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
     // ---- decoder + closed-form spatial gradient
     if constexpr (H > 0) {
       float o, a[kIn];
+      if (!decoder_ready) { mbar_wait(&stage.decoder, 0); decoder_ready = true; }
       mlp_value_and_input_grad<H, L>(sm_dec, z, slope, o, a);
       const float s = p.dec.sdf_scale;
       if (p.out.sdf) p.out.sdf[q] = o * s;

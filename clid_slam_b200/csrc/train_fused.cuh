@@ -77,20 +77,20 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
   __shared__ float sm_scalar[3][kWarps];
 
   const ClidMap& m = p.map;
-  stage_decoder<H, 1>(sm_dec, p.dec);
-  if constexpr (kBricks) {
-    const uint4* st_src = reinterpret_cast<const uint4*>(p.bricks.stencil);
-    uint4* st_dst = reinterpret_cast<uint4*>(stencil);
-#pragma unroll
-    for (int i = threadIdx.x; i < 64 * kBrickSlots / 2; i += kFusedThreads) st_dst[i] = __ldg(st_src + i);
-  } else {
+  // asynchronous prologue (common.cuh): TMA bulk copy of the stencil, cp.async copies of the decoder, mbarriers
+  __shared__ StageBarriers stage;
+  stage_barriers_init(stage);
+  if constexpr (kBricks) stage_stencil_async(stencil, p.bricks.stencil, stage);
+  stage_decoder_async<H, 1>(sm_dec, p.dec, stage);
+  if constexpr (!kBricks) {
     for (int c = threadIdx.x; c < m.kc; c += blockDim.x) {
       int64_t h = m.neighbor_dx[3 * c] * m.primes[0] + m.neighbor_dx[3 * c + 1] * m.primes[1] +
                   m.neighbor_dx[3 * c + 2] * m.primes[2];
       cell_mod[c] = floor_mod(h, m.buffer_size);
     }
+    __syncthreads();
   }
-  __syncthreads();
+  bool stencil_ready = !kBricks, decoder_ready = false;
 
   const bool local = p.flags & CLID_QUERY_LOCALLY;
   const bool time_filter = p.flags & CLID_TIME_FILTER;
@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
     TopK<K> top;
     top.init();
     int count = 0;
+    if (!stencil_ready) { mbar_wait(&stage.stencil, 0); stencil_ready = true; }
     if constexpr (kSearch == kSearchBricks) count = search_bricks<K, kQueryThreads>(m, p.bricks, stencil, &scratch.want[0][threadIdx.x], live, px, py, pz, top);
     else if (live) count = search_hashed<K>(m, cell_mod, px, py, pz, local, time_filter, top);
 
@@ -230,6 +231,7 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
       }
 
       float out;
+      if (!decoder_ready) { mbar_wait(&stage.decoder, 0); decoder_ready = true; }
       mlp_l1_pairs<H, true>(sm_dec, z, slope, out, a, mask);
       sdf = out * s;
       if (p.sdf_out && role_variant == 0) p.sdf_out[q] = sdf;
@@ -402,6 +404,7 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
     if (!kFoldOut && p.dec_grad && p.dec.out_bias) atomicAdd(p.dec_grad + H * kIn + 2 * H, d);
   }
   if (kFoldOut || !p.dec_grad) return;
+  if (!decoder_ready) mbar_wait(&stage.decoder, 0);  // a warp without tiles reads the weights below
   float* gW0 = p.dec_grad;
   float* gb0 = gW0 + H * kIn;
   float* gwout = gb0 + H;
