@@ -100,6 +100,20 @@ class ClidAdamArgs(C.Structure):
     ]
 
 
+class ClidReplayPool(C.Structure):
+    _fields_ = [
+        ("coord", C.c_void_p), ("sdf_label", C.c_void_p), ("weight", C.c_void_p), ("time", C.c_void_p),
+        ("count", C.c_int64), ("new_idx", C.c_void_p), ("n_new", C.c_int64), ("bs_new", C.c_int32),
+    ]
+
+
+class ClidMappingArgs(C.Structure):
+    _fields_ = [
+        ("pool", ClidReplayPool), ("train", ClidTrainFusedArgs), ("adam", ClidAdamArgs),
+        ("iters", C.c_int32), ("seed", C.c_uint64), ("offset", C.c_uint64), ("loss_history", C.c_void_p),
+    ]
+
+
 _lib: Optional[C.CDLL] = None
 
 # every symbol include/clid_sdf.h declares: (name, restype, argtypes)
@@ -126,6 +140,11 @@ _SIGNATURES = [
      [C.POINTER(ClidDecoder), C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p]),
     ("clid_adam_step", C.c_int, [C.POINTER(ClidAdamArgs), C.c_void_p]),
     ("clid_adam_advance", C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    ("clid_draw_batch", C.c_int,
+     [C.POINTER(ClidReplayPool), C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+      C.c_void_p, C.c_void_p]),
+    ("clid_mapping_run", C.c_int,
+     [C.POINTER(ClidMap), C.POINTER(ClidDecoder), C.POINTER(ClidMappingArgs), C.c_uint32, C.c_void_p]),
     ("clid_radius_search", C.c_int,
      [C.POINTER(ClidMap), C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("clid_query_certainty", C.c_int,

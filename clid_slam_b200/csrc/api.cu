@@ -323,6 +323,73 @@ int clid_adam_advance(void* step_state, float lr, float beta1, float beta2, clid
   return CLID_OK;
 }
 
+static int check_pool(const ClidReplayPool* pool, int64_t n) {
+  if (!pool->coord || !pool->sdf_label || pool->count <= 0) return set_error(CLID_EINVAL, "replay pool is empty or NULL");
+  if (pool->bs_new < 0 || pool->bs_new > n) return set_error(CLID_EINVAL, "bs_new %d outside 0..n", pool->bs_new);
+  if (pool->bs_new > 0 && (!pool->new_idx || pool->n_new <= 0)) return set_error(CLID_EINVAL, "bs_new without new_idx");
+  return CLID_OK;
+}
+
+static int launch_draw(const DrawParams& d, cudaStream_t stream) {
+  draw_batch_kernel<<<elementwise_grid(d.n, 256), 256, 0, stream>>>(d);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "draw_batch_kernel launch");
+  return CLID_OK;
+}
+
+int clid_draw_batch(const ClidReplayPool* pool, int64_t n, uint64_t seed, uint64_t offset, float* x, float* label,
+                    float* weight, int32_t* ts, int64_t* index_out, clid_stream_t stream) {
+  if (!pool) return set_error(CLID_EINVAL, "pool is NULL");
+  if (n < 0) return set_error(CLID_EINVAL, "n = %lld", (long long)n);
+  if (n == 0) return CLID_OK;
+  if (!x || !label) return set_error(CLID_EINVAL, "x/label is NULL");
+  if (int rc = check_pool(pool, n)) return rc;
+  if ((weight && !pool->weight) || (ts && !pool->time)) return set_error(CLID_EINVAL, "weight/ts requested but the pool has none");
+  DrawParams d;
+  memset(&d, 0, sizeof(d));
+  d.pool = *pool; d.n = n; d.seed = seed; d.offset = offset;
+  d.x = x; d.label = label; d.weight = weight; d.ts = ts; d.index_out = index_out;
+  return launch_draw(d, static_cast<cudaStream_t>(stream));
+}
+
+int clid_mapping_run(const ClidMap* map, const ClidDecoder* dec, const ClidMappingArgs* a, uint32_t flags,
+                     clid_stream_t stream) {
+  if (!map || !dec || !a) return set_error(CLID_EINVAL, "map/dec/args is NULL");
+  if (a->iters < 0) return set_error(CLID_EINVAL, "iters = %d", a->iters);
+  if (a->iters == 0) return CLID_OK;
+  const ClidTrainFusedArgs& t = a->train;
+  if (t.n <= 0) return set_error(CLID_EINVAL, "train.n = %lld", (long long)t.n);
+  if (!t.x || !t.label || !t.loss) return set_error(CLID_EINVAL, "train.x/label/loss scratch is NULL");
+  if (!a->adam.step_state) return set_error(CLID_EINVAL, "clid_mapping_run needs the device step counter (adam.step_state)");
+  if (int rc = check_pool(&a->pool, t.n)) return rc;
+  if ((t.weight && !a->pool.weight) || (t.ts && !a->pool.time)) return set_error(CLID_EINVAL, "weight/ts scratch given but the pool has none");
+  if (t.dec_grad && !t.scratch) return set_error(CLID_EINVAL, "clid_mapping_run needs train.scratch when the decoder trains");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DrawParams d;
+  memset(&d, 0, sizeof(d));
+  d.pool = a->pool; d.n = t.n; d.seed = a->seed;
+  d.x = const_cast<float*>(t.x); d.label = const_cast<float*>(t.label);
+  d.weight = const_cast<float*>(t.weight); d.ts = const_cast<int32_t*>(t.ts);
+  d.loss = t.loss;
+  ClidAdamArgs adam = a->adam;
+  adam.step = 0;  // advance the device counter at every step
+  for (int it = 0; it < a->iters; ++it) {
+    d.offset = a->offset + (uint64_t)it;
+    d.loss_prev_out = (it > 0 && a->loss_history) ? a->loss_history + 3 * (it - 1) : nullptr;
+    if (int rc = launch_draw(d, s)) return rc;
+    if (int rc = clid_train_fused(map, dec, &t, flags, stream)) return rc;
+    if (t.dec_grad)
+      if (int rc = clid_decoder_grad_reduce(dec, t.scratch, t.n, t.numerical, flags, t.dec_grad, stream)) return rc;
+    if (int rc = clid_adam_step(&adam, stream)) return rc;
+  }
+  if (a->loss_history) {
+    copy3_kernel<<<1, 32, 0, s>>>(t.loss, a->loss_history + 3 * (a->iters - 1));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "copy3_kernel launch");
+  }
+  return CLID_OK;
+}
+
 int clid_radius_search(const ClidMap* map, const float* x, int64_t n, uint32_t flags, float* dist2_out,
                        int64_t* idx_out, clid_stream_t stream) {
   if (!map || !dist2_out || !idx_out) return set_error(CLID_EINVAL, "map/outputs are NULL");

@@ -368,6 +368,64 @@ __global__ void adam_advance_kernel(AdamStepState* st, float lr, float beta1, fl
 #endif
 
 #ifdef CLID_PLAIN_KERNELS
+// ------------------------------------------------------------------------------------------
+// replay-pool draw (Mapper.get_batch, utils/mapper.py:473-523)
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), the counter-based generator torch / cuRAND use as well
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+struct DrawParams {
+  ClidReplayPool pool;
+  int64_t n;
+  uint64_t seed, offset;
+  float* x;
+  float* label;
+  float* weight;
+  int32_t* ts;
+  int64_t* index_out;
+  // bookkeeping of clid_mapping_run folded into the draw: loss of the previous iteration -> history, clear
+  float* loss;
+  float* loss_prev_out;
+};
+
+__global__ void __launch_bounds__(256) draw_batch_kernel(const DrawParams p) {
+  if (p.loss != nullptr && blockIdx.x == 0 && threadIdx.x < 3) {
+    if (p.loss_prev_out != nullptr) p.loss_prev_out[threadIdx.x] = p.loss[threadIdx.x];
+    p.loss[threadIdx.x] = 0.f;
+  }
+  const int64_t n_hist = p.n - p.pool.bs_new;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)p.offset, (uint32_t)(p.offset >> 32)),
+                                  make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+    // 64 random bits scaled to [0, range): floor(u * range / 2^64)
+    const uint64_t u = ((uint64_t)r.x << 32) | r.y;
+    int64_t row;
+    if (i < n_hist) row = (int64_t)__umul64hi(u, (uint64_t)p.pool.count);
+    else row = p.pool.new_idx[__umul64hi(u, (uint64_t)p.pool.n_new)];
+    p.x[3 * i] = p.pool.coord[3 * row]; p.x[3 * i + 1] = p.pool.coord[3 * row + 1]; p.x[3 * i + 2] = p.pool.coord[3 * row + 2];
+    p.label[i] = p.pool.sdf_label[row];
+    if (p.weight) p.weight[i] = p.pool.weight[row];
+    if (p.ts) p.ts[i] = p.pool.time[row];
+    if (p.index_out) p.index_out[i] = row;
+  }
+}
+
+__global__ void copy3_kernel(const float* src, float* dst) {
+  if (threadIdx.x < 3) dst[threadIdx.x] = src[threadIdx.x];
+}
+#endif
+
+#ifdef CLID_PLAIN_KERNELS
 __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamParams a) {
   // the parameter block stays in the constant bank: the two scalars are the only per-step values
   const float step_size = a.step_scalars ? __ldg(a.step_scalars) : a.step_size;

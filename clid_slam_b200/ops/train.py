@@ -48,6 +48,34 @@ def supported(config, decoder) -> Optional[str]:
     return None
 
 
+def draw_batch(coord: torch.Tensor, sdf_label: torch.Tensor, weight: torch.Tensor, time: torch.Tensor, count: int,
+               n: int, seed: int, offset: int, new_idx: Optional[torch.Tensor] = None, bs_new: int = 0):
+    """Mapper.get_batch on the library's generator (clid_draw_batch): n pool rows, the last bs_new of them out of
+    new_idx.  Returns (x [n,3], label [n], weight [n], ts [n] int32, index [n] int64)."""
+    lib = _lib.load()
+    _q._require_cuda(coord, "replay pool")
+    dev = coord.device
+    pool = _lib.ClidReplayPool()
+    pool.coord = _lib.ptr(coord, torch.float32, "coord pool")
+    pool.sdf_label = _lib.ptr(sdf_label, torch.float32, "sdf_label_pool")
+    pool.weight = _lib.ptr(weight, torch.float32, "weight_pool")
+    pool.time = _lib.ptr(time, torch.int32, "time_pool")
+    pool.count = int(count)
+    if bs_new > 0:
+        new_idx = new_idx.to(torch.int64).contiguous()
+        pool.new_idx, pool.n_new, pool.bs_new = new_idx.data_ptr(), int(new_idx.shape[0]), int(bs_new)
+    x = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    label = torch.empty(n, dtype=torch.float32, device=dev)
+    w = torch.empty(n, dtype=torch.float32, device=dev)
+    ts = torch.empty(n, dtype=torch.int32, device=dev)
+    index = torch.empty(n, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.clid_draw_batch(C.byref(pool), n, int(seed) & (2**64 - 1), int(offset), x.data_ptr(), label.data_ptr(),
+                                 w.data_ptr(), ts.data_ptr(), index.data_ptr(), _lib.current_stream(dev))
+    _lib.check(rc, "clid_draw_batch")
+    return x, label, w, ts, index
+
+
 class FusedTrainer:
     def __init__(self, config, neural_points, decoder):
         why = supported(config, decoder)
@@ -108,6 +136,7 @@ class FusedTrainer:
         self.overlap_decoder = True
         self._side_stream = None
         self._pending_reduce = None
+        self._loop_bufs = None      # [bs] batch scratch of run_loop
 
     # ------------------------------------------------------------------
     def _shifted(self, x: torch.Tensor, eik_index: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -270,6 +299,90 @@ class FusedTrainer:
                 self._reduce_pending()
         return loss
 
+    def ensure_step_state(self) -> None:
+        """Device-resident optimiser step counter {step, step_size, bc2_sqrt, pad} (ClidAdamArgs.step_state)."""
+        if self.step_state is None:
+            if self.step != 0:
+                raise RuntimeError("the device step counter must be created before the first optimiser step")
+            self.step_state = torch.zeros(4, dtype=torch.int32, device=self.device)
+
+    def run_loop(self, pool, iters: int, seed: int, global_coord: bool = True) -> torch.Tensor:
+        """`iters` mapping iterations enqueued by ONE native call (clid_mapping_run): replay-pool draw, fused
+        forward + loss + backward, decoder-gradient reduction, Adam -- no Python between iterations.
+        pool: the Mapper (its replay-pool tensors, new_idx, pool_sample_count and dataset flags are read like
+        Mapper.get_batch does).  Returns the loss history [iters, 3] (device tensor)."""
+        cfg, npm, dec, lib, dev = self.cfg, self.npm, self.dec, self.lib, self.device
+        if iters <= 0:
+            return torch.empty(0, 3, dtype=torch.float32, device=dev)
+        self.ensure_step_state()
+        n = int(cfg.bs)
+        numerical = self.numerical and self.weight_e > 0
+        if numerical and int(cfg.gradient_decimation) != 10:
+            raise NotImplementedError("the native loop runs the one-kernel iteration (gradient_decimation 10)")
+        # touched flags only save traffic; a whole-call decision (the loop cannot switch in the middle)
+        self._gathers += iters * n * int(cfg.query_nn_k)
+        if self.touched is not None and self._gathers > self.dense_switch * self.rows:
+            self.touched = None
+
+        ma = _lib.ClidMappingArgs()
+        coord = pool.global_coord_pool if global_coord else pool.coord_pool
+        ma.pool.coord = _lib.ptr(coord, torch.float32, "coord pool")
+        ma.pool.sdf_label = _lib.ptr(pool.sdf_label_pool, torch.float32, "sdf_label_pool")
+        ma.pool.weight = _lib.ptr(pool.weight_pool, torch.float32, "weight_pool")
+        ma.pool.time = _lib.ptr(pool.time_pool, torch.int32, "time_pool")
+        ma.pool.count = int(pool.pool_sample_count)
+        new_idx = pool.new_idx
+        use_new = (cfg.bs_new_sample > 0 and new_idx is not None and not pool.dataset.lose_track
+                   and not pool.dataset.stop_status and new_idx.shape[0] > 0)
+        if use_new:
+            new_idx = new_idx.to(torch.int64).contiguous()
+            ma.pool.new_idx, ma.pool.n_new = new_idx.data_ptr(), int(new_idx.shape[0])
+            ma.pool.bs_new = min(int(new_idx.shape[0]), int(cfg.bs_new_sample))
+
+        bufs = self._loop_bufs
+        if bufs is None or bufs[0].shape[0] != n:
+            f32 = dict(dtype=torch.float32, device=dev)
+            bufs = (torch.empty(n, 3, **f32), torch.empty(n, **f32), torch.empty(n, **f32),
+                    torch.empty(n, dtype=torch.int32, device=dev), torch.zeros(3, **f32))
+            self._loop_bufs = bufs
+        x, label, weight, ts, loss = bufs
+        history = torch.empty(iters, 3, dtype=torch.float32, device=dev)
+
+        m, flags = _q.map_struct(npm, True, npm.local_point_certainties)
+        bricks = npm.brick_index(True) if os.environ.get("CLID_DISABLE_BRICKS", "0") != "1" else None
+        if bricks is not None:
+            m.bricks = C.pointer(bricks.struct)
+            flags |= _q.brick_flags(bricks)
+        if dec.use_leaky_relu:
+            flags |= _lib.LEAKY_RELU
+        ds = dec.abi_struct()
+        a = ma.train
+        a.x, a.ts, a.label, a.weight = x.data_ptr(), ts.data_ptr(), label.data_ptr(), weight.data_ptr()
+        a.n, a.n_norm, a.nd_norm = n, 0, 0
+        a.numerical = int(bool(numerical))
+        a.num_eps = float(cfg.voxel_size_m * cfg.num_grad_step_ratio)
+        a.weight_e = self.weight_e
+        a.weighted = int(bool(cfg.loss_weight_on))
+        a.gfeat = self.feat_grad.data_ptr() if self.train_features else None
+        a.touched = None if self.touched is None else self.touched.data_ptr()
+        a.dec_grad = None if self.dec_grad is None else self.dec_grad.data_ptr()
+        a.loss = loss.data_ptr()
+        if self.dec_grad is not None:
+            need = int(lib.clid_train_fused_scratch_bytes(n, a.numerical))
+            if self._scratch is None or self._scratch.numel() < need:
+                self._scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+            a.scratch, a.scratch_bytes = self._scratch.data_ptr(), need
+        ma.adam = self._adam_args(True, True, 0)
+        ma.iters, ma.seed, ma.offset = int(iters), int(seed) & (2**64 - 1), int(self.step)
+        ma.loss_history = history.data_ptr()
+        with torch.cuda.device(dev):
+            rc = lib.clid_mapping_run(C.byref(m), C.byref(ds), C.byref(ma), flags, _lib.current_stream(dev))
+        _lib.check(rc, "clid_mapping_run")
+        self.step += iters
+        # draw + fused + Adam advance + Adam [+ decoder-gradient reduction] per iteration, + the last loss copy
+        self.launches += iters * (4 + (1 if self.dec_grad is not None else 0)) + 1
+        return history
+
     def _want_overlap(self) -> bool:
         """Fork the decoder side of the optimiser step onto a second stream?  It costs two extra host calls,
         so: always inside a CUDA-graph capture (the host cost is paid once), otherwise only when the feature
@@ -382,8 +495,8 @@ class FusedTrainer:
             tdist.all_reduce(flat, op=tdist.ReduceOp.SUM)
         self.unpack_spatial(flat, loss, shards)
 
-    def _adam_call(self, features: bool, decoder: bool, step_arg: int) -> None:
-        cfg, npm, dev = self.cfg, self.npm, self.device
+    def _adam_args(self, features: bool, decoder: bool, step_arg: int) -> "_lib.ClidAdamArgs":
+        cfg, npm = self.cfg, self.npm
         aa = _lib.ClidAdamArgs()
         if features and self.train_features:
             aa.feat = npm.local_geo_features.data.data_ptr()
@@ -402,6 +515,11 @@ class FusedTrainer:
         aa.lr, aa.beta1, aa.beta2 = float(cfg.lr), 0.9, 0.99
         aa.eps, aa.weight_decay, aa.step = float(cfg.adam_eps), float(cfg.weight_decay), step_arg
         aa.step_state = None if self.step_state is None else self.step_state.data_ptr()
+        return aa
+
+    def _adam_call(self, features: bool, decoder: bool, step_arg: int) -> None:
+        dev = self.device
+        aa = self._adam_args(features, decoder, step_arg)
         with torch.cuda.device(dev):
             _lib.check(self.lib.clid_adam_step(C.byref(aa), _lib.current_stream(dev)), "clid_adam_step")
         self.launches += 1
@@ -461,8 +579,7 @@ class StepPipeline:
         if shards is None and trainer.touched is not None and 2 * n * int(trainer.cfg.query_nn_k) >= trainer.rows:
             trainer.touched = None  # a replayed graph cannot switch later: large batches run dense from the start
         self.device = dev
-        if trainer.step_state is None:
-            trainer.step_state = torch.zeros(4, dtype=torch.int32, device=dev)
+        trainer.ensure_step_state()
         # multi-GPU (spatial shards): two graphs per buffer with the ONE NCCL all-reduce of the step launched
         # eagerly between them -- [kernels, pack] | all-reduce(flat) | [unpack, Adam]
         if sync and shards is None:

@@ -60,6 +60,8 @@ class Mapper:
         # mapping() calls with at least this many iterations capture [get_batch + iteration] once in a CUDA
         # graph and replay it (host cost per iteration ~15 us instead of ~140 us of Python / ctypes); 0 disables
         self.graph_min_iters = int(os.environ.get("CLID_MAPPING_GRAPH_MIN_ITERS", "24"))
+        # mapping() through the native loop (clid_mapping_run); False: Python loop / CUDA graph over get_batch
+        self.native_loop = os.environ.get("CLID_NATIVE_LOOP", "1") != "0"
         self.last_losses = None        # [iters,3] device tensor (total, bce, eikonal) of the last mapping() call
 
         dev, f32 = self.device, self.dtype
@@ -272,10 +274,24 @@ class Mapper:
             coord, sdf_label, ts, _, _, weight = self._batch_in_global_frame()
             return trainer.iteration(coord, sdf_label, ts, weight)
 
+        stock_batches = getattr(self.get_batch, "__func__", None) is Mapper.get_batch
+        # Native loop (the default): the whole call -- replay-pool draw, iteration, optimiser step, x iter_count --
+        # is enqueued by ONE C call (clid_mapping_run), ~10 us of host time per iteration instead of ~140 us of
+        # Python / ctypes, for the 10-iteration calls of every shipped run file as well.  The draw uses the
+        # library's counter-based generator (seeded from torch's), not torch.randint's sequence; a get_batch
+        # replaced by the caller (tests feed recorded batches) runs call by call below.
+        one_kernel = (not trainer.numerical or trainer.weight_e == 0 or int(self.config.gradient_decimation) == 10)
+        if (self.native_loop and stock_batches and not self.ba_done_flag and one_kernel
+                and torch.device(self.device).type == "cuda" and self.pool_sample_count > 0):
+            seed = int(torch.randint(0, 2**62, (1,)).item())  # CPU generator: follows torch.manual_seed, no device sync
+            self.last_losses = trainer.run_loop(self, iter_count, seed, global_coord=True)
+            self.total_iter += iter_count
+            self._log_losses()
+            return
+
         # the replay pool draw (torch.randint on the CUDA generator, fixed shapes) and the iteration are
         # graph-safe; a get_batch replaced by the caller (tests feed recorded batches) is not assumed to be
-        graphable = (self.graph_min_iters > 0 and iter_count >= self.graph_min_iters
-                     and getattr(self.get_batch, "__func__", None) is Mapper.get_batch
+        graphable = (self.graph_min_iters > 0 and iter_count >= self.graph_min_iters and stock_batches
                      and torch.device(self.device).type == "cuda")
         if not graphable:
             for _ in range(iter_count):
@@ -286,7 +302,7 @@ class Mapper:
             return
 
         dev = torch.device(self.device)
-        trainer.step_state = torch.zeros(4, dtype=torch.int32, device=dev)  # device-side Adam step counter
+        trainer.ensure_step_state()  # device-side Adam step counter
         history = torch.empty(iter_count, 3, dtype=torch.float32, device=dev)
         history[0].copy_(body())  # first iteration eagerly: builds the brick index, configures the kernels
         trainer._want_overlap()  # the side stream of the forked optimiser step must exist before the capture

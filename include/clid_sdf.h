@@ -306,6 +306,47 @@ CLID_API int clid_adam_step(const ClidAdamArgs* args, clid_stream_t stream);
  * step >= 0).  For callers that split one optimiser step over several clid_adam_step(step < 0) launches. */
 CLID_API int clid_adam_advance(void* step_state, float lr, float beta1, float beta2, clid_stream_t stream);
 
+/* ---- the mapping loop (utils/mapper.py:473-523 get_batch + :642-836 loop body) ----------------------- */
+
+/* Replay pool of the mapper (utils/mapper.py:84-97, 297-333): device pointers, borrowed. */
+typedef struct ClidReplayPool {
+  const float* coord;      /* [count,3] global_coord_pool (global_coord=True) or coord_pool               */
+  const float* sdf_label;  /* [count]                                                                      */
+  const float* weight;     /* [count] signed sample weight                                                 */
+  const int32_t* time;     /* [count] frame stamps                                                         */
+  int64_t count;           /* pool_sample_count                                                            */
+  const int64_t* new_idx;  /* [n_new] pool rows of this frame's newly observed samples, or NULL            */
+  int64_t n_new;
+  int32_t bs_new;          /* how many of the batch come from new_idx (min(n_new, bs_new_sample), 0 = none)  */
+} ClidReplayPool;
+
+/* Mapper.get_batch (utils/mapper.py:473-523): n uniformly drawn pool rows -- the last bs_new of them from
+ * new_idx -- gathered into x [n,3], label [n], weight [n], ts [n]; index_out [n] int64 (optional) receives the
+ * drawn rows.  The draw is a counter-based generator (Philox4x32-10, key = seed, counter = (offset, sample)),
+ * i.e. reproducible for (seed, offset) but NOT the sequence torch.randint would produce: callers that need
+ * the reference's exact batches feed them through clid_train_fused themselves. */
+CLID_API int clid_draw_batch(const ClidReplayPool* pool, int64_t n, uint64_t seed, uint64_t offset, float* x,
+                             float* label, float* weight, int32_t* ts, int64_t* index_out, clid_stream_t stream);
+
+/* `iters` iterations of the loop body of Mapper.mapping (utils/mapper.py:642-836) enqueued back to back by ONE
+ * call: [clid_draw_batch -> clid_train_fused -> clid_decoder_grad_reduce -> clid_adam_step] x iters, no host
+ * work in between (the reference runs ~600 eager launches and ~10 host synchronisations per iteration; the
+ * Python driver of this library ~10 ctypes calls).  train.x / label / weight / ts must point at caller-owned
+ * [train.n] scratch batches that the loop fills; adam.step_state is required (device-side step counter);
+ * train.loss [3] is used as the per-iteration accumulator and loss_history [iters,3] receives every
+ * iteration's (total, bce, eikonal). */
+typedef struct ClidMappingArgs {
+  ClidReplayPool pool;
+  ClidTrainFusedArgs train;
+  ClidAdamArgs adam;
+  int32_t iters;
+  uint64_t seed;
+  uint64_t offset;         /* iteration i draws with counter offset + i                                    */
+  float* loss_history;     /* [iters,3]                                                                    */
+} ClidMappingArgs;
+CLID_API int clid_mapping_run(const ClidMap* map, const ClidDecoder* dec, const ClidMappingArgs* args,
+                              uint32_t flags, clid_stream_t stream);
+
 /* NeuralPoints.radius_neighborhood_search (model/neural_points.py:971-1030): the raw candidate
  * table.  dist2_out [n,kc] f32, idx_out [n,kc] int64 global ids (-1 invalid).  Only
  * CLID_TIME_FILTER is read from flags. */

@@ -151,3 +151,87 @@ def test_graphed_mapping_tracks_the_eager_loop(mode):
     # and the decoders moved the same way
     for a, b in zip(results[True][2], results[False][2]):
         assert torch.nn.functional.cosine_similarity(a.flatten() - 0, b.flatten() - 0, dim=0) > 0.99
+
+
+def test_native_batch_draw_follows_get_batch_semantics():
+    """clid_draw_batch: uniform rows of the pool, the last bs_new of the batch out of new_idx, values gathered from
+    the drawn rows, reproducible for (seed, offset) and different across offsets (utils/mapper.py:473-523)."""
+    from clid_slam_b200.ops.train import draw_batch
+
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    P, n, bs_new = 50_000, 16384, 1000
+    coord = torch.randn(P + 77, 3, generator=gen, device="cuda")  # rows beyond pool_sample_count must never be drawn
+    label = torch.randn(P + 77, generator=gen, device="cuda")
+    weight = torch.randn(P + 77, generator=gen, device="cuda")
+    time = torch.randint(0, 9, (P + 77,), generator=gen, device="cuda", dtype=torch.int32)
+    new_idx = torch.randperm(P, generator=gen, device="cuda")[:3000]
+    x, lb, w, ts, idx = draw_batch(coord, label, weight, time, P, n, seed=1234, offset=7, new_idx=new_idx, bs_new=bs_new)
+    assert int(idx.min()) >= 0 and int(idx.max()) < P
+    assert torch.equal(x, coord[idx]) and torch.equal(lb, label[idx]) and torch.equal(w, weight[idx]) and torch.equal(ts, time[idx])
+    assert bool(torch.isin(idx[n - bs_new:], new_idx).all()), "the tail of the batch comes from the new samples"
+    # uniform over the pool: 16 equal bins of the history part, chi-square with 15 dof (99.9 % quantile 37.7)
+    hist = torch.bincount((idx[: n - bs_new] * 16 // P), minlength=16).double()
+    expect = (n - bs_new) / 16
+    assert float(((hist - expect) ** 2 / expect).sum()) < 45.0
+    again = draw_batch(coord, label, weight, time, P, n, seed=1234, offset=7, new_idx=new_idx, bs_new=bs_new)[4]
+    other = draw_batch(coord, label, weight, time, P, n, seed=1234, offset=8, new_idx=new_idx, bs_new=bs_new)[4]
+    assert torch.equal(idx, again) and not torch.equal(idx, other)
+
+
+@pytest.mark.parametrize("mode", ["numerical", "analytic"])
+def test_native_mapping_loop_matches_the_python_loop(mode):
+    """Mapper.mapping through clid_mapping_run (one native call for all iterations) against the call-by-call Python
+    loop fed with the very batches the native draw produces: same losses, same trained map."""
+    from clid_slam_b200.config import ncd128
+    from clid_slam_b200.model.decoder import Decoder
+    from clid_slam_b200.model.local_point_cloud_map import LocalPointCloudMap
+    from clid_slam_b200.model.neural_points import NeuralPoints
+    from clid_slam_b200.ops.train import draw_batch
+    from clid_slam_b200.utils.mapper import Mapper
+
+    iters = 10
+    results = []
+    for native in (True, False):
+        torch.manual_seed(42)
+        cfg = ncd128()
+        cfg.device = "cuda"
+        cfg.use_pin_mapper = True
+        cfg.buffer_size = 2_000_003
+        cfg.feature_std = 0.05
+        cfg.bs = 4096
+        if mode == "analytic":
+            cfg.numerical_grad, cfg.gradient_decimation = False, 1
+        dec = Decoder(cfg, cfg.geo_mlp_hidden_dim, cfg.geo_mlp_level, 1)
+        npm = NeuralPoints(cfg)
+        ds = FakeDataset(1)
+        mapper = Mapper(cfg, ds, npm, LocalPointCloudMap(cfg), dec)
+        gen = torch.Generator(device="cuda").manual_seed(5)
+        npm.travel_dist = torch.zeros(1, device="cuda")
+        mapper.process_frame(_scan(gen, "cuda"), None, torch.eye(4, device="cuda", dtype=torch.float64), 0)
+        mapper.adaptive_iter_offset = 0
+        mapper.native_loop = native
+        torch.manual_seed(7)  # the native loop seeds its generator from torch's CPU generator
+        if not native:
+            seed = int(torch.randint(0, 2**62, (1,)).item())
+            n_new = 0 if mapper.new_idx is None else int(mapper.new_idx.shape[0])
+            bs_new = min(n_new, cfg.bs_new_sample) if cfg.bs_new_sample > 0 else 0
+            feed = iter(range(iters))
+
+            def replay(global_coord=False):
+                x, lb, w, ts, _ = draw_batch(mapper.global_coord_pool, mapper.sdf_label_pool, mapper.weight_pool,
+                                             mapper.time_pool, mapper.pool_sample_count, cfg.bs, seed, next(feed),
+                                             new_idx=mapper.new_idx, bs_new=bs_new)
+                return x, lb, ts, None, None, None, w
+
+            mapper.get_batch = replay
+        mapper.mapping(iters)
+        results.append((mapper.last_losses.cpu(), npm.geo_features.clone(), npm.point_certainties.clone(),
+                        [p.detach().clone() for p in dec.parameters()]))
+    (l_n, f_n, c_n, d_n), (l_p, f_p, c_p, d_p) = results
+    assert l_n.shape == (iters, 3)
+    torch.testing.assert_close(l_n, l_p, rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(c_n, c_p, rtol=1e-4, atol=1e-5)
+    bad = ((f_n - f_p).abs() > 1e-5 + 1e-3 * f_p.abs()).double().mean().item()
+    assert bad < 5e-3, f"{bad:.2e} of the feature entries differ"  # Adam turns ~0 gradients' signs into +-lr steps
+    for a, b in zip(d_n, d_p):
+        torch.testing.assert_close(a, b, rtol=2e-3, atol=2e-5)
