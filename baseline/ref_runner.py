@@ -63,7 +63,7 @@ class _FakeDataset:  # the attributes utils/mapper.py reads from SLAMDataset
 
 
 def run(device: str, mode: str, batch: int, side: int, sheets: int, steps: int, warmup: int, threads: int = 0,
-        pool_batches: int = 4, inference_passes: int = 3):
+        pool_batches: int = 4, inference_passes: int = 3, local_map_radius: float = 1.0e4):
     """Times `Mapper.mapping(steps)` (after `mapping(warmup)`) and the inference forward + gradient.
     Returns a dict (samples/s of both, ms per step, the world size, the final losses are not exposed by
     the reference)."""
@@ -83,7 +83,7 @@ def run(device: str, mode: str, batch: int, side: int, sheets: int, steps: int, 
     cfg.o3d_vis_on = False
     cfg.wandb_vis_on = False
     cfg.feature_std = 0.05
-    cfg.local_map_radius = 1.0e4
+    cfg.local_map_radius = local_map_radius
     cfg.numerical_grad = mode == "numerical"
     cfg.gradient_decimation = 10 if cfg.numerical_grad else 1
     cfg.bs = batch
@@ -134,5 +134,6 @@ def run(device: str, mode: str, batch: int, side: int, sheets: int, steps: int, 
             fwd.append(time.perf_counter() - t0)
     fwd_s = sum(fwd) / len(fwd)
     return {"samples_per_s": batch / step_s, "ms_per_step": step_s * 1e3, "neural_points": int(npm.count()),
+            "local_points": int(npm.local_count()),
             "inference_samples_per_s": batch / fwd_s, "inference_ms": fwd_s * 1e3,
             "threads": torch.get_num_threads(), "device": device, "steps": steps, "warmup": warmup}

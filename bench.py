@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--mode", default="analytic", choices=["analytic", "numerical"],
                     help="eikonal gradient mode of the training step")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference legs (CPU and eager CUDA)")
+    ap.add_argument("--no-shipped-config", action="store_true", help="skip the configs[1] leg (process_frame + mapping(10))")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity gate against the oracle")
     ap.add_argument("--sharding", default="spatial", choices=["spatial", "replicated"],
                     help="N > 1: slab-partitioned samples and neural points with a neighbour exchange of the band "
@@ -497,6 +498,10 @@ def run_native(args):
             line["parity"] = parity
         if numerical_line is not None:
             line["numerical_mode"] = numerical_line
+        if world == 1 and not args.no_shipped_config:
+            # the configuration the reference ships (configs[1]), both gradient modes; untimed w.r.t. `value`
+            line["shipped_config"] = {mode: shipped_config(device, mode, with_reference=not args.no_cpu_baseline)
+                                      for mode in ("numerical", "analytic")}
         if world == 1 and not args.no_cpu_baseline:
             # free the benchmark's device memory before the reference builds its own world on the same GPU
             line["cpu_baseline"] = cpu_reference(args.mode, steps=3, warmup=1, n=BATCH)
@@ -511,6 +516,106 @@ def run_native(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ shipped configuration
+SHIP_SIDE, SHIP_SHEETS, SHIP_RADIUS, SHIP_SCAN = 600, 1, 72.0, 30000
+
+
+def shipped_config(device, mode, frames=4, with_reference=True):
+    """BASELINE configs[1]: the configuration the reference ships (config/run_ncd128.yaml: 16384-sample batches,
+    10 iterations per frame), driven the way slam.py:135-208 drives it -- per frame Mapper.process_frame (sampler,
+    map insert, replay pool, local window; the brick index is rebuilt lazily by the first query) then
+    Mapper.mapping(10) with a fresh trainer.  ~100 k local neural points (one wavy sheet, local_map_radius 72 m),
+    30 k-point synthetic scans.  Times are host wall clock with a device synchronise on both sides."""
+    import numpy as np
+    import torch
+
+    from clid_slam_b200.config import ncd128
+    from clid_slam_b200.model.decoder import Decoder
+    from clid_slam_b200.model.local_point_cloud_map import LocalPointCloudMap
+    from clid_slam_b200.model.neural_points import NeuralPoints
+    from clid_slam_b200.synth import wavy_sheets
+    from clid_slam_b200.utils.mapper import Mapper
+
+    class _DS:
+        lose_track = False
+        stop_status = False
+        processed_frame = 0
+        gt_pose_provided = True
+        pgo_poses = None
+        static_mask = None
+
+    torch.manual_seed(42)
+    cfg = ncd128()
+    cfg.device = device
+    cfg.feature_std = 0.05
+    cfg.local_map_radius = SHIP_RADIUS
+    cfg.numerical_grad = mode == "numerical"
+    cfg.gradient_decimation = 10 if cfg.numerical_grad else 1
+    dec = Decoder(cfg, cfg.geo_mlp_hidden_dim, cfg.geo_mlp_level, 1)
+    npm = NeuralPoints(cfg)
+    gen = torch.Generator(device=device).manual_seed(1)
+    world = wavy_sheets(SHIP_SIDE, SHIP_SHEETS, cfg.voxel_size_m, gen, device=device)
+    n_total = frames + 1
+    ds = _DS()
+    ds.gt_poses = ds.odom_poses = np.tile(np.eye(4), (n_total, 1, 1))
+    npm.travel_dist = torch.zeros(1, device=device)
+    npm.update(world, torch.zeros(3, device=device), torch.eye(3, device=device), 0)
+    mapper = Mapper(cfg, ds, npm, LocalPointCloudMap(cfg), dec)
+    rows = {"process_frame_ms": [], "mapping_ms": [], "mapping_enqueue_ms": [], "local_points": []}
+    for frame in range(n_total):
+        ds.processed_frame = frame
+        pose = torch.eye(4, device=device, dtype=torch.float64)
+        pose[0, 3], pose[2, 3] = 0.5 * frame, 2.0
+        ds.gt_poses[frame] = pose.cpu().numpy()
+        npm.travel_dist = torch.arange(frame + 1, device=device, dtype=torch.float32) * 0.5
+        # a scan: 30 k world points within range of the sensor, slightly noisy, in the sensor frame
+        origin = pose[:3, 3].float()
+        near = world[(world - origin).norm(dim=1) < cfg.max_range]
+        pick = torch.randint(0, near.shape[0], (SHIP_SCAN,), generator=gen, device=device)
+        scan = near[pick] + 0.01 * torch.randn(SHIP_SCAN, 3, generator=gen, device=device) - origin
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mapper.process_frame(scan, None, pose, frame)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        mapper.mapping(cfg.iters)
+        t2 = time.perf_counter()
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        if frame >= 1:  # frame 0 pays one-off costs (kernel attributes, first allocations)
+            rows["process_frame_ms"].append((t1 - t0) * 1e3)
+            rows["mapping_enqueue_ms"].append((t2 - t1) * 1e3)
+            rows["mapping_ms"].append((t3 - t1) * 1e3)
+            rows["local_points"].append(int(npm.local_count()))
+    iters = max(1, cfg.iters + mapper.adaptive_iter_offset)
+    med = {k: statistics.median(v) for k, v in rows.items()}
+    out = {"workload": f"BASELINE configs[1]: run_ncd128 shapes, batch {cfg.bs}, {iters} iterations/frame ({mode} gradient), "
+                       f"{int(med['local_points'])} local neural points, {SHIP_SCAN}-point scans; per frame process_frame + mapping",
+           "frames_timed": frames, "iterations_per_frame": iters,
+           "process_frame_ms": med["process_frame_ms"], "mapping_ms": med["mapping_ms"],
+           "mapping_host_enqueue_ms": med["mapping_enqueue_ms"],
+           "mapping_us_per_iteration": med["mapping_ms"] * 1e3 / iters,
+           "host_us_per_iteration": med["mapping_enqueue_ms"] * 1e3 / iters,
+           "samples_per_s_in_mapping": iters * cfg.bs / (med["mapping_ms"] * 1e-3),
+           "final_loss": [float(v) for v in mapper.last_losses[-1].tolist()]}
+    if with_reference:
+        try:
+            from baseline import ref_runner
+
+            if ref_runner.available():
+                del mapper, npm
+                torch.cuda.empty_cache()
+                r = ref_runner.run(device, mode, cfg.bs, SHIP_SIDE, SHIP_SHEETS, steps=10, warmup=10, inference_passes=2,
+                                   local_map_radius=SHIP_RADIUS)
+                out["reference_eager_cuda_us_per_iteration"] = r["ms_per_step"] * 1e3
+                out["reference_local_points"] = r["local_points"]
+                out["speedup_over_eager_cuda"] = r["ms_per_step"] * 1e3 / out["mapping_us_per_iteration"]
+        except Exception as exc:
+            out["reference_eager_cuda_us_per_iteration"] = None
+            out["reference_error"] = f"{type(exc).__name__}: {exc}"[:200]
+    return out
 
 
 # ------------------------------------------------------------------------------------------ reference arm
