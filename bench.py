@@ -53,9 +53,12 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference legs (CPU and eager CUDA)")
     ap.add_argument("--no-shipped-config", action="store_true", help="skip the configs[1] leg (process_frame + mapping(10))")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity gate against the oracle")
-    ap.add_argument("--sharding", default="spatial", choices=["spatial", "replicated"],
-                    help="N > 1: slab-partitioned samples and neural points with a neighbour exchange of the band "
-                         "gradients (default) or any-sample-anywhere with a dense feature-gradient all-reduce")
+    ap.add_argument("--sharding", default="peer", choices=["peer", "spatial", "replicated"],
+                    help="N > 1: slab-partitioned samples and neural points; 'peer' (default): band gradients added straight "
+                         "into the slab neighbours' tables by the fused kernel and [decoder grads | loss] all-reduced by a "
+                         "one-shot kernel pair, both over NVLink peer memory, one CUDA graph per step, no NCCL on the data "
+                         "path; 'spatial': NCCL all-reduce + neighbour send/recv between two graphs; 'replicated': "
+                         "any-sample-anywhere with a dense feature-gradient all-reduce")
     return ap.parse_args()
 
 
@@ -191,7 +194,7 @@ def run_native(args):
     gen = torch.Generator(device=device).manual_seed(1000 + rank)
     n_batches = 4  # rotate a few batches so no step sees the previous step's exact access pattern
     shards = None
-    if world > 1 and args.sharding == "spatial":
+    if world > 1 and args.sharding in ("spatial", "peer"):
         # slab partition along the longest map axis; a rank's samples are those whose voxel lies in
         # its slab (what a per-rank replay pool would hand out), see clid_slam_b200/dist.py
         from clid_slam_b200.dist import SpatialShards
@@ -232,6 +235,9 @@ def run_native(args):
         parity = parity_gate(npm, dec, cfg, *_xlwt(batches[0]))
 
     trainer = FusedTrainer(cfg, npm, dec)
+    peer_mode = world > 1 and args.sharding == "peer"
+    if peer_mode:
+        trainer.attach_peers(shards)
     n_global = BATCH * world
     nd_global = 0
     if cfg.numerical_grad:
@@ -251,9 +257,9 @@ def run_native(args):
         from clid_slam_b200.ops.train import StepPipeline
 
         # neighbour send/recv on a process group of its own: overlaps the [decoder grads | loss] all-reduce
-        p2p_group = dist.new_group() if multi and shards is not None else None
-        kw = dict(n_global=n_global, nd_global=nd_global, shards=shards, sync=multi and shards is None,
-                  p2p_group=p2p_group)
+        p2p_group = dist.new_group() if multi and shards is not None and not peer_mode else None
+        kw = dict(n_global=n_global, nd_global=nd_global, shards=None if peer_mode else shards,
+                  sync=multi and shards is None, p2p_group=p2p_group)
         pipe_dev = StepPipeline(trainer, BATCH, buffers=batches, **kw)
         pipe_host = StepPipeline(trainer, BATCH, **kw)
 
@@ -263,7 +269,7 @@ def run_native(args):
         def step(i):
             x, label, weight, ts = batches[i % n_batches]
             return trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global,
-                                     sync=multi and shards is None, shards=shards)
+                                     sync=multi and shards is None, shards=None if peer_mode else shards)
 
     for i in range(max(args.warmup, 3)):
         flush.zero_()
@@ -313,8 +319,8 @@ def run_native(args):
         if graphed:
             pipe_host.stage((i + 1) % 2, host_batches[(i + 1) % n_batches])
             loss = pipe_host.run(i % 2)
-            if multi:
-                # N > 1: the host side of a step (two graph launches + NCCL enqueues from Python) is about as
+            if multi and not peer_mode:
+                # N > 1 through NCCL: the host side of a step (two graph launches + NCCL enqueues from Python) is about as
                 # long as the step itself, so the loss is simply read back here (blocking)
                 loss_host = loss.cpu()
                 losses_read += 1
@@ -333,12 +339,12 @@ def run_native(args):
         else:
             x, label, weight, ts = (t.to(device, non_blocking=True) for t in host_batches[i % n_batches])
             loss = trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global,
-                                     sync=shards is None, shards=shards)
+                                     sync=shards is None, shards=None if peer_mode else shards)
             loss_host = loss.cpu()  # device -> host read of the step's result (synchronises)
             losses_read += 1
             e1.record()
         e2e_events.append((e0, e1))
-    if graphed and not multi:
+    if graphed and (peer_mode or not multi):
         loss_ready[(args.steps - 1) % 2].synchronize()
         loss_host = loss_pinned[(args.steps - 1) % 2].clone()
         losses_read += 1
@@ -365,8 +371,10 @@ def run_native(args):
         flush.zero_()
         x, label, weight, ts = batches[i % n_batches]
         trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global,
-                          sync=multi and shards is None, shards=shards)
+                          sync=multi and shards is None, shards=None if peer_mode else shards)
     sync_all()
+    if peer_mode:
+        trainer.peer.check()
     fwd_ms = [a.elapsed_time(b) for a, b in trainer.forward_events]
     bwd_ms = [a.elapsed_time(b) for a, b in trainer.backward_events]
     trainer.forward_events = trainer.backward_events = None
@@ -458,6 +466,11 @@ def run_native(args):
                 "samples_per_step": samples_per_step, "neural_points": int(npm.count()),
                 "mean_valid_candidates": mean_nn, "l2": "flushed before every timed step (256 MiB write, then 256 MiB read so evictions are clean)",
                 "parallelism": ("single GPU" if world == 1 else
+                                f"x{world}: samples and neural points sharded by map slab; boundary-band feature gradients "
+                                f"({int(shards.shared_rows.numel())} band rows in total) are added into the slab neighbour's "
+                                f"table by the fused kernel over NVLink peer memory, [decoder grads | loss] all-reduced by a "
+                                f"one-shot peer-memory kernel pair, one CUDA graph per step, no NCCL on the data path"
+                                if peer_mode else
                                 f"x{world}: samples and neural points sharded by map slab; per step one 3 kB NCCL "
                                 f"all-reduce [decoder grads | loss] and a neighbour send/recv of the boundary-band "
                                 f"feature gradients ({int(shards.shared_rows.numel())} band rows in total)"
@@ -488,7 +501,7 @@ def run_native(args):
                     "wall_ms_per_step_incl_flush": wall_e2e_ms / args.steps,
                     "wall_ms_per_step_incl_flush_device_resident_loop": wall_dev_ms / args.steps,
                     "pipeline": ("depth 2: batch i+1 staged host->device on a copy stream during step i; the loss of "
-                                 "step i-1 is read on the host after step i has been enqueued") if (graphed and not multi)
+                                 "step i-1 is read on the host after step i has been enqueued") if (graphed and (peer_mode or not multi))
                     else "batch i+1 staged host->device on a copy stream during step i; blocking loss read per step"},
             "gpu_launches": launches,
             "clocks": clocks,

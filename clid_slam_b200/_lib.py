@@ -81,7 +81,8 @@ class ClidTrainFusedArgs(C.Structure):
         ("n", C.c_int64), ("n_norm", C.c_int64), ("nd_norm", C.c_int64),
         ("weight_e", C.c_float), ("num_eps", C.c_float), ("weighted", C.c_int32), ("numerical", C.c_int32),
         ("gfeat", C.c_void_p), ("touched", C.c_void_p), ("dec_grad", C.c_void_p), ("loss", C.c_void_p),
-        ("sdf_out", C.c_void_p), ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t),
+        ("sdf_out", C.c_void_p), ("peer_grad", C.c_void_p * 2), ("peer_axis", C.c_int32), ("peer_band", C.c_int32 * 4),
+        ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t),
     ]
 
 
@@ -97,6 +98,14 @@ class ClidAdamArgs(C.Structure):
         ("dec_grad", C.c_void_p), ("dec_m", C.c_void_p), ("dec_v", C.c_void_p),
         ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
         ("weight_decay", C.c_float), ("step", C.c_int32), ("step_state", C.c_void_p),
+    ]
+
+
+class ClidPeerArgs(C.Structure):
+    _fields_ = [
+        ("slots_of", C.c_void_p * 8), ("flags_of", C.c_void_p * 8), ("epoch", C.c_void_p),
+        ("rank", C.c_int32), ("world", C.c_int32), ("n0", C.c_int32), ("n1", C.c_int32), ("stride", C.c_int32),
+        ("timeout_ms", C.c_int32), ("error", C.c_void_p),
     ]
 
 
@@ -140,6 +149,13 @@ _SIGNATURES = [
      [C.POINTER(ClidDecoder), C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p]),
     ("clid_adam_step", C.c_int, [C.POINTER(ClidAdamArgs), C.c_void_p]),
     ("clid_adam_advance", C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    ("clid_enable_peer_access", C.c_int, [C.c_int32]),
+    ("clid_peer_alloc", C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    ("clid_peer_free", C.c_int, [C.c_void_p]),
+    ("clid_ipc_open", C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    ("clid_ipc_close", C.c_int, [C.c_void_p]),
+    ("clid_peer_publish", C.c_int, [C.POINTER(ClidPeerArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("clid_peer_reduce", C.c_int, [C.POINTER(ClidPeerArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
     ("clid_draw_batch", C.c_int,
      [C.POINTER(ClidReplayPool), C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
       C.c_void_p, C.c_void_p]),

@@ -12,6 +12,7 @@
 #include "query_fwd.cuh"
 #include "train.cuh"
 #include "decoder_grad.cuh"
+#include "peer.cuh"
 #include "train_fused.cuh"
 
 namespace clid {
@@ -236,6 +237,13 @@ int clid_train_fused(const ClidMap* map, const ClidDecoder* dec, const ClidTrain
   p.n = a->n; p.n_norm = a->n_norm > 0 ? a->n_norm : a->n;
   p.nd_norm = a->nd_norm > 0 ? a->nd_norm : (a->n + 9) / 10;
   p.weight_e = a->weight_e; p.weighted = a->weighted; p.flags = flags;
+  for (int s = 0; s < 2; ++s) {
+    p.peer_grad[s] = a->peer_grad[s];
+    if (a->peer_grad[s] && !aligned16(a->peer_grad[s])) return set_error(CLID_EINVAL, "peer_grad must be 16-byte aligned");
+  }
+  if ((a->peer_grad[0] || a->peer_grad[1]) && (a->peer_axis < 0 || a->peer_axis > 2)) return set_error(CLID_EINVAL, "peer_axis %d", a->peer_axis);
+  p.peer_axis = a->peer_axis;
+  for (int s = 0; s < 4; ++s) p.peer_band[s] = a->peer_band[s];
   p.num_eps = 0.f;
   if (a->numerical) {
     if (!(a->num_eps > 0.f)) return set_error(CLID_EINVAL, "numerical mode needs num_eps > 0");
@@ -320,6 +328,87 @@ int clid_adam_advance(void* step_state, float lr, float beta1, float beta2, clid
   adam_advance_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<AdamStepState*>(step_state), lr, beta1, beta2);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "adam_advance_kernel launch");
+  return CLID_OK;
+}
+
+static int check_peer(const ClidPeerArgs* a) {
+  if (!a) return set_error(CLID_EINVAL, "peer args are NULL");
+  if (a->world < 1 || a->world > 8 || a->rank < 0 || a->rank >= a->world) return set_error(CLID_EINVAL, "rank %d / world %d", a->rank, a->world);
+  if (a->n0 < 0 || a->n1 < 0 || a->n0 + a->n1 <= 0 || a->n0 + a->n1 > a->stride) return set_error(CLID_EINVAL, "n0 %d + n1 %d vs stride %d", a->n0, a->n1, a->stride);
+  if (!a->epoch) return set_error(CLID_EINVAL, "epoch is NULL");
+  for (int r = 0; r < a->world; ++r)
+    if (!a->slots_of[r] || !a->flags_of[r]) return set_error(CLID_EINVAL, "slots/flags of rank %d are NULL", r);
+  return CLID_OK;
+}
+
+int clid_enable_peer_access(int32_t peer_device) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev == peer_device) return CLID_OK;
+  int can = 0;
+  e = cudaDeviceCanAccessPeer(&can, dev, peer_device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceCanAccessPeer");
+  if (!can) return set_error(CLID_EUNSUPPORTED, "device %d cannot access device %d (no NVLink / PCIe peer path)", dev, peer_device);
+  e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); return CLID_OK; }
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+  return CLID_OK;
+}
+
+int clid_peer_alloc(size_t bytes, void** ptr_out, void* handle64_out) {
+  if (!ptr_out || !handle64_out || bytes == 0) return set_error(CLID_EINVAL, "ptr_out/handle64_out is NULL or bytes == 0");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  e = cudaMemset(p, 0, bytes);
+  if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaMemset"); }
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaIpcGetMemHandle"); }
+  memcpy(handle64_out, &h, sizeof(h));
+  *ptr_out = p;
+  return CLID_OK;
+}
+
+int clid_peer_free(void* ptr) {
+  if (!ptr) return CLID_OK;
+  cudaError_t e = cudaFree(ptr);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFree");
+  return CLID_OK;
+}
+
+int clid_ipc_open(const void* handle64, void** base_out) {
+  if (!handle64 || !base_out) return set_error(CLID_EINVAL, "handle/base_out is NULL");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  cudaError_t e = cudaIpcOpenMemHandle(base_out, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle");
+  return CLID_OK;
+}
+
+int clid_ipc_close(void* base) {
+  if (!base) return CLID_OK;
+  cudaError_t e = cudaIpcCloseMemHandle(base);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaIpcCloseMemHandle");
+  return CLID_OK;
+}
+
+int clid_peer_publish(const ClidPeerArgs* a, const float* src0, const float* src1, clid_stream_t stream) {
+  if (int rc = check_peer(a)) return rc;
+  if ((a->n0 > 0 && !src0) || (a->n1 > 0 && !src1)) return set_error(CLID_EINVAL, "src is NULL");
+  peer_publish_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a, src0, src1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "peer_publish_kernel launch");
+  return CLID_OK;
+}
+
+int clid_peer_reduce(const ClidPeerArgs* a, float* dst0, float* dst1, clid_stream_t stream) {
+  if (int rc = check_peer(a)) return rc;
+  if ((a->n0 > 0 && !dst0) || (a->n1 > 0 && !dst1)) return set_error(CLID_EINVAL, "dst is NULL");
+  peer_reduce_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a, dst0, dst1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "peer_reduce_kernel launch");
   return CLID_OK;
 }
 

@@ -40,6 +40,9 @@ struct TrainFusedParams {
   float* loss;           // [3] += total, bce, eikonal
   float* sdf_out;        // [n] or NULL (diagnostics)
   float* fold_rows;      // kFoldOut: [tiles*32][16] rows (c'[12], activation bits) for decoder_grad_kernel
+  float* peer_grad[2];   // gfeat of the lower / upper slab neighbour (peer-mapped) or NULL
+  int peer_axis;
+  int peer_band[4];      // inclusive cell ranges of the bands shared with the lower / upper neighbour
   int64_t n;
   int64_t n_norm;        // mean denominator of the bce term (global batch size when sharded)
   int64_t nd_norm;       // mean denominator of the numerical eikonal term (global decimated count)
@@ -50,6 +53,16 @@ struct TrainFusedParams {
 };
 
 constexpr int kFusedThreads = kQueryThreads;
+
+// which boundary band (1 = shared with the lower slab neighbour, 2 = with the upper one, 0 = private) the neural
+// point at coordinate q of the slab axis lies in; the cell rounding is the host's (dist.SpatialShards)
+__device__ __forceinline__ uint32_t band_of(const TrainFusedParams& p, float q, float res) {
+  const int c = cell_of(q, res);
+  uint32_t b = 0u;
+  if (p.peer_grad[0] != nullptr && c >= p.peer_band[0] && c <= p.peer_band[1]) b |= 1u;
+  if (p.peer_grad[1] != nullptr && c >= p.peer_band[2] && c <= p.peer_band[3]) b |= 2u;
+  return b;
+}
 constexpr int kNumTileSamples = 20;  // base samples per warp tile in numerical mode
 
 // kFoldOut: the decoder-gradient fold (Gd += d c') is not done by the warp itself; every lane writes
@@ -162,6 +175,8 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
     int row[K];
     float vx[K], vy[K], vz[K], w[K], u[K];
     float S = 0.f, sdf = 0.f, cbar = 0.f;
+    uint32_t peer_bits = 0u;  // two bits per neighbour: its row is shared with the lower (1) / upper (2) slab neighbour
+    const bool peers = p.peer_grad[0] != nullptr || p.peer_grad[1] != nullptr;
     float z[kIn], a[kIn];
     Moments mom;
 #pragma unroll
@@ -181,6 +196,7 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
           vx[k] = valid ? px - rec[k].x : 0.f; vy[k] = valid ? py - rec[k].y : 0.f; vz[k] = valid ? pz - rec[k].z : 0.f;
           u[k] = valid ? 1.0f / (top.d[k] + kIdwEps) : 0.f;
           S += u[k];
+          if (peers && valid) peer_bits |= band_of(p, p.peer_axis == 0 ? rec[k].x : (p.peer_axis == 1 ? rec[k].y : rec[k].z), m.resolution) << (2 * k);
         }
       } else {
 #pragma unroll
@@ -192,6 +208,7 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
           vx[k] = valid ? px - qx : 0.f; vy[k] = valid ? py - qy : 0.f; vz[k] = valid ? pz - qz : 0.f;
           u[k] = valid ? 1.0f / (top.d[k] + kIdwEps) : 0.f;
           S += u[k];
+          if (peers && valid) peer_bits |= band_of(p, p.peer_axis == 0 ? qx : (p.peer_axis == 1 ? qy : qz), m.resolution) << (2 * k);
         }
       }
 #pragma unroll
@@ -326,6 +343,9 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
             }
             red_add_row(p.gfeat, row[k], tt);
             if (p.touched) p.touched[row[k]] = 1;
+            // band rows: the same contribution straight into the slab neighbour's gradient table (NVLink)
+            if (peer_bits & (1u << (2 * k))) red_add_row(p.peer_grad[0], row[k], tt);
+            if (peer_bits & (2u << (2 * k))) red_add_row(p.peer_grad[1], row[k], tt);
           }
         }
       }

@@ -137,6 +137,7 @@ class SpatialShards:
                 boundaries = torch.empty(0, dtype=torch.int64, device=dev)
         self.boundaries = boundaries.to(device=dev, dtype=torch.int64).contiguous()
         band = reach + margin
+        self.band = int(band)
         shared = torch.zeros(cell.shape[0], dtype=torch.bool, device=dev)
         for b in self.boundaries.tolist():
             shared |= (cell >= b - band) & (cell <= b + band - 1)
@@ -222,3 +223,103 @@ class NeighbourExchange:
     def unpack(self, grad: torch.Tensor) -> None:
         for _, rows, _, recv in self.sides:
             grad.index_add_(0, rows, recv)
+
+
+class PeerLink:
+    """Peer-mapped buffers of all ranks of one box (CUDA IPC over NVLink / NVSwitch) for the fused gradient
+    exchange of the spatially sharded step -- no NCCL call on the step's data path:
+
+      grad[2]   [rows, F]  feature-gradient tables, ping-pong by step parity.  clid_train_fused adds the
+                contributions to a boundary-band row into the slab neighbour's table as well
+                (ClidTrainFusedArgs.peer_grad, red.global.add over NVLink); a rank can run at most one step ahead
+                of its neighbours (the flag wait below), so two tables make a second barrier unnecessary.
+      slots     [world, stride] + flags [world]: one-shot all-reduce of [decoder gradients | loss]
+                (clid_peer_publish / clid_peer_reduce), whose flag wait is also the barrier that orders the
+                neighbours' remote adds before this rank's optimiser step.
+
+    Everything lives in ONE torch allocation per rank; its cudaIpcMemHandle (torch's `_share_cuda_`) travels through
+    torch.distributed once, and every other rank opens it with ITS device current (clid_ipc_open), so the mapping
+    belongs to the importing device with lazy peer access to the exporter -- memory imported under another
+    device's context is not reachable from this device's kernels."""
+
+    def __init__(self, rows: int, feat_dim: int, n_small: int, device: torch.device, group=None):
+        import ctypes as C
+
+        from . import _lib
+
+        self.rank, self.world = world()
+        if self.world > 8:
+            raise ValueError("PeerLink covers one box (<= 8 GPUs)")
+        self.device = torch.device(device)
+        self.stride = (int(n_small) + 31) // 32 * 32
+        grad_bytes = (rows * feat_dim * 4 + 255) // 256 * 256
+        slots_bytes = (max(self.world, 1) * self.stride * 4 + 255) // 256 * 256
+        self._off = {"grad0": 0, "grad1": grad_bytes, "slots": 2 * grad_bytes, "flags": 2 * grad_bytes + slots_bytes}
+        total = 2 * grad_bytes + slots_bytes + 256
+        lib = _lib.load()
+        # one zero-filled cudaMalloc allocation owned by the library (clid_peer_alloc): its base pointer and IPC handle
+        # are exact (a block of torch's caching allocator has neither), torch sees it through the CUDA array interface
+        base_ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.clid_peer_alloc(total, C.byref(base_ptr), handle), "clid_peer_alloc")
+        self._base = int(base_ptr.value)
+
+        class _Raw:  # zero-copy torch view of the allocation
+            __cuda_array_interface__ = {"shape": (total,), "typestr": "|u1", "data": (self._base, False), "version": 3}
+
+        self.buf = torch.as_tensor(_Raw(), device=self.device)
+        assert self.buf.data_ptr() == self._base
+
+        def view(name, nbytes, dtype, shape):
+            o = self._off[name]
+            return self.buf[o:o + nbytes].view(dtype).view(shape)
+
+        self.grad = [view("grad0", rows * feat_dim * 4, torch.float32, (rows, feat_dim)),
+                     view("grad1", rows * feat_dim * 4, torch.float32, (rows, feat_dim))]
+        self.slots = view("slots", max(self.world, 1) * self.stride * 4, torch.float32, (max(self.world, 1), self.stride))
+        self.flags = view("flags", 64, torch.int32, (16,))
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.error = torch.zeros(1, dtype=torch.int32, device=self.device)
+        torch.cuda.synchronize(self.device)
+        self.base_of = {self.rank: self._base}
+        self._opened = []
+        if self.world > 1:
+            table = [None] * self.world
+            dist.all_gather_object(table, bytes(handle.raw), group=group)
+            with torch.cuda.device(self.device):
+                for r, h in enumerate(table):
+                    if r == self.rank:
+                        continue
+                    ptr = C.c_void_p()
+                    _lib.check(lib.clid_ipc_open(h, C.byref(ptr)), f"clid_ipc_open (rank {r})")
+                    self._opened.append(ptr)
+                    self.base_of[r] = int(ptr.value)
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=group)  # nobody publishes before everybody has opened everything
+
+    def ptr(self, rank: int, name: str) -> int:
+        """Device address of buffer `name` ('grad0' | 'grad1' | 'slots' | 'flags') of `rank`, valid on this device."""
+        return self.base_of[rank] + self._off[name]
+
+    def grad_ptr(self, rank: int, parity: int) -> int:
+        import os
+
+        if os.environ.get("CLID_PEER_DEBUG_SELF") == "1":  # developer knob: exercise the kernel path without NVLink
+            rank = self.rank
+        return self.ptr(rank, "grad1" if parity else "grad0")
+
+    def args(self, n0: int, n1: int):
+        from . import _lib
+
+        a = _lib.ClidPeerArgs()
+        for r in range(self.world):
+            a.slots_of[r] = self.ptr(r, "slots")
+            a.flags_of[r] = self.ptr(r, "flags")
+        a.epoch, a.error = self.epoch.data_ptr(), self.error.data_ptr()
+        a.rank, a.world, a.n0, a.n1, a.stride, a.timeout_ms = self.rank, self.world, int(n0), int(n1), self.stride, 2000
+        return a
+
+    def check(self) -> None:
+        if int(self.error.item()) != 0:
+            raise RuntimeError("clid_peer_reduce timed out waiting for a peer rank (a rank died or the ranks ran a "
+                               "different number of steps)")

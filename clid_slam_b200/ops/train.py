@@ -137,6 +137,9 @@ class FusedTrainer:
         self._side_stream = None
         self._pending_reduce = None
         self._loop_bufs = None      # [bs] batch scratch of run_loop
+        # multi-GPU over peer memory (attach_peers): dist.PeerLink + the slab geometry of this rank
+        self.peer = None
+        self._peer_geom = None
 
     # ------------------------------------------------------------------
     def _shifted(self, x: torch.Tensor, eik_index: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -152,7 +155,8 @@ class FusedTrainer:
 
     def iteration(self, x: torch.Tensor, label: torch.Tensor, ts: Optional[torch.Tensor], weight: torch.Tensor,
                   apply_step: bool = True, n_global: int = 0, nd_global: int = 0, sync: bool = False,
-                  shards=None, eik_index: Optional[torch.Tensor] = None, exchange: bool = True):
+                  shards=None, eik_index: Optional[torch.Tensor] = None, exchange: bool = True,
+                  parity: Optional[int] = None):
         """One mapping iteration on the batch.  With apply_step=False the optimiser step is left to
         a later `adam_step()` call, so the accumulated gradients can be inspected (tests).
 
@@ -173,6 +177,18 @@ class FusedTrainer:
         # the one-kernel numerical mode evaluates the x[::10] subset inside the warp tiles; explicit
         # subsets (eik_index, sharded batches) and other decimations take the three-launch path
         one_kernel_ok = (not numerical) or (int(cfg.gradient_decimation) == 10 and eik_index is None)
+        if self.peer is not None:
+            # peer-memory step: the fused kernel exchanges the band gradients itself, one kernel pair all-reduces the rest
+            if not (self.single_kernel and one_kernel_ok):
+                raise NotImplementedError("the peer-memory step runs the one-kernel iteration")
+            self._parity = int(self.step % 2 if parity is None else parity)
+            self.feat_grad = self.peer.grad[self._parity]
+            loss = self._iteration_single_kernel(x, label, ts, weight, n_global, nd_global, numerical, defer_reduce=False)
+            self._peer_all_reduce(loss)
+            self.losses.append(loss)
+            if apply_step:
+                self.adam_step()
+            return loss
         if self.single_kernel and one_kernel_ok:
             defer = bool(apply_step and exchange and shards is None and not sync and self._want_overlap())
             loss = self._iteration_single_kernel(x, label, ts, weight, n_global, nd_global, numerical, defer_reduce=defer)
@@ -275,6 +291,8 @@ class FusedTrainer:
         a.touched = None if self.touched is None else self.touched.data_ptr()
         a.dec_grad = None if self.dec_grad is None else self.dec_grad.data_ptr()
         a.loss = loss.data_ptr()
+        if self.peer is not None:
+            self._peer_train_args(a, self._parity)
         if self.dec_grad is not None and self.use_scratch:
             need = int(lib.clid_train_fused_scratch_bytes(n, a.numerical))
             if self._scratch is None or self._scratch.numel() < need:
@@ -298,6 +316,53 @@ class FusedTrainer:
             if not defer_reduce:
                 self._reduce_pending()
         return loss
+
+    # ------------------------------------------------------------------ multi-GPU over peer memory
+    def attach_peers(self, shards, group=None) -> None:
+        """Spatially sharded training without NCCL on the data path (dist.PeerLink): the fused kernel adds
+        boundary-band gradients straight into the slab neighbours' tables over NVLink, [decoder gradients | loss]
+        are all-reduced by a one-shot peer-memory kernel pair, everything stays inside the step's CUDA graph."""
+        from .. import dist as _dist
+
+        rank, world = _dist.world()
+        if not shards.pairwise:
+            raise ValueError("slabs narrower than two bands: a band row would have three contributors")
+        n_small = (self.dec_grad.numel() if self.dec_grad is not None else 0) + 3
+        self.peer = _dist.PeerLink(self.rows, self.feat_grad.shape[1], n_small, self.device, group=group)
+        b = shards.boundaries.tolist()
+        reach_band = shards.band
+        lo = (b[rank - 1] - reach_band, b[rank - 1] + reach_band - 1) if rank > 0 else None
+        hi = (b[rank] - reach_band, b[rank] + reach_band - 1) if rank < world - 1 else None
+        self._peer_geom = (int(shards.axis), lo, hi, rank, world)
+        if self.touched is not None:  # band rows may receive gradient from the neighbour only
+            left, right = shards.neighbour_rows(rank)
+            for rows in (left, right):
+                if rows is not None and rows.numel():
+                    self.touched[rows] = 1
+        self.feat_grad = self.peer.grad[0]
+
+    def _peer_train_args(self, a, parity: int) -> None:
+        axis, lo, hi, rank, world = self._peer_geom
+        a.gfeat = self.peer.grad[parity].data_ptr()
+        a.peer_axis = axis
+        if lo is not None:
+            a.peer_grad[0] = self.peer.grad_ptr(rank - 1, parity)
+            a.peer_band[0], a.peer_band[1] = lo
+        if hi is not None:
+            a.peer_grad[1] = self.peer.grad_ptr(rank + 1, parity)
+            a.peer_band[2], a.peer_band[3] = hi
+
+    def _peer_all_reduce(self, loss: torch.Tensor) -> None:
+        """[decoder gradients | loss] summed over ranks through peer memory (also the barrier after which every
+        neighbour's remote gradient adds of this step are visible)."""
+        n0 = self.dec_grad.numel() if self.dec_grad is not None else 0
+        pa = self.peer.args(n0, 3)
+        dg = None if self.dec_grad is None else self.dec_grad.data_ptr()
+        stream = _lib.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.clid_peer_publish(C.byref(pa), dg, loss.data_ptr(), stream), "clid_peer_publish")
+            _lib.check(self.lib.clid_peer_reduce(C.byref(pa), dg, loss.data_ptr(), stream), "clid_peer_reduce")
+        self.launches += 2
 
     def ensure_step_state(self) -> None:
         """Device-resident optimiser step counter {step, step_size, bc2_sqrt, pad} (ClidAdamArgs.step_state)."""
@@ -576,7 +641,7 @@ class StepPipeline:
             raise RuntimeError("StepPipeline must own the optimiser from its first step")
         self.trainer, self.n = trainer, int(n)
         dev = trainer.device
-        if shards is None and trainer.touched is not None and 2 * n * int(trainer.cfg.query_nn_k) >= trainer.rows:
+        if shards is None and trainer.peer is None and trainer.touched is not None and 2 * n * int(trainer.cfg.query_nn_k) >= trainer.rows:
             trainer.touched = None  # a replayed graph cannot switch later: large batches run dense from the start
         self.device = dev
         trainer.ensure_step_state()
@@ -587,6 +652,8 @@ class StepPipeline:
                                       "sharding (dense feature-gradient all-reduce) runs call by call")
         self.shards = shards
         f32 = dict(dtype=torch.float32, device=dev)
+        if trainer.peer is not None and buffers is not None and len(buffers) % 2 != 0:
+            raise ValueError("the peer-memory step alternates two gradient tables: use an even number of input buffers")
         if buffers is not None:
             self.bufs = [tuple(b) for b in buffers]
             for x, label, weight, ts in self.bufs:
@@ -657,15 +724,18 @@ class StepPipeline:
     def _iteration(self, k, n_global, nd_global):
         x, label, weight, ts = self.bufs[k]
         if self.shards is None:
-            return self.trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global)
+            # peer-memory multi-GPU step: buffer k always runs with gradient table k % 2 (the buffers rotate in order)
+            parity = k % 2 if self.trainer.peer is not None else None
+            return self.trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global, parity=parity)
         return self.trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global, shards=self.shards,
                                       exchange=False)
 
     def _snapshot(self):
         t = self.trainer
         npm = t.npm
-        tensors = [npm.local_geo_features.data, npm.local_point_certainties, npm.local_point_ts_update, t.feat_grad, t.feat_m,
-                   t.feat_v, t.step_state] + [p.data for p in t.dec_tensors if p is not None]
+        grads = list(t.peer.grad) if t.peer is not None else [t.feat_grad]
+        tensors = [npm.local_geo_features.data, npm.local_point_certainties, npm.local_point_ts_update, t.feat_m,
+                   t.feat_v, t.step_state] + grads + [p.data for p in t.dec_tensors if p is not None]
         for extra in (t.touched, t.dec_grad, t.dec_m, t.dec_v):
             if extra is not None:
                 tensors.append(extra)
@@ -714,4 +784,5 @@ class StepPipeline:
     @property
     def launches_per_step(self) -> int:
         # fused kernel + Adam advance + Adam on the features [+ decoder-gradient reduction + Adam on the decoder]
-        return 3 + (2 if self.trainer.dec_grad is not None else 0)
+        # [+ peer publish + peer reduce]
+        return 3 + (2 if self.trainer.dec_grad is not None else 0) + (2 if self.trainer.peer is not None else 0)

@@ -252,6 +252,15 @@ typedef struct ClidTrainFusedArgs {
   float* dec_grad;       /* flat [W0,b0,wout,bout] += or NULL (frozen decoder) */
   float* loss;           /* [3] += total, bce, eikonal */
   float* sdf_out;        /* [n] or NULL */
+  /* Multi-GPU, samples and neural points partitioned into slabs along one axis (clid_slam_b200/dist.py): the
+   * feature rows within the boundary band a rank shares with a slab neighbour must receive the gradients of BOTH
+   * ranks.  With peer_grad set the kernel adds every contribution to such a row a second time, straight into the
+   * neighbour's gfeat through its peer mapping (red.global.add.v4.f32 over NVLink) -- no pack / send / recv / unpack
+   * pass, the exchange rides inside the compute kernel. */
+  float* peer_grad[2];   /* gfeat of the lower / upper slab neighbour, peer-mapped device pointers, or NULL         */
+  int32_t peer_axis;     /* 0..2: axis the slabs are cut along                                                   */
+  int32_t peer_band[4];  /* inclusive cell ranges [lo0, lo1] / [hi0, hi1] of the band shared with the lower /
+                            upper neighbour, in voxel cells floor(p[axis] / resolution) of the NEURAL POINT       */
   void* scratch;         /* clid_train_fused_scratch_bytes(n, numerical) bytes of device scratch, or NULL.
                             With it every evaluated point writes its 64-byte decoder-gradient row
                             [delta z + s tau ; delta | activation bits] there and the caller reduces the
@@ -346,6 +355,40 @@ typedef struct ClidMappingArgs {
 } ClidMappingArgs;
 CLID_API int clid_mapping_run(const ClidMap* map, const ClidDecoder* dec, const ClidMappingArgs* args,
                               uint32_t flags, clid_stream_t stream);
+
+/* ---- one-shot all-reduce of [decoder gradients | loss] over peer memory (multi-GPU, one box) ---------------
+ * Every rank owns `slots` [world][n_floats] and `flags` [world] (uint32, zero-initialised) in peer-accessible
+ * device memory.  clid_peer_publish copies the rank's [src0 | src1] into slot `rank` of EVERY rank (its own
+ * included) through the peer mappings, then stores a new epoch into flag `rank` of every rank (system-scope
+ * release).  clid_peer_reduce waits until all `world` flags of the local rank carry the current epoch -- which also
+ * orders the peers' remote gradient adds of clid_train_fused before whatever follows -- and writes the sum over
+ * ranks, taken in rank order so every rank gets bit-identical values, back into dst0 / dst1.  Both are single
+ * kernel launches that can be captured in a CUDA graph: the epoch lives in `epoch` (device, uint32, zero-initialised,
+ * local).  No NCCL, no host involvement. */
+typedef struct ClidPeerArgs {
+  float* slots_of[8];       /* slots base of every rank (peer-mapped; own = local pointer)                        */
+  uint32_t* flags_of[8];    /* flags base of every rank                                                           */
+  uint32_t* epoch;          /* local                                                                              */
+  int32_t rank, world;      /* world <= 8                                                                         */
+  int32_t n0, n1;           /* floats of src0 / src1 (n0 + n1 <= slot stride)                                      */
+  int32_t stride;           /* floats per slot                                                                    */
+  int32_t timeout_ms;       /* clid_peer_reduce gives up waiting after this long (0 = 2000) and sets *error       */
+  int32_t* error;           /* local device int: set to 1 on a wait time-out (a peer died); may be NULL           */
+} ClidPeerArgs;
+/* cudaDeviceEnablePeerAccess(peer_device) for the current device (idempotent): the kernels of this device may then
+ * store / red into memory of peer_device mapped into this process (CUDA IPC). */
+CLID_API int clid_enable_peer_access(int32_t peer_device);
+/* cudaIpcOpenMemHandle / cudaIpcCloseMemHandle with the CURRENT device as the importing device (lazy peer access to
+ * the exporting one): handle64 = the 64-byte cudaIpcMemHandle_t of another process's allocation; *base_out = the base
+ * of its mapping in this process. */
+/* The one place where the library owns device memory: a zero-filled cudaMalloc allocation that can be exported to
+ * the other ranks of the box (its base pointer and its 64-byte cudaIpcMemHandle_t), and its release. */
+CLID_API int clid_peer_alloc(size_t bytes, void** ptr_out, void* handle64_out);
+CLID_API int clid_peer_free(void* ptr);
+CLID_API int clid_ipc_open(const void* handle64, void** base_out);
+CLID_API int clid_ipc_close(void* base);
+CLID_API int clid_peer_publish(const ClidPeerArgs* args, const float* src0, const float* src1, clid_stream_t stream);
+CLID_API int clid_peer_reduce(const ClidPeerArgs* args, float* dst0, float* dst1, clid_stream_t stream);
 
 /* NeuralPoints.radius_neighborhood_search (model/neural_points.py:971-1030): the raw candidate
  * table.  dist2_out [n,kc] f32, idx_out [n,kc] int64 global ids (-1 invalid).  Only

@@ -1,6 +1,7 @@
-"""Multi-GPU check (torchrun, N >= 2): the neighbour send/recv exchange of the boundary-band gradients
-gives the same training trajectory as the flat all-reduce over all bands, and both agree with a
-single-process run on the union batch (up to fp32 summation order)."""
+"""Multi-GPU check (torchrun, N >= 2): the peer-memory step (band gradients added into the slab neighbour's table
+by the fused kernel, one-shot peer all-reduce of [decoder grads | loss]), the NCCL neighbour send/recv exchange
+and the flat all-reduce over all bands give the same training trajectory, and all agree with a single-process
+run on the union batch (up to fp32 summation order)."""
 import copy, os, sys
 import torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -30,12 +31,14 @@ def build():
 
 n = 16384
 results = {}
-for mode in ("p2p", "flat", "single"):
+for mode in ("peer", "p2p", "flat", "single"):
     cfg, dec, npm = build()
     shards = SpatialShards(npm.local_neural_points, cfg.voxel_size_m, reach=cfg.num_nei_cells, world_size=world)
     if mode == "flat":
         shards.pairwise = False
     trainer = FusedTrainer(cfg, npm, dec)
+    if mode == "peer":
+        trainer.attach_peers(shards)
     losses = []
     for it in range(6):
         # identical global batch on every rank, split by slab ownership
@@ -45,13 +48,16 @@ for mode in ("p2p", "flat", "single"):
             loss = trainer.iteration(x, label, ts, weight)
         else:
             mine = shards.owner_of(x) == rank
-            loss = trainer.iteration(x[mine], label[mine], ts[mine], weight[mine], n_global=n * world, shards=shards)
+            loss = trainer.iteration(x[mine], label[mine], ts[mine], weight[mine], n_global=n * world,
+                                     shards=None if mode == "peer" else shards)
         losses.append(loss.clone())
     feats = npm.local_geo_features.data.clone()
     if mode != "single":
         shards.gather_features(feats, rank)
     results[mode] = (torch.stack(losses), feats, torch.cat([p.data.flatten() for p in dec.flat_parameters()]))
-    assert mode == "single" or trainer.neighbour_exchange(shards) is not None or mode == "flat"
+    if mode == "peer":
+        trainer.peer.check()
+    assert mode in ("single", "flat", "peer") or trainer.neighbour_exchange(shards) is not None
 
 torch.cuda.synchronize()
 if rank == 0:
@@ -63,6 +69,8 @@ if rank == 0:
         bad = (df > 1e-5 + 1e-3 * fb.abs()).double().mean().item()
         print(f"{what}: max rel loss diff {dl:.2e}; features max abs diff {df.max().item():.2e}, outside 1e-3 rel + 1e-5: {bad * 100:.3f} %; "
               f"decoder max abs diff {dd:.2e}")
+    cmp("peer", "single", f"N={world} peer-memory step vs single process")
+    cmp("peer", "p2p", f"N={world} peer-memory step vs NCCL neighbour exchange")
     cmp("p2p", "flat", f"N={world} neighbour exchange vs flat all-reduce")
     cmp("p2p", "single", f"N={world} neighbour exchange vs single process")
     cmp("flat", "single", f"N={world} flat all-reduce vs single process")
