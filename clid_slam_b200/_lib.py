@@ -156,6 +156,9 @@ _SIGNATURES = [
     ("clid_ipc_close", C.c_int, [C.c_void_p]),
     ("clid_peer_publish", C.c_int, [C.POINTER(ClidPeerArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
     ("clid_peer_reduce", C.c_int, [C.POINTER(ClidPeerArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("clid_registration_terms", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.c_int32, C.c_float, C.c_float,
+      C.c_void_p, C.c_void_p, C.c_void_p]),
     ("clid_draw_batch", C.c_int,
      [C.POINTER(ClidReplayPool), C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
       C.c_void_p, C.c_void_p]),

@@ -412,6 +412,24 @@ int clid_peer_reduce(const ClidPeerArgs* a, float* dst0, float* dst1, clid_strea
   return CLID_OK;
 }
 
+int clid_registration_terms(const float* pc_imu, const float* sdf, const float* grad, const int32_t* nn_count, int64_t n,
+                            const float* rot9, int32_t min_nn, float min_grad, float max_grad, double* out28,
+                            uint8_t* valid_out, clid_stream_t stream) {
+  if (n < 0) return set_error(CLID_EINVAL, "n = %lld", (long long)n);
+  if (n == 0) return CLID_OK;
+  if (!pc_imu || !sdf || !grad || !nn_count || !rot9 || !out28) return set_error(CLID_EINVAL, "a required pointer is NULL");
+  RegParams p;
+  p.pc_imu = pc_imu; p.sdf = sdf; p.grad = grad; p.nn_count = nn_count; p.n = n;
+  for (int i = 0; i < 9; ++i) p.rot[i] = rot9[i];  // HOST array: nine floats, row-major
+  p.min_nn = min_nn; p.min_grad = min_grad; p.max_grad = max_grad; p.out = out28; p.valid_out = valid_out;
+  int grid = elementwise_grid(n, 256);
+  if (grid > 592) grid = 592;
+  registration_terms_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "registration_terms_kernel launch");
+  return CLID_OK;
+}
+
 static int check_pool(const ClidReplayPool* pool, int64_t n) {
   if (!pool->coord || !pool->sdf_label || pool->count <= 0) return set_error(CLID_EINVAL, "replay pool is empty or NULL");
   if (pool->bs_new < 0 || pool->bs_new > n) return set_error(CLID_EINVAL, "bs_new %d outside 0..n", pool->bs_new);

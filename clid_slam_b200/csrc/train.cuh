@@ -420,6 +420,73 @@ __global__ void __launch_bounds__(256) draw_batch_kernel(const DrawParams p) {
   }
 }
 
+// registration epilogue (include/clid_sdf.h clid_registration_terms)
+struct RegParams {
+  const float* pc_imu;
+  const float* sdf;
+  const float* grad;
+  const int32_t* nn_count;
+  int64_t n;
+  float rot[9];
+  int32_t min_nn;
+  float min_grad, max_grad;
+  double* out;
+  uint8_t* valid_out;
+};
+
+__global__ void __launch_bounds__(256) registration_terms_kernel(const RegParams p) {
+  double acc[28];
+#pragma unroll
+  for (int i = 0; i < 28; ++i) acc[i] = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gx = p.grad[3 * i], gy = p.grad[3 * i + 1], gz = p.grad[3 * i + 2];
+    const float gn = sqrtf(gx * gx + gy * gy + gz * gz);
+    const bool valid = p.nn_count[i] >= p.min_nn && gn < p.max_grad && gn > p.min_grad;
+    if (p.valid_out) p.valid_out[i] = valid ? 1 : 0;
+    if (!valid) continue;
+    const float x = p.pc_imu[3 * i], y = p.pc_imu[3 * i + 1], z = p.pc_imu[3 * i + 2];
+    // A = R [p]x ; [p]x = [[0,-z,y],[z,0,-x],[-y,x,0]]  ->  column c of A = R * column c of [p]x
+    const float* R = p.rot;
+    float h[6];
+    {
+      float u0 = gx * R[0] + gy * R[3] + gz * R[6];  // g^T R
+      float u1 = gx * R[1] + gy * R[4] + gz * R[7];
+      float u2 = gx * R[2] + gy * R[5] + gz * R[8];
+      h[0] = -(u1 * z - u2 * y);   // -(g^T R [p]x)_0 = -(u . col0), col0 = (0, z, -y)
+      h[1] = -(-u0 * z + u2 * x);  // col1 = (-z, 0, x)
+      h[2] = -(u0 * y - u1 * x);   // col2 = (y, -x, 0)
+    }
+    h[3] = gx; h[4] = gy; h[5] = gz;
+    const double s = (double)p.sdf[i];
+    const double an = (double)gn - 1.0;
+    const double w = (1.0 / (1.0 + an * an)) * (0.4 / (0.4 + s * s)) * 1000.0;
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const double wa = w * (double)h[a];
+#pragma unroll
+      for (int b = a; b < 6; ++b) acc[k++] += wa * (double)h[b];
+      acc[21 + a] += wa * s;
+    }
+    acc[27] += 1.0;
+  }
+  __shared__ double red[8][28];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 28; ++i) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 28) {
+    double v = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][threadIdx.x];
+    if (v != 0.0) atomicAdd(p.out + threadIdx.x, v);
+  }
+}
+
 __global__ void copy3_kernel(const float* src, float* dst) {
   if (threadIdx.x < 3) dst[threadIdx.x] = src[threadIdx.x];
 }

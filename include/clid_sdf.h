@@ -315,6 +315,21 @@ CLID_API int clid_adam_step(const ClidAdamArgs* args, clid_stream_t stream);
  * step >= 0).  For callers that split one optimiser step over several clid_adam_step(step < 0) launches. */
 CLID_API int clid_adam_advance(void* step_state, float lr, float beta1, float beta2, clid_stream_t stream);
 
+/* ---- registration epilogue (utils/error_state_iekf.py:176-264 h_model, :303-309 update_iterated) ---------- */
+
+/* What IEKFOM.update_iterated needs from h_model, reduced on the device: with, per scan point i,
+ *   valid_i = nn_count_i >= min_nn  and  min_grad < |g_i| < max_grad          (:230-247; sdf_std == 0 for weighted_first)
+ *   h_i     = [ -(g_i^T R [p_i]x) , g_i ]   (fp32, like H[:, 0:3] / H[:, 3:6], :250-255; p_i in the imu frame)
+ *   w_i     = 1000 / (1 + (|g_i| - 1)^2) * 0.4 / (0.4 + sdf_i^2)              (fp64, R_inv, :258-262)
+ * out[0..20] = upper triangle (row-major) of sum_i w_i h_i h_i^T  (= H^T R^-1 H, its 6 x 6 non-zero block),
+ * out[21..26] = sum_i w_i h_i sdf_i (= H^T R^-1 z), out[27] = number of valid points, all accumulated in fp64 (+=;
+ * the caller zero-fills).  sdf / grad / nn_count are the outputs of clid_query_forward at the transformed points;
+ * valid_out [n] (uint8, optional) receives the mask; rot9 is a HOST array (row-major R).  One launch instead of ~25 eager ops and a boolean-mask
+ * compaction (host synchronisation) per registration iteration. */
+CLID_API int clid_registration_terms(const float* pc_imu, const float* sdf, const float* grad, const int32_t* nn_count,
+                                     int64_t n, const float* rot9, int32_t min_nn, float min_grad, float max_grad,
+                                     double* out28, uint8_t* valid_out, clid_stream_t stream);
+
 /* ---- the mapping loop (utils/mapper.py:473-523 get_batch + :642-836 loop body) ----------------------- */
 
 /* Replay pool of the mapper (utils/mapper.py:84-97, 297-333): device pointers, borrowed. */
