@@ -143,6 +143,7 @@ _SIGNATURES = [
      [C.POINTER(ClidMap), C.POINTER(ClidDecoder), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
       C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("clid_train_fused_scratch_bytes", C.c_size_t, [C.c_int64, C.c_int32]),
+    ("clid_train_fused_scratch_bytes_for", C.c_size_t, [C.POINTER(ClidDecoder), C.c_int64, C.c_int32]),
     ("clid_train_fused", C.c_int,
      [C.POINTER(ClidMap), C.POINTER(ClidDecoder), C.POINTER(ClidTrainFusedArgs), C.c_uint32, C.c_void_p]),
     ("clid_decoder_grad_reduce", C.c_int,

@@ -13,6 +13,7 @@
 #include "train.cuh"
 #include "decoder_grad.cuh"
 #include "peer.cuh"
+#include "mlp_l2.cuh"
 #include "train_fused.cuh"
 
 namespace clid {
@@ -210,11 +211,20 @@ int clid_train_backward(const ClidMap* map, const ClidDecoder* dec, const float*
   return dispatch_train_backward(p, static_cast<cudaStream_t>(stream));
 }
 
+static int64_t fused_row_slots(int64_t n, int32_t numerical) {  // 32 evaluation slots per tile
+  const int64_t per_tile = numerical ? kNumTileSamples : 32;
+  return (n + per_tile - 1) / per_tile * 32;
+}
+
 size_t clid_train_fused_scratch_bytes(int64_t n, int32_t numerical) {
   if (n <= 0) return 0;
-  const int64_t per_tile = numerical ? kNumTileSamples : 32;
-  const int64_t tiles = (n + per_tile - 1) / per_tile;
-  return (size_t)tiles * 32 * kFoldRow * sizeof(float);
+  return (size_t)fused_row_slots(n, numerical) * kFoldRow * sizeof(float);
+}
+
+size_t clid_train_fused_scratch_bytes_for(const ClidDecoder* dec, int64_t n, int32_t numerical) {
+  if (n <= 0 || !dec) return 0;
+  const int row = dec->levels == 2 ? L2Row<32>::kFloats : kFoldRow;
+  return (size_t)fused_row_slots(n, numerical) * row * sizeof(float);
 }
 
 int clid_train_fused(const ClidMap* map, const ClidDecoder* dec, const ClidTrainFusedArgs* a, uint32_t flags,
@@ -249,9 +259,9 @@ int clid_train_fused(const ClidMap* map, const ClidDecoder* dec, const ClidTrain
     if (!(a->num_eps > 0.f)) return set_error(CLID_EINVAL, "numerical mode needs num_eps > 0");
     p.num_eps = a->num_eps;
   }
-  const bool have_scratch = a->scratch && a->scratch_bytes >= clid_train_fused_scratch_bytes(a->n, a->numerical);
+  const bool have_scratch = a->scratch && a->scratch_bytes >= clid_train_fused_scratch_bytes_for(dec, a->n, a->numerical);
   if (a->scratch && (reinterpret_cast<uintptr_t>(a->scratch) & 15u)) return set_error(CLID_EINVAL, "scratch must be 16-byte aligned");
-  if (p.dec_grad && have_scratch) {
+  if ((p.dec_grad || dec->levels == 2) && have_scratch) {
     // decoder-gradient rows go to scratch; a dense reduction kernel folds them afterwards
     p.fold_rows = static_cast<float*>(a->scratch);
   }
@@ -266,6 +276,13 @@ int clid_decoder_grad_reduce(const ClidDecoder* dec, const void* scratch, int64_
   if (n == 0) return CLID_OK;
   if (!scratch || (reinterpret_cast<uintptr_t>(scratch) & 15u)) return set_error(CLID_EINVAL, "scratch is NULL or misaligned");
   if (int rc = check_decoder(dec)) return rc;
+  if (dec->levels == 2) {
+    DecoderGradL2Params g2;
+    memset(&g2, 0, sizeof(g2));
+    g2.dec = *dec; g2.rows = static_cast<const float*>(scratch); g2.dec_grad = dec_grad; g2.flags = flags;
+    g2.n_rows = fused_row_slots(n, numerical);
+    return launch_decoder_grad_l2(g2, static_cast<cudaStream_t>(stream));
+  }
   DecoderGradParams g;
   memset(&g, 0, sizeof(g));
   g.dec = *dec; g.rows = static_cast<const float*>(scratch); g.dec_grad = dec_grad; g.flags = flags;

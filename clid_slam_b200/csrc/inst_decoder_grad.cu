@@ -1,6 +1,7 @@
 // decoder_grad_kernel instantiations and launch geometry.
 #include "launch.h"
 #include "decoder_grad.cuh"
+#include "mlp_l2.cuh"
 
 namespace clid {
 
@@ -19,6 +20,20 @@ static int launch_decoder_grad_t(const DecoderGradParams& p, int sm_count, cudaS
   kern<<<grid, DgSmem<H>::kWarps * 32, DgSmem<H>::kBytes, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "decoder_grad_kernel launch");
+  return CLID_OK;
+}
+
+int launch_decoder_grad_l2(const DecoderGradL2Params& p, cudaStream_t stream) {
+  DeviceInfo info;
+  if (int rc = device_info(&info)) return rc;
+  if (p.n_rows == 0) return CLID_OK;
+  if (p.dec.hidden_dim != 32 || p.dec.levels != 2)
+    return set_error(CLID_EUNSUPPORTED, "decoder_grad_l2_kernel is compiled for 32 x 2 decoders; got %d x %d", p.dec.hidden_dim, p.dec.levels);
+  const int64_t want = (p.n_rows + 7) / 8;
+  const int grid = (int)(want < info.sm_count ? want : info.sm_count);
+  decoder_grad_l2_kernel<32><<<grid, 256, 0, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "decoder_grad_l2_kernel launch");
   return CLID_OK;
 }
 

@@ -14,6 +14,7 @@ struct TrainBwdParams;
 struct TrainFusedParams;
 struct QueryBwdParams;
 struct DecoderGradParams;
+struct DecoderGradL2Params;
 
 int set_error(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
@@ -39,5 +40,6 @@ int dispatch_train_fused_hashed(const TrainFusedParams& p, cudaStream_t stream);
 
 // inst_decoder_grad.cu
 int launch_decoder_grad(const DecoderGradParams& p, cudaStream_t stream);
+int launch_decoder_grad_l2(const DecoderGradL2Params& p, cudaStream_t stream);
 
 }  // namespace clid

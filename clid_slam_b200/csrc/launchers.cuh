@@ -54,14 +54,14 @@ static int dispatch_query_t(const QueryParams& p, bool has_dec, cudaStream_t str
                    "use the unfused query + torch decoder path", H, L);
 }
 
-template <int H, int K, int kSearch, bool kNumerical, bool kFoldOut>
+template <int H, int L, int K, int kSearch, bool kNumerical, bool kFoldOut>
 static int launch_train_fused(const TrainFusedParams& p, cudaStream_t stream) {
   DeviceInfo info;
   if (int rc = device_info(&info)) return rc;
   constexpr int kWarps = kFusedThreads / 32;
-  const size_t smem = (size_t)(MlpLayout<H, 1>::kFloats + search_smem_floats<kSearch>() +
+  const size_t smem = (size_t)(MlpLayout<H, L>::kFloats + search_smem_floats<kSearch>() +
                                (kFoldOut ? 0 : kWarps * 32 * kInPad + kWarps * 32 * (H / 32) + kWarps * H * kInPad)) * sizeof(float);
-  auto kern = train_fused_l1_kernel<H, K, kSearch, kNumerical, kFoldOut>;
+  auto kern = train_fused_kernel<H, L, K, kSearch, kNumerical, kFoldOut>;
   static thread_local int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {
     if (smem > 48 * 1024) {
@@ -79,21 +79,27 @@ static int launch_train_fused(const TrainFusedParams& p, cudaStream_t stream) {
   int grid = (int)(want < cap ? want : cap);
   kern<<<grid, kFusedThreads, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return cuda_fail(e, "train_fused_l1_kernel launch");
+  if (e != cudaSuccess) return cuda_fail(e, "train_fused_kernel launch");
   return CLID_OK;
 }
 
 template <int kSearch>
 static int dispatch_train_fused_t(const TrainFusedParams& p, cudaStream_t stream) {
   const int H = p.dec.hidden_dim;
-  if (p.dec.levels != 1 || (H != 32 && H != 64 && H != 128))
-    return set_error(CLID_EUNSUPPORTED, "fused training is compiled for one hidden level with H in {32,64,128}; got %d x %d",
-                     H, p.dec.levels);
   if (p.map.knn > 6) return set_error(CLID_EUNSUPPORTED, "fused training is compiled for query_nn_k <= 6");
   const bool num = p.num_eps > 0.f;  // set by clid_train_fused only in numerical mode
+  if (p.dec.levels == 2 && H == 32) {
+    // two hidden levels: the decoder gradient always leaves the kernel as rows (a frozen decoder still gets its scratch:
+    // the rows park h1 / h2 between the forward and the finish)
+    if (!p.fold_rows) return set_error(CLID_EINVAL, "a two-level decoder needs ClidTrainFusedArgs.scratch");
+    return num ? launch_train_fused<32, 2, 6, kSearch, true, true>(p, stream) : launch_train_fused<32, 2, 6, kSearch, false, true>(p, stream);
+  }
+  if (p.dec.levels != 1 || (H != 32 && H != 64 && H != 128))
+    return set_error(CLID_EUNSUPPORTED, "fused training is compiled for decoders 32x1, 64x1, 128x1 and 32x2; got %d x %d",
+                     H, p.dec.levels);
 #define CLID_FUSED(HH) \
-  (p.fold_rows ? (num ? launch_train_fused<HH, 6, kSearch, true, true>(p, stream) : launch_train_fused<HH, 6, kSearch, false, true>(p, stream)) \
-               : (num ? launch_train_fused<HH, 6, kSearch, true, false>(p, stream) : launch_train_fused<HH, 6, kSearch, false, false>(p, stream)))
+  (p.fold_rows ? (num ? launch_train_fused<HH, 1, 6, kSearch, true, true>(p, stream) : launch_train_fused<HH, 1, 6, kSearch, false, true>(p, stream)) \
+               : (num ? launch_train_fused<HH, 1, 6, kSearch, true, false>(p, stream) : launch_train_fused<HH, 1, 6, kSearch, false, false>(p, stream)))
   if (H == 64) return CLID_FUSED(64);
   if (H == 32) return CLID_FUSED(32);
   return CLID_FUSED(128);

@@ -23,6 +23,7 @@
 #include "query_bwd.cuh"
 #include "query_fwd.cuh"
 #include "train.cuh"
+#include "mlp_l2.cuh"
 
 namespace clid {
 
@@ -69,9 +70,12 @@ constexpr int kNumTileSamples = 20;  // base samples per warp tile in numerical 
 // its 64-byte row [c'(12) | activation bits | pad] to global memory and decoder_grad_kernel
 // (tile_kernel.cuh) reduces all rows afterwards.  The warp-serial fold costs ~28 % of this kernel's
 // time (profiles/), as a separate dense reduction it is a few microseconds.
-template <int H, int K, int kSearch, bool kNumerical, bool kFoldOut>
-__global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fused_l1_kernel(const __grid_constant__ TrainFusedParams p) {
-  using Lay = MlpLayout<H, 1>;
+// L: hidden levels of the decoder.  L == 2 (H == 32) always hands its decoder gradient to the reduction kernel as
+// per-sample rows (mlp_l2.cuh); L == 1 can also fold it inside this kernel (kFoldOut false).
+template <int H, int L, int K, int kSearch, bool kNumerical, bool kFoldOut>
+__global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fused_kernel(const __grid_constant__ TrainFusedParams p) {
+  static_assert(L == 1 || (L == 2 && kFoldOut), "two-level decoders write rows for decoder_grad_l2_kernel");
+  using Lay = MlpLayout<H, L>;
   constexpr int kRows = H / 32;
   constexpr int kMaskWords = H / 32;
   constexpr int kWarps = kFusedThreads / 32;
@@ -94,7 +98,7 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
   __shared__ StageBarriers stage;
   stage_barriers_init(stage);
   if constexpr (kBricks) stage_stencil_async(stencil, p.bricks.stencil, stage);
-  stage_decoder_async<H, 1>(sm_dec, p.dec, stage);
+  stage_decoder_async<H, L>(sm_dec, p.dec, stage);
   if constexpr (!kBricks) {
     for (int c = threadIdx.x; c < m.kc; c += blockDim.x) {
       int64_t h = m.neighbor_dx[3 * c] * m.primes[0] + m.neighbor_dx[3 * c + 1] * m.primes[1] +
@@ -175,6 +179,10 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
     int row[K];
     float vx[K], vy[K], vz[K], w[K], u[K];
     float S = 0.f, sdf = 0.f, cbar = 0.f;
+    uint32_t m1_bits = 0u, m2_bits = 0u;  // L == 2: activation patterns of the two hidden levels
+    float stau[kIn];                      // s tau0: the tangent input of the analytic eikonal term
+#pragma unroll
+    for (int i = 0; i < kIn; ++i) stau[i] = 0.f;
     uint32_t peer_bits = 0u;  // two bits per neighbour: its row is shared with the lower (1) / upper (2) slab neighbour
     const bool peers = p.peer_grad[0] != nullptr || p.peer_grad[1] != nullptr;
     float z[kIn], a[kIn];
@@ -249,7 +257,8 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
 
       float out;
       if (!decoder_ready) { mbar_wait(&stage.decoder, 0); decoder_ready = true; }
-      mlp_l1_pairs<H, true>(sm_dec, z, slope, out, a, mask);
+      if constexpr (L == 2) mlp_l2_forward_train<H>(sm_dec, z, slope, out, a, m1_bits, m2_bits, p.fold_rows + (tile * 32 + lane) * L2Row<H>::kFloats);
+      else mlp_l1_pairs<H, true>(sm_dec, z, slope, out, a, mask);
       sdf = out * s;
       if (p.sdf_out && role_variant == 0) p.sdf_out[q] = sdf;
 #pragma unroll
@@ -314,7 +323,7 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
         tau[10] = invS * (rx * P[2] + ry * P[4] + rz * P[5] - dusum * z[10]);
         if (count > 0) { tau[8] += rx; tau[9] += ry; tau[10] += rz; }
 #pragma unroll
-        for (int i = 0; i < kIn; ++i) c[i] = fmaf(delta, z[i], s * tau[i]);
+        for (int i = 0; i < kIn; ++i) { stau[i] = s * tau[i]; c[i] = fmaf(delta, z[i], stau[i]); }
       } else {
 #pragma unroll
         for (int i = 0; i < kIn; ++i) c[i] = delta * z[i];
@@ -351,7 +360,14 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
       }
     }
 
-    if constexpr (kFoldOut) {
+    if constexpr (L == 2) {
+      // ---- two-level decoder: finish this sample's row (tangent products, c1, e2) or clear it
+      if (p.fold_rows) {
+        float* l2row = p.fold_rows + (tile * 32 + lane) * L2Row<H>::kFloats;
+        if (live) mlp_l2_finish_row<H, !kNumerical>(sm_dec, c, stau, c[kIn], slope, m1_bits, m2_bits, l2row);
+        else l2_zero_row<H>(l2row);
+      }
+    } else if constexpr (kFoldOut) {
       // ---- row for the decoder-gradient reduction (dead lanes write zeros: c stays 0 for them)
       if (p.fold_rows) {
         float4* dst = reinterpret_cast<float4*>(p.fold_rows + (tile * 32 + lane) * 16);

@@ -41,8 +41,9 @@ def supported(config, decoder) -> Optional[str]:
         return "SGD optimiser"
     if getattr(config, "ekional_add_to", "all") != "all" and config.ekional_loss_on and config.weight_e > 0:
         return f"ekional_add_to={config.ekional_add_to}"
-    if len(decoder.layers) != 1 or decoder.layers[0].out_features not in (32, 64, 128):
-        return f"decoder {decoder.layers[0].out_features} x {len(decoder.layers)}"
+    shape = (decoder.layers[0].out_features, len(decoder.layers))
+    if shape not in ((32, 1), (64, 1), (128, 1), (32, 2)):  # the decoders train_fused_kernel is compiled for
+        return f"decoder {shape[0]} x {shape[1]}"
     if decoder.layers[0].in_features != config.feature_dim + 3 or config.feature_dim != 8:
         return "feature_dim != 8 or positional encoding"
     return None
@@ -106,7 +107,7 @@ class FusedTrainer:
         self.dec_numel = [0 if p is None else p.numel() for p in self.dec_tensors]
         # absent biases still own a slot in the flat layout the kernels use
         h = decoder.layers[0].out_features
-        expect = [h * decoder.layers[0].in_features, h, h, 1]
+        expect = [h * decoder.layers[0].in_features, h] + [h * h, h] * (len(decoder.layers) - 1) + [h, 1]
         self.dec_numel = [max(a, b) for a, b in zip(self.dec_numel, expect)]
         total = sum(self.dec_numel)
         if self.train_decoder:
@@ -293,8 +294,8 @@ class FusedTrainer:
         a.loss = loss.data_ptr()
         if self.peer is not None:
             self._peer_train_args(a, self._parity)
-        if self.dec_grad is not None and self.use_scratch:
-            need = int(lib.clid_train_fused_scratch_bytes(n, a.numerical))
+        if (self.dec_grad is not None and self.use_scratch) or len(dec.layers) == 2:
+            need = int(lib.clid_train_fused_scratch_bytes_for(C.byref(ds), n, a.numerical))
             if self._scratch is None or self._scratch.numel() < need:
                 self._scratch = torch.empty(need, dtype=torch.uint8, device=dev)
             a.scratch, a.scratch_bytes = self._scratch.data_ptr(), need
@@ -309,7 +310,7 @@ class FusedTrainer:
             ev1.record()
             self.forward_events.append((ev0, ev1))
         self.launches += 1 if n > 0 else 0
-        if a.scratch and n > 0:
+        if a.scratch and n > 0 and self.dec_grad is not None:
             # the per-point decoder-gradient rows sit in scratch: dense reduction into dec_grad -- now, or
             # on the side stream of the following adam_step()
             self._pending_reduce = (ds, a.scratch, n, a.numerical, flags)
@@ -432,8 +433,8 @@ class FusedTrainer:
         a.touched = None if self.touched is None else self.touched.data_ptr()
         a.dec_grad = None if self.dec_grad is None else self.dec_grad.data_ptr()
         a.loss = loss.data_ptr()
-        if self.dec_grad is not None:
-            need = int(lib.clid_train_fused_scratch_bytes(n, a.numerical))
+        if self.dec_grad is not None or len(dec.layers) == 2:
+            need = int(lib.clid_train_fused_scratch_bytes_for(C.byref(ds), n, a.numerical))
             if self._scratch is None or self._scratch.numel() < need:
                 self._scratch = torch.empty(need, dtype=torch.uint8, device=dev)
             a.scratch, a.scratch_bytes = self._scratch.data_ptr(), need

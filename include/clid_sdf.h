@@ -217,7 +217,8 @@ CLID_API int clid_sdf_loss(const ClidLossArgs* args, clid_stream_t stream);
  *   touched  [n_gather+1]   = 1 for rows that received a contribution (may be NULL)
  *   dec_grad flat [W0 (HxD), b0 (H), wout (H), bout (1)] +=, NULL when the decoder is frozen
  * Compiled for one hidden level with H in {32, 64, 128}; other decoders return
- * CLID_EUNSUPPORTED (the host then differentiates through clid_query_backward instead). */
+ * CLID_EUNSUPPORTED (clid_train_fused also covers 32 x 2; otherwise the host differentiates through
+ * clid_query_backward instead). */
 CLID_API int clid_train_backward(const ClidMap* map, const ClidDecoder* dec, const float* x,
                                  const int32_t* knn_idx, const float* dlogit, const float* dgrad,
                                  int64_t n, int64_t n_r, uint32_t flags, float* gfeat,
@@ -271,6 +272,10 @@ typedef struct ClidTrainFusedArgs {
 } ClidTrainFusedArgs;
 /* Device scratch clid_train_fused wants for n samples (64 bytes per evaluated point, 16-byte aligned). */
 CLID_API size_t clid_train_fused_scratch_bytes(int64_t n, int32_t numerical);
+/* The same for a given decoder: two-level decoders (32 x 2) write 448-byte rows
+ * [delta z + tau0 ; delta | beta1 | delta h1 + tau1 | delta h2 + tau2 | activation bits] and need the scratch even
+ * when the decoder is frozen (csrc/mlp_l2.cuh). */
+CLID_API size_t clid_train_fused_scratch_bytes_for(const ClidDecoder* dec, int64_t n, int32_t numerical);
 CLID_API int clid_train_fused(const ClidMap* map, const ClidDecoder* dec, const ClidTrainFusedArgs* args,
                               uint32_t flags, clid_stream_t stream);
 

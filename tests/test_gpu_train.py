@@ -9,6 +9,7 @@ import helpers as hp
 pytestmark = pytest.mark.gpu
 
 L1_CASES = [n for n in gio.names("train") if "l2h32" not in n]
+L2_CASES = [n for n in gio.names("train") if "l2h32" in n]
 ALL_CASES = gio.names("train")
 
 
@@ -72,6 +73,29 @@ def test_fused_training_matches_reference(name, variant, monkeypatch):
         if not frozen:
             flat = torch.cat([gio.t(fx[f"dec_grad_it{it}_{j}"]).flatten() for j in range(4)])
             gio.assert_close(trainer.dec_grad, flat, 1e-3, 1e-7, f"dL/ddecoder it{it}")
+        trainer.adam_step()
+    _check_final_state(fx, npm, dec)
+
+
+@pytest.mark.parametrize("name", L2_CASES)
+def test_fused_training_of_the_two_level_decoder_matches_reference(name):
+    """32 x 2 decoder (BASELINE configs[0]) through train_fused_kernel<32, 2> + decoder_grad_l2_kernel: losses,
+    dL/dfeatures, dL/d{W0, b0, W1, b1, wout, bout} per iteration and the post-Adam state against the reference."""
+    from clid_slam_b200.ops.train import FusedTrainer
+
+    fx, m, cfg, npm, dec, frozen = _setup(name)
+    assert len(dec.layers) == 2
+    trainer = FusedTrainer(cfg, npm, dec)
+    for it in range(int(fx["n_iters"])):
+        x, label, ts, weight = _batch(fx, it)
+        loss = trainer.iteration(x, label, ts, weight, apply_step=False)
+        gio.assert_close(loss[0], fx["loss_total"][it], hp.LOSS_RTOL, 0, f"total loss it{it}")
+        gio.assert_close(loss[1], fx["loss_bce"][it], 1e-4, 0, f"bce loss it{it}")
+        gio.assert_close(loss[2], fx["loss_eikonal"][it], 1e-4, 0, f"eikonal loss it{it}")
+        gio.assert_close(trainer.feat_grad, fx["feat_grads"][it], 1e-3, 2e-9, f"dL/dfeatures it{it}", 1e-3)
+        if not frozen:
+            flat = torch.cat([gio.t(fx[f"dec_grad_it{it}_{j}"]).flatten() for j in range(6)])
+            gio.assert_close(trainer.dec_grad, flat, 1e-3, 1e-7, f"dL/ddecoder it{it}", 1e-3)
         trainer.adam_step()
     _check_final_state(fx, npm, dec)
 
