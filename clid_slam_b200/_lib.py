@@ -109,6 +109,14 @@ class ClidPeerArgs(C.Structure):
     ]
 
 
+class ClidLocalCloud(C.Structure):
+    _fields_ = [
+        ("table", C.c_void_p), ("buffer_size", C.c_int64), ("primes", C.c_int64 * 3), ("points", C.c_void_p),
+        ("n_points", C.c_int64), ("neighbor_idx", C.c_void_p), ("kc", C.c_int32), ("resolution", C.c_float),
+        ("max_valid_range", C.c_float),
+    ]
+
+
 class ClidReplayPool(C.Structure):
     _fields_ = [
         ("coord", C.c_void_p), ("sdf_label", C.c_void_p), ("weight", C.c_void_p), ("time", C.c_void_p),
@@ -157,6 +165,7 @@ _SIGNATURES = [
     ("clid_ipc_close", C.c_int, [C.c_void_p]),
     ("clid_peer_publish", C.c_int, [C.POINTER(ClidPeerArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
     ("clid_peer_reduce", C.c_int, [C.POINTER(ClidPeerArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("clid_region_sdf", C.c_int, [C.POINTER(ClidLocalCloud), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("clid_registration_terms", C.c_int,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.c_int32, C.c_float, C.c_float,
       C.c_void_p, C.c_void_p, C.c_void_p]),

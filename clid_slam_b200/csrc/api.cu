@@ -14,6 +14,7 @@
 #include "decoder_grad.cuh"
 #include "peer.cuh"
 #include "mlp_l2.cuh"
+#include "feeder.cuh"
 #include "train_fused.cuh"
 
 namespace clid {
@@ -426,6 +427,30 @@ int clid_peer_reduce(const ClidPeerArgs* a, float* dst0, float* dst1, clid_strea
   peer_reduce_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a, dst0, dst1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "peer_reduce_kernel launch");
+  return CLID_OK;
+}
+
+int clid_region_sdf(const ClidLocalCloud* c, const float* points, int64_t n, float* sdf_abs, uint8_t* surface_mask,
+                    clid_stream_t stream) {
+  if (!c) return set_error(CLID_EINVAL, "cloud is NULL");
+  if (n < 0) return set_error(CLID_EINVAL, "n = %lld", (long long)n);
+  if (n == 0) return CLID_OK;
+  if (!points || !sdf_abs || !surface_mask) return set_error(CLID_EINVAL, "points/outputs are NULL");
+  if (!c->table || c->buffer_size <= 0 || !c->neighbor_idx || c->kc < 1 || c->kc > CLID_MAX_KC)
+    return set_error(CLID_EINVAL, "local point-cloud map: table / neighbourhood missing");
+  if (c->n_points > 0 && !c->points) return set_error(CLID_EINVAL, "local point-cloud map: points are NULL");
+  if (!(c->resolution > 0.f)) return set_error(CLID_EINVAL, "resolution must be positive");
+  RegionSdfParams p;
+  memset(&p, 0, sizeof(p));
+  p.points = points; p.table = c->table; p.map_points = c->points; p.neighbor_idx = c->neighbor_idx;
+  p.n = n; p.buffer_size = c->buffer_size; p.m = c->n_points;
+  for (int i = 0; i < 3; ++i) p.primes[i] = c->primes[i];
+  p.kc = c->kc; p.resolution = c->resolution; p.max_valid_range = c->max_valid_range;
+  p.eta_threshold = 0.2f; p.dist_threshold = 0.1f;  // estimate_plane defaults (local_point_cloud_map.py:155-157)
+  p.sdf_abs = sdf_abs; p.surface_mask = surface_mask;
+  region_sdf_kernel<<<elementwise_grid(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "region_sdf_kernel launch");
   return CLID_OK;
 }
 

@@ -77,7 +77,42 @@ class LocalPointCloudMap:
 
     def region_specific_sdf_estimation(self, points: torch.Tensor):
         """(|sdf| [N], surface_mask [N]) for surface samples in the world frame
-        (model/local_point_cloud_map.py:98-152)."""
+        (model/local_point_cloud_map.py:98-152).  On a CUDA map: one launch of clid_region_sdf."""
+        if points.is_cuda and self.buffer_pt_index.is_cuda:
+            return self._region_sdf_native(points)
+        return self._region_sdf_torch(points)
+
+    def _region_sdf_native(self, points: torch.Tensor):
+        import ctypes as C
+
+        from .. import _lib
+
+        pts = points.detach().float().contiguous()
+        n = pts.shape[0]
+        c = _lib.ClidLocalCloud()
+        c.table = _lib.ptr(self.buffer_pt_index, torch.int64, "local buffer_pt_index")
+        c.buffer_size = self.buffer_size
+        for i, pr in enumerate(PRIMES_LOCAL):
+            c.primes[i] = pr
+        cloud = self.local_point_cloud_map.contiguous()
+        c.points = _lib.ptr(cloud, torch.float32, "local_point_cloud_map") if cloud.shape[0] else None
+        c.n_points = cloud.shape[0]
+        nidx = self.neighbor_idx.contiguous()
+        c.neighbor_idx, c.kc = _lib.ptr(nidx, torch.int64, "neighbor_idx"), nidx.shape[0]
+        c.resolution, c.max_valid_range = float(self.resolution), float(self.max_valid_range)
+        sdf_abs = torch.empty(n, dtype=torch.float32, device=pts.device)
+        mask = torch.empty(n, dtype=torch.uint8, device=pts.device)
+        with torch.cuda.device(pts.device):
+            rc = _lib.load().clid_region_sdf(C.byref(c), pts.data_ptr(), n, sdf_abs.data_ptr(), mask.data_ptr(),
+                                            _lib.current_stream(pts.device))
+        _lib.check(rc, "clid_region_sdf")
+        mask = mask.bool()
+        if not self.config.silence:
+            print(mask.sum().item() / max(mask.numel(), 1))
+        return sdf_abs, mask
+
+    def _region_sdf_torch(self, points: torch.Tensor):
+        """The same with torch ops (host logic; what the CPU tests pin against the reference's fixtures)."""
         n = points.shape[0]
         far = self.max_valid_range
         sdf_abs = torch.full((n,), far, device=points.device, dtype=torch.float32)

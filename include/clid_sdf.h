@@ -320,6 +320,29 @@ CLID_API int clid_adam_step(const ClidAdamArgs* args, clid_stream_t stream);
  * step >= 0).  For callers that split one optimiser step over several clid_adam_step(step < 0) launches. */
 CLID_API int clid_adam_advance(void* step_state, float lr, float beta1, float beta2, clid_stream_t stream);
 
+/* ---- per-frame feeders ---------------------------------------------------------------------- */
+
+/* LocalPointCloudMap.region_specific_sdf_estimation + estimate_plane (model/local_point_cloud_map.py:98-201): for
+ * every surface sample, probe the kc cells (neighbor_idx [kc,3]) of the raw-point voxel hash `table`
+ * (primes (73856093, 19349663, 83492791), -1 empty), take the four nearest stored points, fit a least-squares
+ * plane through them and return the point-to-plane distance when the neighbourhood is flat
+ * (sigma_min / (sigma_mid + 1e-6) <= 0.2) and all four points lie within 0.1 m of the plane, else the distance to the
+ * nearest stored point; samples with fewer than four neighbours use the nearest point; surface_mask = a stored point
+ * was found at all.  One launch instead of ~30 eager ops and a batched cuSOLVER SVD per scan. */
+typedef struct ClidLocalCloud {
+  const int64_t* table;         /* [buffer_size]                      */
+  int64_t buffer_size;
+  int64_t primes[3];
+  const float* points;          /* [n_points,3] local_point_cloud_map */
+  int64_t n_points;
+  const int64_t* neighbor_idx;  /* [kc,3]                             */
+  int32_t kc;
+  float resolution;             /* local_voxel_size_m                 */
+  float max_valid_range;
+} ClidLocalCloud;
+CLID_API int clid_region_sdf(const ClidLocalCloud* cloud, const float* points, int64_t n, float* sdf_abs,
+                             uint8_t* surface_mask, clid_stream_t stream);
+
 /* ---- registration epilogue (utils/error_state_iekf.py:176-264 h_model, :303-309 update_iterated) ---------- */
 
 /* What IEKFOM.update_iterated needs from h_model, reduced on the device: with, per scan point i,

@@ -72,3 +72,33 @@ def test_mesher_query_points_matches_the_reference_mesher():
     sdf_np, _, _, mask_np = mesher.query_points(grid, 7000, mask_min_nn_count=int(fx["mesh_min_nn"]))
     assert isinstance(sdf_np, np.ndarray) and sdf_np.dtype == np.float64 and mask_np.shape == sdf_np.shape
     np.testing.assert_allclose(sdf_np, sdf.numpy().astype(np.float64), rtol=0, atol=0)
+
+
+def test_native_region_sdf_matches_the_torch_mirror():
+    """clid_region_sdf against the torch restatement of LocalPointCloudMap.region_specific_sdf_estimation (which the
+    CPU suite pins to the reference's fixtures): same surface mask, same |sdf| labels; the plane-acceptance tests
+    (sigma ratio <= 0.2, residual <= 0.1 m) may flip for a handful of borderline neighbourhoods (fp32 LAPACK SVD
+    there, double Jacobi here)."""
+    from clid_slam_b200.config import ncd128
+    from clid_slam_b200.model.local_point_cloud_map import LocalPointCloudMap
+
+    cfg = ncd128()
+    cfg.device = "cuda"
+    cfg.local_buffer_size = 2_000_003
+    lpm = LocalPointCloudMap(cfg)
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    xy = (torch.rand(60000, 2, generator=gen, device="cuda") - 0.5) * 60
+    floor = torch.cat((xy, 0.4 * torch.sin(xy[:, :1] / 4) + 0.01 * torch.randn(60000, 1, generator=gen, device="cuda")), 1)
+    wall = torch.cat((torch.full((8000, 1), 9.0, device="cuda"), (torch.rand(8000, 2, generator=gen, device="cuda") - 0.5) * 12), 1)
+    lpm.update_map(torch.zeros(3, device="cuda"), torch.cat((floor, wall), 0))
+    assert lpm.local_point_cloud_map.shape[0] > 20000
+    pick = torch.randint(0, floor.shape[0], (50000,), generator=gen, device="cuda")
+    q = torch.cat((floor[pick] + 0.15 * torch.randn(50000, 3, generator=gen, device="cuda"),
+                   (torch.rand(3000, 3, generator=gen, device="cuda") - 0.5) * 100,       # mostly far from everything
+                   -floor[pick[:2000]]), 0).contiguous()                                    # negative cells too
+    sdf_n, mask_n = lpm._region_sdf_native(q)
+    sdf_t, mask_t = lpm._region_sdf_torch(q)
+    assert torch.equal(mask_n, mask_t)
+    bad = ((sdf_n - sdf_t).abs() > 1e-5 + 1e-4 * sdf_t.abs()).double().mean().item()
+    assert bad < 2e-3, f"{bad:.2e} of the labels differ"
+    assert 0.3 < float(mask_n.float().mean()) < 1.0
