@@ -165,6 +165,12 @@ _SIGNATURES = [
     ("clid_ipc_close", C.c_int, [C.c_void_p]),
     ("clid_peer_publish", C.c_int, [C.POINTER(ClidPeerArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
     ("clid_peer_reduce", C.c_int, [C.POINTER(ClidPeerArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("clid_brick_keep", C.c_int,
+     [C.POINTER(ClidMap), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("clid_brick_keys", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]),
+    ("clid_brick_fill", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("clid_region_sdf", C.c_int, [C.POINTER(ClidLocalCloud), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("clid_registration_terms", C.c_int,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.c_int32, C.c_float, C.c_float,

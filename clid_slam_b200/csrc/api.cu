@@ -454,6 +454,57 @@ int clid_region_sdf(const ClidLocalCloud* c, const float* points, int64_t n, flo
   return CLID_OK;
 }
 
+int clid_brick_keep(const ClidMap* m, const float* points, const int64_t* gids, int64_t n, const int32_t* ts_create,
+                    int32_t* cells, uint8_t* keep, int32_t* bbox, clid_stream_t stream) {
+  if (!m || !points || !cells || !keep || !bbox) return set_error(CLID_EINVAL, "a required pointer is NULL");
+  if (n <= 0) return n < 0 ? set_error(CLID_EINVAL, "n = %lld", (long long)n) : CLID_OK;
+  if (!m->buffer_pt_index || m->buffer_size <= 0 || !(m->resolution > 0.f)) return set_error(CLID_EINVAL, "hash table / resolution missing");
+  if (ts_create && (!m->travel_dist || m->cur_ts < 0 || m->cur_ts >= m->n_travel)) return set_error(CLID_EINVAL, "time filter without travel_dist / cur_ts");
+  BrickKeyParams p;
+  memset(&p, 0, sizeof(p));
+  p.points = points; p.gids = gids; p.table = m->buffer_pt_index; p.buffer_size = m->buffer_size;
+  for (int i = 0; i < 3; ++i) p.primes[i] = m->primes[i];
+  p.ts_create = ts_create; p.travel_dist = m->travel_dist; p.cur_ts = m->cur_ts;
+  p.diff_travel_dist_local = m->diff_travel_dist_local; p.resolution = m->resolution; p.n = n;
+  p.cells = cells; p.keep = keep; p.bbox = bbox;
+  brick_keep_kernel<<<elementwise_grid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "brick_keep_kernel launch");
+  return CLID_OK;
+}
+
+int clid_brick_keys(const int32_t* cells, const uint8_t* keep, int64_t n, const int32_t* lo3, const int32_t* dims3, int64_t* keys,
+                    clid_stream_t stream) {
+  if (!cells || !keep || !lo3 || !dims3 || !keys) return set_error(CLID_EINVAL, "a required pointer is NULL");
+  if (n <= 0) return n < 0 ? set_error(CLID_EINVAL, "n = %lld", (long long)n) : CLID_OK;
+  brick_key_kernel<<<elementwise_grid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(cells, keep, n, lo3[0], lo3[1], lo3[2],
+                                                                                            dims3[0], dims3[1], keys);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "brick_key_kernel launch");
+  return CLID_OK;
+}
+
+int clid_brick_fill(const int64_t* sorted_keys, const int64_t* order, int64_t n_kept, const float* points, const int32_t* dims3,
+                    float* records, ClidBrickHeader* headers, uint32_t* hood, clid_stream_t stream) {
+  if (!sorted_keys || !order || !points || !dims3 || !records || !headers) return set_error(CLID_EINVAL, "a required pointer is NULL");
+  if (n_kept <= 0) return set_error(CLID_EINVAL, "n_kept = %lld", (long long)n_kept);
+  if (!aligned16(records) || !aligned16(headers) || (hood && (reinterpret_cast<uintptr_t>(hood) & 127u)))
+    return set_error(CLID_EINVAL, "records / headers must be 16-byte aligned, hood 128-byte aligned");
+  const int64_t nb = (int64_t)dims3[0] * dims3[1] * dims3[2];
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // headers start as {mask 0, base INT_MAX, count 0}
+  cudaError_t e = cudaMemsetAsync(headers, 0, (size_t)nb * sizeof(ClidBrickHeader), s);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(headers)");
+  brick_header_init_kernel<<<elementwise_grid(nb, 256), 256, 0, s>>>(headers, nb);
+  brick_scatter_kernel<<<elementwise_grid(n_kept, 256), 256, 0, s>>>(sorted_keys, order, n_kept, points, nullptr,
+                                                                      reinterpret_cast<float4*>(records), headers);
+  brick_hood_kernel<<<elementwise_grid(nb * 8, 256), 256, 0, s>>>(headers, dims3[0], dims3[1], dims3[2], hood);
+  brick_header_fix_kernel<<<elementwise_grid(nb, 256), 256, 0, s>>>(headers, nb);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "brick fill kernels launch");
+  return CLID_OK;
+}
+
 int clid_registration_terms(const float* pc_imu, const float* sdf, const float* grad, const int32_t* nn_count, int64_t n,
                             const float* rot9, int32_t min_nn, float min_grad, float max_grad, double* out28,
                             uint8_t* valid_out, clid_stream_t stream) {

@@ -120,7 +120,9 @@ class SpatialShards:
             ext = points.amax(0) - points.amin(0)
             axis = int(torch.argmax(ext).item())
         self.axis = axis
-        cell = torch.floor(points[:, axis] / self.resolution).to(torch.int64)
+        from .utils.tools import ieee_div
+
+        cell = torch.floor(ieee_div(points[:, axis], self.resolution)).to(torch.int64)
         if boundaries is None:
             if world_size > 1:
                 q = torch.arange(1, world_size, device=dev, dtype=torch.float32) / world_size
@@ -165,7 +167,9 @@ class SpatialShards:
 
     def owner_of(self, x: torch.Tensor) -> torch.Tensor:
         """Rank that processes each sample of x [n,3]."""
-        cell = torch.floor(x[:, self.axis] / self.resolution).to(torch.int64)
+        from .utils.tools import ieee_div
+
+        cell = torch.floor(ieee_div(x[:, self.axis], self.resolution)).to(torch.int64)
         return torch.searchsorted(self.boundaries, cell, right=True)
 
     def gather_features(self, features: torch.Tensor, rank: int, group=None) -> None:

@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import torch
 
-from ..utils.tools import voxel_down_sample_torch
+from ..utils.tools import ieee_div, voxel_down_sample_torch
 
 PRIMES_LOCAL = (73856093, 19349663, 83492791)  # model/local_point_cloud_map.py:27-29 (2nd prime differs)
 
@@ -45,7 +45,7 @@ class LocalPointCloudMap:
         self.map_size = config.local_map_size
 
     def voxel_hash(self, points: torch.Tensor) -> torch.Tensor:
-        cells = (points / self.resolution).floor().to(self.primes)
+        cells = ieee_div(points, self.resolution).floor().to(self.primes)
         return torch.fmod((cells * self.primes).sum(-1), self.buffer_size)
 
     def insert_points(self, points: torch.Tensor) -> None:
@@ -120,7 +120,7 @@ class LocalPointCloudMap:
         chunk = 262144
         for head in range(0, n, chunk):
             pts = points[head:head + chunk, :]
-            cells = (pts / self.resolution).floor().to(self.primes)
+            cells = ieee_div(pts, self.resolution).floor().to(self.primes)
             cells = cells[..., None, :] + self.neighbor_idx
             slots = torch.fmod((cells * self.primes).sum(-1), self.buffer_size)
             idx = self.buffer_pt_index[slots]

@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from ..ops import query as _q
-from ..utils.tools import voxel_down_sample_min_value_torch, voxel_down_sample_torch
+from ..utils.tools import ieee_div, voxel_down_sample_min_value_torch, voxel_down_sample_torch
 
 PRIMES = (73856093, 19349669, 83492791)  # model/neural_points.py:79-81
 
@@ -146,7 +146,7 @@ class NeuralPoints(nn.Module):
 
     # ------------------------------------------------------------------ hashing
     def _slots_of(self, points: torch.Tensor) -> torch.Tensor:
-        cells = (points / self.resolution).floor().to(self.primes)
+        cells = ieee_div(points, self.resolution).floor().to(self.primes)
         return torch.fmod((cells * self.primes).sum(-1), int(self.buffer_size))
 
     def _store_slots(self, slots: torch.Tensor, values: torch.Tensor) -> None:
@@ -237,6 +237,7 @@ class NeuralPoints(nn.Module):
 
         d2 = ((self.neural_points[in_time] - sensor_position) ** 2).sum(-1)
         chosen = torch.nonzero(in_time).squeeze(-1)[d2 < self.local_map_radius**2]
+        self._local_gids = chosen  # ascending global ids of the local points (== nonzero(local_mask[:-1]))
         mask = torch.zeros(m, dtype=torch.bool, device=dev)
         mask[chosen] = True
 
@@ -370,10 +371,11 @@ class NeuralPoints(nn.Module):
         """Cell offsets inside the sphere |d|^2 < (num_nei_cells + search_alpha)^2 and the matching
         validity radius (model/neural_points.py:931-969).  Toggled at run time by the mapper
         (mapper.py:409-423), so the kernels take the table as an argument."""
-        r = torch.arange(-num_nei_cells, num_nei_cells + 1, device=self.primes.device, dtype=self.primes.dtype)
+        r = torch.arange(-num_nei_cells, num_nei_cells + 1, dtype=self.primes.dtype)
         cube = torch.stack(torch.meshgrid(r, r, r, indexing="ij"), dim=-1).reshape(-1, 3)
         inside = (cube**2).sum(-1) < (num_nei_cells + search_alpha) ** 2
-        self.neighbor_dx = cube[inside].contiguous()
+        self._neighbor_dx_cpu = cube[inside].contiguous()  # host copy: the brick-index build reads it without a sync
+        self.neighbor_dx = self._neighbor_dx_cpu.to(self.primes.device)
         self.neighbor_K = self.neighbor_dx.shape[0]
         self.max_valid_dist2 = 3 * ((num_nei_cells + 1) * self.resolution) ** 2
         self._touch()

@@ -63,6 +63,17 @@ def _stencil_table(offsets_cpu: torch.Tensor, reach: int, span: int) -> torch.Te
     return _STENCILS[key]
 
 
+_STENCILS_DEV = {}
+
+
+def _stencil_on(dev, offsets_cpu: torch.Tensor, reach: int, span: int) -> torch.Tensor:
+    """Device copy of the stencil table, uploaded once per (neighbourhood, device)."""
+    key = (offsets_cpu.numpy().tobytes(), reach, span, str(dev))
+    if key not in _STENCILS_DEV:
+        _STENCILS_DEV[key] = _stencil_table(offsets_cpu, reach, span).to(dev)
+    return _STENCILS_DEV[key]
+
+
 def _make_stencil_table(offsets_cpu: torch.Tensor, reach: int, span: int) -> torch.Tensor:
     inside = {tuple(int(v) for v in row) for row in offsets_cpu.tolist()}
     table = np.zeros((64, span**3), dtype=np.uint64)
@@ -119,7 +130,9 @@ class BrickIndex:
 def build(npm, query_locally: bool) -> Optional[BrickIndex]:
     """Index of the points a query of `npm` can return; None when the fast path is not exact or
     not applicable (then the hashed kernel is used)."""
-    offsets_cpu = npm.neighbor_dx.detach().cpu()
+    offsets_cpu = getattr(npm, "_neighbor_dx_cpu", None)
+    if offsets_cpu is None or tuple(offsets_cpu.shape) != tuple(npm.neighbor_dx.shape):
+        offsets_cpu = npm.neighbor_dx.detach().cpu()  # a map whose table was set from outside (tests, old pickles)
     reach = int(offsets_cpu.abs().max().item()) if offsets_cpu.numel() else 0
     span = (2 * reach + 7) // 4
     if npm.count() == 0:
@@ -128,6 +141,74 @@ def build(npm, query_locally: bool) -> Optional[BrickIndex]:
         return _fallback(f"num_nei_cells = {reach}: a neighbourhood must span 2 bricks per axis") if reach > 2 else None
     if not hash_is_alias_free(int(npm.buffer_size), reach):
         return _fallback(f"hash table of {int(npm.buffer_size)} slots aliases cells inside a neighbourhood")
+    dev = npm.neural_points.device
+    if dev.type == "cuda" and NATIVE_BUILD:
+        return _build_native(npm, query_locally, offsets_cpu, reach, span)
+    return _build_torch(npm, query_locally, offsets_cpu, reach, span)
+
+
+NATIVE_BUILD = os.environ.get("CLID_NATIVE_BRICK_BUILD", "1") != "0"
+
+
+def _build_native(npm, query_locally: bool, offsets_cpu, reach: int, span: int) -> Optional[BrickIndex]:
+    """The index through clid_brick_keep / clid_brick_keys / clid_brick_fill (csrc/feeder.cuh) around one torch.sort:
+    four launches and ONE 28-byte read-back (the bounding box sizes the dense header array) per rebuild."""
+    import ctypes as C
+
+    from . import query as _q
+
+    dev = npm.neural_points.device
+    lib = _lib.load()
+    if query_locally:
+        pts = npm.local_neural_points.contiguous()
+        gids = getattr(npm, "_local_gids", None)
+        if gids is None or gids.shape[0] != pts.shape[0] or gids.device != dev:
+            gids = torch.nonzero(npm.local_mask[:-1]).flatten()
+        gids = gids.contiguous()
+        gid_ptr = gids.data_ptr()
+    else:
+        pts = npm.neural_points.contiguous()
+        gids, gid_ptr = None, None
+    n = pts.shape[0]
+    if n == 0:
+        return None
+    m, _ = _q.map_struct(npm, query_locally)
+    time_filter = bool(query_locally and npm.temporal_local_map_on)
+    ts_ptr = _lib.ptr(npm.point_ts_create, torch.int32, "point_ts_create") if time_filter else None
+    cells = torch.empty(n, 3, dtype=torch.int32, device=dev)
+    keep = torch.empty(n, dtype=torch.uint8, device=dev)
+    i32 = torch.iinfo(torch.int32)
+    bbox = torch.tensor([i32.max] * 3 + [i32.min] * 3 + [0], dtype=torch.int32, device=dev)
+    stream = _lib.current_stream(dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.clid_brick_keep(C.byref(m), pts.data_ptr(), gid_ptr, n, ts_ptr, cells.data_ptr(), keep.data_ptr(),
+                                       bbox.data_ptr(), stream), "clid_brick_keep")
+    bb = bbox.cpu().tolist()  # the one synchronisation of a rebuild
+    n_kept = bb[6]
+    if n_kept == 0:
+        return None
+    lo = [bb[a] - 4 for a in range(3)]  # one empty brick all around (ClidBricks.apron)
+    dims = [(bb[3 + a] + 4 - lo[a]) // 4 + 1 for a in range(3)]
+    n_bricks = dims[0] * dims[1] * dims[2]
+    if n_bricks > MAX_BRICKS:
+        return _fallback(f"bounding box of {dims} bricks exceeds the dense header cap of {MAX_BRICKS}")
+    lo_c, dims_c = (C.c_int32 * 3)(*lo), (C.c_int32 * 3)(*dims)
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.clid_brick_keys(cells.data_ptr(), keep.data_ptr(), n, lo_c, dims_c, keys.data_ptr(), stream), "clid_brick_keys")
+    sorted_keys, order = torch.sort(keys)  # kept points first, in (brick, cell) order
+    records = torch.empty(n_kept, 4, dtype=torch.float32, device=dev)
+    headers = torch.empty(n_bricks, 4, dtype=torch.int32, device=dev)
+    hood = torch.empty(n_bricks, 32, dtype=torch.int32, device=dev) if USE_HOOD and n_bricks <= MAX_HOOD_BRICKS else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.clid_brick_fill(sorted_keys.data_ptr(), order.data_ptr(), n_kept, pts.data_ptr(), dims_c,
+                                       records.data_ptr(), headers.data_ptr(), None if hood is None else hood.data_ptr(),
+                                       stream), "clid_brick_fill")
+    return BrickIndex(headers, records, _stencil_on(dev, offsets_cpu, reach, span), lo, dims, span, reach, apron=1, hood=hood)
+
+
+def _build_torch(npm, query_locally: bool, offsets_cpu, reach: int, span: int) -> Optional[BrickIndex]:
+    """The same index with torch ops (host logic for CPU maps and the cross-check of the native build)."""
     dev = npm.neural_points.device
     res = float(npm.resolution)
     primes = npm.primes
@@ -142,7 +223,9 @@ def build(npm, query_locally: bool) -> Optional[BrickIndex]:
         rows = gids.to(torch.int32)
     if pts.shape[0] == 0:
         return None
-    cells = (pts / res).floor().to(torch.int64)
+    from ..utils.tools import ieee_div
+
+    cells = ieee_div(pts, res).floor().to(torch.int64)
     slots = torch.fmod((cells * primes).sum(-1), int(npm.buffer_size))
     keep = npm.buffer_pt_index[slots] == gids  # the point owns its voxel's slot
     if query_locally and npm.temporal_local_map_on:

@@ -71,9 +71,18 @@ def transform_batch_torch(points: torch.Tensor, transformation: torch.Tensor) ->
     return torch.einsum("nij,nj->ni", rot, points) + trans
 
 
+def ieee_div(x: torch.Tensor, divisor: float) -> torch.Tensor:
+    """x / divisor with IEEE division on every device.  torch's CUDA kernels turn `tensor / python_scalar` into a
+    multiplication by the reciprocal, which moves a coordinate that sits within one ulp of a voxel face into the
+    neighbouring cell; the CPU kernels (what the reference fixtures pin) and the CUDA kernels of this library
+    (cell_of: floorf(__fdiv_rn(x, res))) divide.  A 0-dim tensor divisor makes torch divide too, so the host logic,
+    the kernels and the CPU reference agree on every point's voxel."""
+    return x / torch.full((), divisor, dtype=x.dtype, device=x.device)
+
+
 def _voxel_keys(points: torch.Tensor, voxel_size: float):
-    lowest = torch.floor(points.min(dim=0)[0] / voxel_size).long()
-    cell_f = torch.floor(points / voxel_size)
+    lowest = torch.floor(ieee_div(points.min(dim=0)[0], voxel_size)).long()
+    cell_f = torch.floor(ieee_div(points, voxel_size))
     cell = cell_f.long() - lowest
     span = cell.max()  # the reference uses one span for all axes (utils/tools.py:662-663)
     key = cell[:, 0] + cell[:, 1] * span + cell[:, 2] * span * span

@@ -343,6 +343,24 @@ typedef struct ClidLocalCloud {
 CLID_API int clid_region_sdf(const ClidLocalCloud* cloud, const float* points, int64_t n, float* sdf_abs,
                              uint8_t* surface_mask, clid_stream_t stream);
 
+/* Brick index build (ClidBricks; replaces the ~20 eager torch ops of a per-frame rebuild), three calls around the
+ * caller's sort:
+ *   clid_brick_keep   per candidate point (the local window with its global ids `gids`, or the whole map with
+ *                     gids == NULL): voxel cell, "owns its hash slot" and travel-distance predicates
+ *                     (model/neural_points.py:1003-1009 when ts_create != NULL) -> cells [n,3] i32, keep [n] u8, and
+ *                     bbox [7] i32 (caller presets {INT_MAX x3, INT_MIN x3, 0}) = cell bounding box + count of the kept
+ *   clid_brick_keys   keys [n] i64 = brick * 64 + cell bit for kept points (INT64_MAX otherwise), for the grid with
+ *                     first cell lo[3] and dims[0..1] bricks per row / plane
+ *   clid_brick_fill   after sorting the keys (order [n] = source index of every sorted position): records
+ *                     [n_kept,4], headers [dims product] and, if hood != NULL, the 128-byte neighbourhood lines */
+CLID_API int clid_brick_keep(const ClidMap* map, const float* points, const int64_t* gids, int64_t n,
+                             const int32_t* ts_create, int32_t* cells, uint8_t* keep, int32_t* bbox, clid_stream_t stream);
+CLID_API int clid_brick_keys(const int32_t* cells, const uint8_t* keep, int64_t n, const int32_t* lo3, const int32_t* dims3,
+                             int64_t* keys, clid_stream_t stream);
+CLID_API int clid_brick_fill(const int64_t* sorted_keys, const int64_t* order, int64_t n_kept, const float* points,
+                             const int32_t* dims3, float* records, ClidBrickHeader* headers, uint32_t* hood,
+                             clid_stream_t stream);
+
 /* ---- registration epilogue (utils/error_state_iekf.py:176-264 h_model, :303-309 update_iterated) ---------- */
 
 /* What IEKFOM.update_iterated needs from h_model, reduced on the device: with, per scan point i,

@@ -102,3 +102,34 @@ def test_native_region_sdf_matches_the_torch_mirror():
     bad = ((sdf_n - sdf_t).abs() > 1e-5 + 1e-4 * sdf_t.abs()).double().mean().item()
     assert bad < 2e-3, f"{bad:.2e} of the labels differ"
     assert 0.3 < float(mask_n.float().mean()) < 1.0
+
+
+@pytest.mark.parametrize("locally", [True, False], ids=["local", "global"])
+def test_native_brick_build_equals_the_torch_build(locally):
+    """clid_brick_keep / keys / fill (one read-back) against the torch-op build of the same index: identical records,
+    headers (mask, count, first record of every occupied brick) and neighbourhood lines, with a time-filtered
+    second frame and hash collisions in play."""
+    import oracle.sdf_oracle as oc
+    from clid_slam_b200.ops import bricks as B
+
+    cfg = oc.OracleConfig(buffer_size=400_009, local_map_radius=30.0)
+    m, params, gen = hp.build_oracle_world(90, 2, seed=3, cfg=cfg)
+    m.travel_dist = torch.tensor([0.0, 500.0])
+    pts2 = oc.wavy_sheets(40, 1, cfg.voxel_size_m, gen) + torch.tensor([3.0, 2.0, 0.2])
+    oc.map_insert(m, pts2, torch.zeros(3), 1, generator=gen)
+    oc.reset_local_window(m, torch.zeros(3), 0)
+    npm = hp.product_map(m)
+    off = npm.neighbor_dx.detach().cpu()
+    a = B._build_native(npm, locally, off, 2, 2)
+    b = B._build_torch(npm, locally, off, 2, 2)
+    assert a is not None and b is not None
+    assert list(a.struct.origin) == list(b.struct.origin) and list(a.struct.dims) == list(b.struct.dims)
+    assert torch.equal(a.records, b.records)
+    ha, hb = a.headers.view(-1, 4), b.headers.view(-1, 4)
+    assert torch.equal(ha[:, [0, 1, 3]], hb[:, [0, 1, 3]]), "occupancy masks and counts"
+    occupied = hb[:, 3] > 0
+    assert torch.equal(ha[occupied, 2], hb[occupied, 2]), "first record of every occupied brick"
+    assert torch.equal(a.hood.view(-1, 32)[:, :16], b.hood.view(-1, 32)[:, :16])
+    # first-record words of the neighbourhood lines matter for occupied bricks only
+    occ8 = (b.hood.view(-1, 32)[:, 0:16:2] != 0) | (b.hood.view(-1, 32)[:, 1:16:2] != 0)
+    assert torch.equal(a.hood.view(-1, 32)[:, 16:24][occ8], b.hood.view(-1, 32)[:, 16:24][occ8])
