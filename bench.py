@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--mode", default="analytic", choices=["analytic", "numerical"],
                     help="eikonal gradient mode of the training step")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference legs (CPU and eager CUDA)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: 131072 samples per GPU and step (weak, the default the driver measures) or 131072 samples in "
+                         "total, split over the GPUs (strong)")
     ap.add_argument("--no-shipped-config", action="store_true", help="skip the configs[1] leg (process_frame + mapping(10))")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity gate against the oracle")
     ap.add_argument("--sharding", default="peer", choices=["peer", "spatial", "replicated"],
@@ -153,6 +156,7 @@ def _xlwt(batch):
 
 
 def run_native(args):
+    global BATCH
     import torch
     import torch.distributed as dist
 
@@ -166,6 +170,8 @@ def run_native(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    if args.scaling == "strong" and world > 1:
+        BATCH = BATCH // world  # the global batch stays at 131072 samples
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -457,7 +463,7 @@ def run_native(args):
             "metric": "sampled-points/sec through SDF decoder+grad+loss (train step: fused gather+MLP+grad forward, "
                       "bce+eikonal loss, backward, Adam)",
             "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": "BASELINE configs[2]: 131072 samples/batch/GPU, 1.08M neural points (4 wavy sheets, "
