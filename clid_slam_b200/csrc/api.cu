@@ -306,7 +306,10 @@ int clid_adam_step(const ClidAdamArgs* a, clid_stream_t stream) {
   AdamParams p;
   memset(&p, 0, sizeof(p));
   p.feat = a->feat; p.feat_grad = a->feat_grad; p.feat_m = a->feat_m; p.feat_v = a->feat_v;
-  p.touched = a->touched; p.rows = a->rows;
+  p.touched = a->touched; p.rows = a->rows; p.feat_stride = kFeat;
+  if (a->rows > 0 && ((reinterpret_cast<uintptr_t>(a->feat) | reinterpret_cast<uintptr_t>(a->feat_grad) | reinterpret_cast<uintptr_t>(a->feat_m) |
+                       reinterpret_cast<uintptr_t>(a->feat_v)) & 31u))
+    return set_error(CLID_EINVAL, "feature buffers must be 32-byte aligned (rows move with 256-bit loads / stores)");
   for (int t = 0; t < a->dec_tensors; ++t) { p.dec_param[t] = a->dec_param[t]; p.dec_numel[t] = a->dec_numel[t]; }
   p.dec_tensors = a->dec_tensors;
   p.dec_grad = a->dec_grad; p.dec_m = a->dec_m; p.dec_v = a->dec_v;
@@ -327,7 +330,7 @@ int clid_adam_step(const ClidAdamArgs* a, clid_stream_t stream) {
 #ifndef CLID_ADAM_BLOCKS_PER_SM
 #define CLID_ADAM_BLOCKS_PER_SM 16
 #endif
-  int grid = elementwise_grid(a->rows * 2 > 0 ? a->rows * 2 : 1, 256);
+  int grid = elementwise_grid(a->rows > 0 ? (a->rows + 1) / 2 : 1, 256);
   {
     // persistent blocks: leave thread slots for the decoder-gradient reduction that may run beside this kernel
     DeviceInfo info;

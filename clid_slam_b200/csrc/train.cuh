@@ -323,6 +323,7 @@ struct AdamParams {
   float* feat_v;          // [rows,8]
   const uint8_t* touched; // [rows] or NULL = every row
   int64_t rows;
+  int32_t feat_stride;    // floats between consecutive rows of `feat` (8)
   // decoder tensors, in flat order [W0, b0, (W1, b1, ...), wout, bout]
   float* dec_param[2 * CLID_MAX_LEVELS + 2];
   int32_t dec_numel[2 * CLID_MAX_LEVELS + 2];
@@ -345,12 +346,16 @@ struct AdamStepState {
   int32_t pad;
 };
 
+// `inv_bc2` = 1 / sqrt(1 - beta2^t), formed once per thread.  The two IEEE divisions torch's formula implies
+// (sqrt(v) / bc2_sqrt, m / denom) compile to ~20-instruction subroutines each and made the step ISSUE-bound
+// (ncu r2: issue active 66 %, 4.25 TB/s); a multiplication and a MUFU-based division (<= 2 ulp, far inside the
+// 1e-4 parity bound on post-Adam parameters) leave ~15 instructions per element and the kernel on the HBM roofline.
 __device__ __forceinline__ float adam_update(float p, float g, float& mm, float& vv, const AdamParams& a,
-                                             float step_size, float bc2_sqrt) {
+                                             float step_size, float inv_bc2) {
   mm = mm + (g - mm) * (1.0f - a.beta1);                     // exp_avg.lerp_(grad, 1 - beta1)
   vv = fmaf(1.0f - a.beta2, g * g, vv * a.beta2);            // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
-  const float denom = sqrtf(vv) / bc2_sqrt + a.eps;
-  return p - step_size * (mm / denom);
+  const float denom = fmaf(__fsqrt_rn(vv), inv_bc2, a.eps);  // sqrt(v) / bc2_sqrt + eps
+  return fmaf(-step_size, __fdividef(mm, denom), p);         // p - step_size * m / denom
 }
 
 #ifdef CLID_PLAIN_KERNELS
@@ -496,25 +501,47 @@ __global__ void copy3_kernel(const float* src, float* dst) {
 __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamParams a) {
   // the parameter block stays in the constant bank: the two scalars are the only per-step values
   const float step_size = a.step_scalars ? __ldg(a.step_scalars) : a.step_size;
-  const float bc2_sqrt = a.step_scalars ? __ldg(a.step_scalars + 1) : a.bc2_sqrt;
-  // feature rows: one thread per float4 half-row
-  const int64_t halves = a.rows * 2;
-  for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h < halves; h += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = h >> 1;
-    if (a.touched && !a.touched[row]) continue;
-    float4* pg = reinterpret_cast<float4*>(a.feat_grad) + h;
-    float4 g = *pg;
-    float4* pp = reinterpret_cast<float4*>(a.feat) + h;
-    float4* pm = reinterpret_cast<float4*>(a.feat_m) + h;
-    float4* pv = reinterpret_cast<float4*>(a.feat_v) + h;
-    float4 p = *pp, mm = *pm, vv = *pv;
-    if (a.weight_decay != 0.f) { g.x = fmaf(a.weight_decay, p.x, g.x); g.y = fmaf(a.weight_decay, p.y, g.y); g.z = fmaf(a.weight_decay, p.z, g.z); g.w = fmaf(a.weight_decay, p.w, g.w); }
-    p.x = adam_update(p.x, g.x, mm.x, vv.x, a, step_size, bc2_sqrt);
-    p.y = adam_update(p.y, g.y, mm.y, vv.y, a, step_size, bc2_sqrt);
-    p.z = adam_update(p.z, g.z, mm.z, vv.z, a, step_size, bc2_sqrt);
-    p.w = adam_update(p.w, g.w, mm.w, vv.w, a, step_size, bc2_sqrt);
-    *pp = p; *pm = mm; *pv = vv;
-    *pg = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float bc2_sqrt = 1.0f / (a.step_scalars ? __ldg(a.step_scalars + 1) : a.bc2_sqrt);  // used as a factor below
+  // feature rows: one thread per 32-byte row, 256-bit loads / stores (LDG.256 / STG.256, sm_100+): four read and four
+  // write instructions per row instead of eight each, and two rows in flight per thread
+  auto ld8 = [](const float* ptr, float (&v)[8]) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(ptr));
+  };
+  auto st8 = [](float* ptr, const float (&v)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+  };
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r0 < a.rows; r0 += 2 * stride) {
+    float g[2][8], p[2][8], mm[2][8], vv[2][8];
+    bool on[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t row = r0 + u * stride;
+      on[u] = row < a.rows && !(a.touched && !a.touched[row]);
+      if (on[u]) {
+        ld8(a.feat_grad + row * 8, g[u]);
+        ld8(a.feat + row * a.feat_stride, p[u]);
+        ld8(a.feat_m + row * 8, mm[u]);
+        ld8(a.feat_v + row * 8, vv[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!on[u]) continue;
+      const int64_t row = r0 + u * stride;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (a.weight_decay != 0.f) g[u][i] = fmaf(a.weight_decay, p[u][i], g[u][i]);
+        p[u][i] = adam_update(p[u][i], g[u][i], mm[u][i], vv[u][i], a, step_size, bc2_sqrt);
+        g[u][i] = 0.f;
+      }
+      st8(a.feat + row * a.feat_stride, p[u]);
+      st8(a.feat_m + row * 8, mm[u]);
+      st8(a.feat_v + row * 8, vv[u]);
+      st8(a.feat_grad + row * 8, g[u]);
+    }
   }
   // decoder: block 0 walks the small tensors
   if (blockIdx.x == 0 && a.dec_grad) {

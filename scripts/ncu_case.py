@@ -35,6 +35,8 @@ if args.case.endswith("_far"):
 if args.case.endswith("_same"):
     x = x[:1].repeat(args.n, 1).contiguous()
 trainer = FusedTrainer(cfg, npm, dec) if args.case.startswith("fused") or args.case == "step" else None
+if trainer is not None:
+    trainer.touched = None  # what StepPipeline / bench.py run at this batch size: dense Adam, no touched-flag stores
 for i in range(args.reps):
     flush.zero_()
     if args.case.startswith("fwd"):
