@@ -63,6 +63,7 @@ class Mapper:
         # mapping() through the native loop (clid_mapping_run); False: Python loop / CUDA graph over get_batch
         self.native_loop = os.environ.get("CLID_NATIVE_LOOP", "1") != "0"
         self.last_losses = None        # [iters,3] device tensor (total, bce, eikonal) of the last mapping() call
+        self.last_host_ms = None       # host wall time of the last native-loop mapping() call: set-up / loop enqueue
 
         dev, f32 = self.device, self.dtype
         self.coord_pool = torch.empty((0, 3), device=dev, dtype=f32)
@@ -268,7 +269,12 @@ class Mapper:
         return coord, sdf_label, ts, sem_label, color_label, weight
 
     def _mapping_fused(self, iter_count: int) -> None:
+        import time
+
+        t0 = time.perf_counter()
+        self.neural_points.brick_index(True)  # (re)built here when the map changed since the last query: one small read-back
         trainer = _train.FusedTrainer(self.config, self.neural_points, self.geo_mlp)
+        t1 = time.perf_counter()
 
         def body():
             coord, sdf_label, ts, _, _, weight = self._batch_in_global_frame()
@@ -285,6 +291,8 @@ class Mapper:
                 and torch.device(self.device).type == "cuda" and self.pool_sample_count > 0):
             seed = int(torch.randint(0, 2**62, (1,)).item())  # CPU generator: follows torch.manual_seed, no device sync
             self.last_losses = trainer.run_loop(self, iter_count, seed, global_coord=True)
+            # host-side cost of this call: index rebuild + trainer set-up, and the enqueue of all iterations
+            self.last_host_ms = {"setup": (t1 - t0) * 1e3, "loop_enqueue": (time.perf_counter() - t1) * 1e3, "iterations": iter_count}
             self.total_iter += iter_count
             self._log_losses()
             return
