@@ -25,6 +25,7 @@ TIME_FILTER = 1 << 2
 LAYER_NORM = 1 << 3
 LEAKY_RELU = 1 << 4
 USE_BRICKS = 1 << 5
+TC_DECODER = 1 << 6
 
 _f32p = C.c_void_p  # device pointers travel as plain addresses
 
@@ -184,6 +185,8 @@ _SIGNATURES = [
      [C.POINTER(ClidMap), C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("clid_query_certainty", C.c_int,
      [C.POINTER(ClidMap), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("clid_decoder_eval", C.c_int,
+     [C.POINTER(ClidDecoder), C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 ]
 
 

@@ -16,6 +16,7 @@
 #include "mlp_l2.cuh"
 #include "feeder.cuh"
 #include "train_fused.cuh"
+#include "decoder_tc.cuh"
 
 namespace clid {
 
@@ -625,6 +626,28 @@ int clid_query_certainty(const ClidMap* map, const float* x, int64_t n, const fl
       *map, x, n, point_certainties, out);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "query_certainty_kernel launch");
+  return CLID_OK;
+}
+
+int clid_decoder_eval(const ClidDecoder* dec, const float* z, int64_t n, uint32_t flags, float* out, float* a,
+                      uint32_t* mask, clid_stream_t stream) {
+  if (!dec || !out) return set_error(CLID_EINVAL, "dec/out is NULL");
+  if (n < 0) return set_error(CLID_EINVAL, "n = %lld", (long long)n);
+  if (n == 0) return CLID_OK;
+  if (!z) return set_error(CLID_EINVAL, "z is NULL");
+  if (int rc = check_decoder(dec)) return rc;
+  if (dec->hidden_dim != tc::kH || dec->levels != 1)
+    return set_error(CLID_EUNSUPPORTED, "the tensor-core decoder is compiled for 64 x 1; got %d x %d", dec->hidden_dim, dec->levels);
+  DecoderEvalParams p;
+  memset(&p, 0, sizeof(p));
+  p.dec = *dec; p.z = z; p.out = out; p.a = a; p.mask = mask; p.n = n; p.flags = flags;
+  DeviceInfo info;
+  if (int rc = device_info(&info)) return rc;
+  const size_t smem = ((sizeof(tc::Shared) + 3) / 4 + MlpLayout<tc::kH, 1>::kFloats) * sizeof(float);
+  const int64_t want = (n + 127) / 128, cap = (int64_t)info.sm_count * 4;
+  decoder_eval_tc_kernel<<<(int)(want < cap ? want : cap), 128, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "decoder_eval_tc_kernel launch");
   return CLID_OK;
 }
 

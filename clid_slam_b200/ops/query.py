@@ -237,3 +237,23 @@ def query_certainty(npm, x: torch.Tensor) -> torch.Tensor:
                                       out.data_ptr(), _lib.current_stream(xd.device))
     _lib.check(rc, "clid_query_certainty")
     return out
+
+
+def decoder_eval(decoder, z: torch.Tensor, want_grad: bool = True, want_mask: bool = False):
+    """Decoder.mlp on caller-supplied inputs z [N,11] and d out / d z, on the tensor cores (clid_decoder_eval,
+    64 x 1 decoders).  Returns (out [N] un-scaled logit, a [N,11] or None, mask [N,2] int32 or None)."""
+    lib = _lib.load()
+    _require_cuda(z, "z")
+    zd = z.detach().float().contiguous()
+    n = zd.shape[0]
+    out = torch.empty(n, dtype=torch.float32, device=zd.device)
+    a = torch.empty(n, zd.shape[1], dtype=torch.float32, device=zd.device) if want_grad else None
+    mask = torch.empty(n, 2, dtype=torch.int32, device=zd.device) if want_mask else None
+    dec = decoder.abi_struct()
+    flags = _lib.LEAKY_RELU if decoder.use_leaky_relu else 0
+    with torch.cuda.device(zd.device):
+        rc = lib.clid_decoder_eval(C.byref(dec), zd.data_ptr(), n, flags, out.data_ptr(),
+                                   None if a is None else a.data_ptr(), None if mask is None else mask.data_ptr(),
+                                   _lib.current_stream(zd.device))
+    _lib.check(rc, "clid_decoder_eval")
+    return out, a, mask

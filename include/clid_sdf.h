@@ -49,7 +49,10 @@ enum ClidFlags {
   CLID_TIME_FILTER = 1 << 2,   /* travel-distance window on point_ts_create (:1003-1009) */
   CLID_LAYER_NORM = 1 << 3,    /* F.layer_norm over the feature dim, no affine, eps 1e-5 (:632-633) */
   CLID_LEAKY_RELU = 1 << 4,    /* decoder.py:66-74, slope 0.01 */
-  CLID_USE_BRICKS = 1 << 5     /* probe through ClidMap.bricks instead of the hash table */
+  CLID_USE_BRICKS = 1 << 5,    /* probe through ClidMap.bricks instead of the hash table */
+  CLID_TC_DECODER = 1 << 6     /* evaluate a 64 x 1 decoder on the tensor cores (tcgen05.mma kind::tf32 with split
+                                * operands, accumulators in TMEM; csrc/decoder_tc.cuh).  Ignored (fp32 FMA path)
+                                * for the other decoder shapes and for the hash-table probe. */
 };
 
 /* Brick index: a compact, per-frame restatement of "which neural point does the voxel hash
@@ -461,6 +464,13 @@ CLID_API int clid_radius_search(const ClidMap* map, const float* x, int64_t n, u
  * point_certainties over the probed cells, invalid cells counting as 0.  out [n]. */
 CLID_API int clid_query_certainty(const ClidMap* map, const float* x, int64_t n,
                                   const float* point_certainties, float* out, clid_stream_t stream);
+
+/* Decoder.mlp on caller-supplied inputs (model/decoder.py:58-82) and its input gradient (what
+ * utils/tools.py:298-311 get_gradient returns for d out / d z), evaluated on the tensor cores:
+ * 64 x 1 decoders only.  z [n,11]; out [n] the un-scaled logit (sdf = sdf_scale * out); a [n,11] or NULL;
+ * mask [n,2] or NULL: activation pattern, unit j -> bit j % 32 of word j / 32.  CLID_LEAKY_RELU is read from flags. */
+CLID_API int clid_decoder_eval(const ClidDecoder* dec, const float* z, int64_t n, uint32_t flags,
+                               float* out, float* a, uint32_t* mask, clid_stream_t stream);
 
 #ifdef __cplusplus
 }
