@@ -151,6 +151,8 @@ int clid_query_forward(const ClidMap* map, const ClidDecoder* dec, const float* 
   p.ts = ts;
   p.n = n;
   p.flags = flags;
+  if ((flags & CLID_TC_DECODER) && (flags & CLID_USE_BRICKS) && dec && dec->hidden_dim == 64 && dec->levels == 1)
+    return dispatch_query_tc(p, static_cast<cudaStream_t>(stream));
   return (flags & CLID_USE_BRICKS) ? dispatch_query_bricks(p, dec != nullptr, static_cast<cudaStream_t>(stream))
                                    : dispatch_query_hashed(p, dec != nullptr, static_cast<cudaStream_t>(stream));
 }

@@ -48,14 +48,12 @@ struct __align__(16) Shared {
 __host__ __device__ constexpr int b1_index(int j, int i) { return (i >> 2) * 256 + (j >> 3) * 32 + (j & 7) * 4 + (i & 3); }
 __host__ __device__ constexpr int b2_index(int i, int j) { return (j >> 2) * 64 + (i >> 3) * 32 + (i & 7) * 4 + (j & 3); }
 
-__device__ __forceinline__ uint32_t tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// x = hi + lo with hi = x rounded to tf32 (10 mantissa bits, round to nearest by an integer add: `cvt.rna.tf32.f32`
+// has no single SASS instruction and costs ~6) and lo = x - hi exactly; the tensor core ignores the 13 low mantissa
+// bits of lo, a relative error of 2^-21 of x.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = tf32_rna(x);
-  lo = tf32_rna(x - __uint_as_float(hi));
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 // ---- TMEM management (one warp allocates and frees) ------------------------------------------------------
@@ -129,8 +127,11 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
 }
 
 // ---- CTA prologue: operands, barriers, TMEM ---------------------------------------------------------------------
-// All threads of the CTA call this (blockDim.x = 128); ends with a CTA barrier.  Returns the TMEM base address.
-__device__ __forceinline__ uint32_t prologue(Shared& sh, const ClidDecoder& dec) {
+// All threads of the CTA call this (blockDim.x = 128) once the fp32 decoder is staged in sm_dec (MlpLayout<64,1>): the
+// caller has waited on its cp.async barrier, or has staged it synchronously (the first barrier below publishes it).
+// Everything is built from shared memory: no global round trip.  Ends with a CTA barrier.  Returns the TMEM base.
+__device__ __forceinline__ uint32_t prologue(Shared& sh, const float* __restrict__ sm_dec) {
+  using Lay = MlpLayout<kH, 1>;
   const int tid = threadIdx.x, nthr = blockDim.x;
   if (tid < 32) tmem_alloc(&sh.tmem_base);
   if (tid == 0) {
@@ -139,42 +140,45 @@ __device__ __forceinline__ uint32_t prologue(Shared& sh, const ClidDecoder& dec)
     mbar_fence_init();
     sh.w1max_bits = 0u;
     sh.bmax_bits = 0u;
-    sh.bout = dec.out_bias ? __ldg(dec.out_bias) : 0.f;
   }
+  if (tid < kK1) sh.a_all[tid] = 0.f;
   __syncthreads();
-  const float* W0 = dec.weight[0];
-  const float* b0 = dec.bias[0];
-  for (int e = tid; e < kH * kK1; e += nthr) {
-    const int j = e >> 4, i = e & 15;
-    float w = 0.f;
-    if (i < kIn) w = __ldg(W0 + j * kIn + i);
-    else if (i == kIn && b0) w = __ldg(b0 + j);
-    const float v = __ldg(dec.out_weight + j) * w;
-    uint32_t hi, lo;
-    split_tf32(w, hi, lo);
-    sh.b1[0][b1_index(j, i)] = __uint_as_float(hi);
-    sh.b1[1][b1_index(j, i)] = __uint_as_float(lo);
-    split_tf32(v, hi, lo);
-    sh.b2[0][b2_index(i, j)] = __uint_as_float(hi);
-    sh.b2[1][b2_index(i, j)] = __uint_as_float(lo);
+  auto w0ext = [&](int j, int i) -> float {
+    return i < kIn ? sm_dec[Lay::kW0 + Lay::w0_index(j, i)] : (i == kIn ? sm_dec[Lay::kB0 + j] : 0.f);
+  };
+  // one 16-byte K chunk per item: b1 chunk = 4 inputs of one unit, b2 chunk = 4 units of one input
+  for (int e = tid; e < kH * (kK1 / 4); e += nthr) {
+    const int j = e >> 2, i0 = (e & 3) * 4;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) split_tf32(w0ext(j, i0 + v), hi[v], lo[v]);
+    *reinterpret_cast<uint4*>(&sh.b1[0][b1_index(j, i0)]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(&sh.b1[1][b1_index(j, i0)]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  for (int e = tid; e < kK1 * (kH / 4); e += nthr) {
+    const int i = e & 15, j0 = (e >> 4) * 4;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) split_tf32(sm_dec[Lay::kWout + j0 + v] * w0ext(j0 + v, i), hi[v], lo[v]);
+    *reinterpret_cast<uint4*>(&sh.b2[0][b2_index(i, j0)]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(&sh.b2[1][b2_index(i, j0)]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
   for (int j = tid; j < kH; j += nthr) {
-    sh.wout[j] = __ldg(dec.out_weight + j);
+    sh.wout[j] = sm_dec[Lay::kWout + j];
     float l1 = 0.f;
-    for (int i = 0; i < kIn; ++i) l1 += fabsf(__ldg(W0 + j * kIn + i));
+#pragma unroll
+    for (int i = 0; i < kIn; ++i) l1 += fabsf(w0ext(j, i));
     atomicMax(&sh.w1max_bits, __float_as_uint(l1));
-    if (b0) atomicMax(&sh.bmax_bits, __float_as_uint(fabsf(__ldg(b0 + j))));
+    atomicMax(&sh.bmax_bits, __float_as_uint(fabsf(sm_dec[Lay::kB0 + j])));
   }
-  for (int i = tid; i < kK1; i += nthr) {
+  {  // a_all[i] = sum_j w_out[j] W0ext[j][i]: 8 threads per column, 8 units each
+    const int i = tid & 15, g = (tid >> 4) & 7;
     float s = 0.f;
-    for (int j = 0; j < kH; ++j) {
-      float w = 0.f;
-      if (i < kIn) w = __ldg(W0 + j * kIn + i);
-      else if (i == kIn && b0) w = __ldg(b0 + j);
-      s = fmaf(__ldg(dec.out_weight + j), w, s);
-    }
-    sh.a_all[i] = s;
+#pragma unroll
+    for (int jj = 0; jj < kH / 8; ++jj) s = fmaf(sm_dec[Lay::kWout + 8 * g + jj], w0ext(8 * g + jj, i), s);
+    if (tid < 128) atomicAdd(&sh.a_all[i], s);
   }
+  if (tid == 0) sh.bout = sm_dec[Lay::kBout];
   fence_smem_to_async_proxy();  // the tensor core reads b1 / b2 through the async proxy
   fence_before_sync();
   __syncthreads();
@@ -244,10 +248,11 @@ __device__ __forceinline__ float exact_pre(const float* __restrict__ sm_dec, con
 
 // every thread, after waiting on bar[0]: pre-activations out of TMEM, logit, activation masks back into TMEM as the
 // A operand of layer 2.  sm_dec: the fp32 weights in MlpLayout<64,1> (for the sign safeguard).
-// mask0 / mask1: unit j -> bit j % 32 of word j / 32 (the layout mlp_l1_pairs records).
-__device__ __forceinline__ void hidden_epilogue(const Shared& sh, const float* __restrict__ sm_dec, uint32_t tlane,
-                                                const float (&z)[kIn], float slope, float& out, uint32_t& mask0,
-                                                uint32_t& mask1) {
+// mask0 / mask1 (kMask): unit j -> bit j % 32 of word j / 32 (the layout mlp_l1_pairs records).
+// Per unit: max (activation), FFMA (logit), FSET (mask as 1.0 / 0.0) -- against ~39 instructions of the FMA decoder.
+template <bool kMask, bool kLeaky>
+__device__ __forceinline__ void hidden_epilogue_t(const Shared& sh, const float* __restrict__ sm_dec, uint32_t tlane,
+                                                  const float (&z)[kIn], float& out, uint32_t& mask0, uint32_t& mask1) {
   fence_after_sync();
   const float thr = sign_threshold(sh, z);
   float o = sh.bout;
@@ -261,9 +266,14 @@ __device__ __forceinline__ void hidden_epilogue(const Shared& sh, const float* _
 #pragma unroll
     for (int u = 0; u < 16; ++u) mn = fminf(mn, fabsf(__uint_as_float(r[u])));
     if (mn < thr) {  // rare: a sign too close to call from the split product
+#pragma unroll 1
+      for (int u = 0; u < 16; ++u) {
+        // r[] is indexed with a loop variable only on this cold path: select by predicate, no local memory
+        const float e = exact_pre<kH>(sm_dec, z, 16 * c + u);
 #pragma unroll
-      for (int u = 0; u < 16; ++u)
-        if (fabsf(__uint_as_float(r[u])) < thr) r[u] = __float_as_uint(exact_pre<kH>(sm_dec, z, 16 * c + u));
+        for (int v = 0; v < 16; ++v)
+          if (v == u && fabsf(__uint_as_float(r[v])) < thr) r[v] = __float_as_uint(e);
+      }
     }
     uint32_t bits = 0u;
     const float4* wo4 = reinterpret_cast<const float4*>(sh.wout + 16 * c);
@@ -275,23 +285,33 @@ __device__ __forceinline__ void hidden_epilogue(const Shared& sh, const float* _
       for (int v = 0; v < 4; ++v) {
         const int u = 4 * u4 + v;
         const float pre = __uint_as_float(r[u]);
-        const bool on = pre > 0.f;
-        o = fmaf(on ? wv[v] : wv[v] * slope, pre, o);
-        r[u] = on ? kOneBits : 0u;
-        bits |= on ? (1u << u) : 0u;
+        const float act = kLeaky ? fmaxf(pre, kLeakySlope * pre) : fmaxf(pre, 0.f);
+        o = fmaf(wv[v], act, o);
+        r[u] = __float_as_uint(pre > 0.f ? 1.0f : 0.0f);
+        if (kMask) bits |= pre > 0.f ? (1u << u) : 0u;
       }
     }
     tmem_st16(tlane + kColD1 + 16 * c, r);
-    if (c == 0) m0 = bits;
-    else if (c == 1) m0 |= bits << 16;
-    else if (c == 2) m1 = bits;
-    else m1 |= bits << 16;
+    if (kMask) {
+      if (c == 0) m0 = bits;
+      else if (c == 1) m0 |= bits << 16;
+      else if (c == 2) m1 = bits;
+      else m1 |= bits << 16;
+    }
   }
   tmem_wait_st();
   fence_before_sync();
   out = o;
   mask0 = m0;
   mask1 = m1;
+}
+
+template <bool kMask>
+__device__ __forceinline__ void hidden_epilogue(const Shared& sh, const float* __restrict__ sm_dec, uint32_t tlane,
+                                                const float (&z)[kIn], float slope, float& out, uint32_t& mask0,
+                                                uint32_t& mask1) {
+  if (slope == 0.f) hidden_epilogue_t<kMask, false>(sh, sm_dec, tlane, z, out, mask0, mask1);
+  else hidden_epilogue_t<kMask, true>(sh, sm_dec, tlane, z, out, mask0, mask1);
 }
 
 // one thread, after the CTA barrier that follows hidden_epilogue
@@ -342,7 +362,7 @@ __global__ void __launch_bounds__(128, 4) decoder_eval_tc_kernel(const __grid_co
   tc::Shared& sh = *reinterpret_cast<tc::Shared*>(smem);
   float* sm_dec = smem + (sizeof(tc::Shared) + 3) / 4;
   stage_decoder<tc::kH, 1>(sm_dec, p.dec);
-  const uint32_t tmem = tc::prologue(sh, p.dec);  // ends with a CTA barrier: sm_dec is visible too
+  const uint32_t tmem = tc::prologue(sh, sm_dec);
   const uint32_t tlane = tc::lane_base(tmem);
   const float slope = (p.flags & CLID_LEAKY_RELU) ? kLeakySlope : 0.f;
   const int64_t n_tiles = (p.n + 127) / 128;
@@ -358,7 +378,7 @@ __global__ void __launch_bounds__(128, 4) decoder_eval_tc_kernel(const __grid_co
     tc::mbar_wait_bounded(&sh.bar[0], parity);
     float out;
     uint32_t m0, m1;
-    tc::hidden_epilogue(sh, sm_dec, tlane, z, slope, out, m0, m1);
+    tc::hidden_epilogue<true>(sh, sm_dec, tlane, z, slope, out, m0, m1);
     __syncthreads();
     if (threadIdx.x == 0) tc::issue_layer2(sh, tmem);
     tc::mbar_wait_bounded(&sh.bar[1], parity);

@@ -29,6 +29,8 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // inst_query_{bricks,hashed}.cu
 int dispatch_query_bricks(const QueryParams& p, bool has_dec, cudaStream_t stream);
 int dispatch_query_hashed(const QueryParams& p, bool has_dec, cudaStream_t stream);
+// inst_query_tc.cu: 64 x 1 decoder on the tensor cores, brick index (CLID_TC_DECODER)
+int dispatch_query_tc(const QueryParams& p, cudaStream_t stream);
 // inst_query_bwd.cu
 int launch_query_backward_first(const QueryBwdParams& p, int grid, cudaStream_t stream);
 int launch_query_backward_second(const QueryBwdParams& p, int grid, cudaStream_t stream);

@@ -25,6 +25,11 @@ def brick_flags(bricks) -> int:
     """Flag bits that select the brick-index kernels for `bricks` (a BrickIndex)."""
     return _lib.USE_BRICKS
 
+# CLID_TC_DECODER=1: the brick-index forward evaluates 64 x 1 decoders on the tensor cores (tcgen05 + TMEM,
+# csrc/decoder_tc.cuh).  Parity-green and measured at the speed of the fp32 FMA decoder, not above it (the kernel is
+# bound by the latency of its gather chain, DESIGN.md section 5), so the FMA kernel stays the default.
+TC_DECODER = os.environ.get("CLID_TC_DECODER", "0") == "1"
+
 _COUNTERS = {}
 _COUNTER_POOLS = {}
 _POOL_SLOTS = 256
@@ -164,6 +169,8 @@ def forward(npm, decoder, x: torch.Tensor, ts: Optional[torch.Tensor], training_
         dec_struct = decoder.abi_struct()
         if decoder.use_leaky_relu:
             flags |= _lib.LEAKY_RELU
+        if TC_DECODER:
+            flags |= _lib.TC_DECODER  # taken by the library for 64 x 1 decoders on the brick index
     out = _lib.ClidQueryOut()
     res = {}
     f32 = dict(dtype=torch.float32, device=dev)

@@ -58,14 +58,19 @@ for reps in (20, 100):
 
 # diagnostics: where does the time go?  (a) far queries: no candidates at all (search ~free, MLP still runs)
 # (b) all queries identical: every load hits L1 (instruction-bound time of the full path)
-def bb(xq, reps=50):
+def bb(xq, reps=20):
+    # the launches are replayed from a CUDA graph: the Python / ctypes cost of a call (~20-50 us) is not in the number
     for _ in range(3):
         fused.sdf_and_gradient(npm, dec, xq, use_bricks=bool(args.bricks))
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            out = fused.sdf_and_gradient(npm, dec, xq, use_bricks=bool(args.bricks))
+    g.replay(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps):
-        fused.sdf_and_gradient(npm, dec, xq, use_bricks=bool(args.bricks))
+    g.replay()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps * 1e3
 far = x + 1000.0

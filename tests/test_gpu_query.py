@@ -49,15 +49,18 @@ def test_query_feature_matches_reference_fixture(name):
 
 
 def _kernel_family(monkeypatch, family):
-    """hashed: reference hash table; bricks: brick index with the 128-byte neighbourhood lines (the
-    default); headers: brick index read through its eight 16-byte headers.  Returns the use_bricks argument."""
+    """hashed: reference hash table; bricks: brick index with the 128-byte neighbourhood lines (the default);
+    headers: brick index read through its eight 16-byte headers; bricks-tc: the brick index with 64 x 1 decoders
+    on the tensor cores (tcgen05).  Returns the use_bricks argument."""
     from clid_slam_b200.ops import bricks as b
+    from clid_slam_b200.ops import query as qy
 
     monkeypatch.setattr(b, "USE_HOOD", family != "headers")
+    monkeypatch.setattr(qy, "TC_DECODER", family == "bricks-tc")
     return family != "hashed"
 
 
-FAMILIES = ["hashed", "bricks", "headers"]
+FAMILIES = ["hashed", "bricks", "headers", "bricks-tc"]
 
 
 @pytest.mark.parametrize("family", FAMILIES)
