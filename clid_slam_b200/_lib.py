@@ -83,6 +83,7 @@ class ClidTrainFusedArgs(C.Structure):
         ("weight_e", C.c_float), ("num_eps", C.c_float), ("weighted", C.c_int32), ("numerical", C.c_int32),
         ("gfeat", C.c_void_p), ("touched", C.c_void_p), ("dec_grad", C.c_void_p), ("loss", C.c_void_p),
         ("sdf_out", C.c_void_p), ("peer_grad", C.c_void_p * 2), ("peer_axis", C.c_int32), ("peer_band", C.c_int32 * 4),
+        ("peer_row", C.c_void_p * 2),
         ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t),
     ]
 

@@ -253,6 +253,7 @@ int clid_train_fused(const ClidMap* map, const ClidDecoder* dec, const ClidTrain
   p.weight_e = a->weight_e; p.weighted = a->weighted; p.flags = flags;
   for (int s = 0; s < 2; ++s) {
     p.peer_grad[s] = a->peer_grad[s];
+    p.peer_row[s] = a->peer_row[s];
     if (a->peer_grad[s] && !aligned16(a->peer_grad[s])) return set_error(CLID_EINVAL, "peer_grad must be 16-byte aligned");
   }
   if ((a->peer_grad[0] || a->peer_grad[1]) && (a->peer_axis < 0 || a->peer_axis > 2)) return set_error(CLID_EINVAL, "peer_axis %d", a->peer_axis);

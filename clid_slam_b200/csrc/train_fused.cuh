@@ -44,6 +44,7 @@ struct TrainFusedParams {
   float* peer_grad[2];   // gfeat of the lower / upper slab neighbour (peer-mapped) or NULL
   int peer_axis;
   int peer_band[4];      // inclusive cell ranges of the bands shared with the lower / upper neighbour
+  const int32_t* peer_row[2];  // partitioned map: local row -> the neighbour's row (-1: absent), or NULL (same numbering)
   int64_t n;
   int64_t n_norm;        // mean denominator of the bce term (global batch size when sharded)
   int64_t nd_norm;       // mean denominator of the numerical eikonal term (global decimated count)
@@ -353,8 +354,13 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
             red_add_row(p.gfeat, row[k], tt);
             if (p.touched) p.touched[row[k]] = 1;
             // band rows: the same contribution straight into the slab neighbour's gradient table (NVLink)
-            if (peer_bits & (1u << (2 * k))) red_add_row(p.peer_grad[0], row[k], tt);
-            if (peer_bits & (2u << (2 * k))) red_add_row(p.peer_grad[1], row[k], tt);
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+              if (peer_bits & ((1u << side) << (2 * k))) {
+                const int prow = p.peer_row[side] ? __ldg(p.peer_row[side] + row[k]) : row[k];
+                if (prow >= 0) red_add_row(p.peer_grad[side], prow, tt);
+              }
+            }
           }
         }
       }

@@ -99,6 +99,72 @@ def reduce_side_effects(certainty: torch.Tensor, certainty_before: torch.Tensor,
     dist.all_reduce(ts_update, op=dist.ReduceOp.MAX, group=group)
 
 
+def slab_boundaries(cell: torch.Tensor, world_size: int) -> torch.Tensor:
+    """[world-1] strictly increasing int64 cell coordinates that cut `cell` (the slab-axis voxel coordinate of
+    every point) into world_size slabs of equal point counts."""
+    dev = cell.device
+    if world_size <= 1 or cell.numel() == 0:
+        return torch.empty(0, dtype=torch.int64, device=dev)
+    q = torch.arange(1, world_size, device=dev, dtype=torch.float32) / world_size
+    srt = torch.sort(cell).values
+    pick = (q * (srt.numel() - 1)).long()
+    # a clustered map can repeat a quantile: keep exactly world-1 strictly increasing boundaries by bumping
+    # repeats (the slabs in between are then empty, which is valid)
+    bnd = srt[pick].tolist()
+    for i in range(1, len(bnd)):
+        if bnd[i] <= bnd[i - 1]:
+            bnd[i] = bnd[i - 1] + 1
+    return torch.tensor(bnd, dtype=torch.int64, device=dev)
+
+
+def axis_cells(points: torch.Tensor, resolution: float, axis: int) -> torch.Tensor:
+    from .utils.tools import ieee_div
+
+    return torch.floor(ieee_div(points[:, axis], float(resolution))).to(torch.int64)
+
+
+def partition_mask(points: torch.Tensor, resolution: float, axis: int, boundaries: torch.Tensor, rank: int,
+                   band: int) -> torch.Tensor:
+    """Points a rank of a PARTITIONED map holds: those of its own slab [b_rank, b_rank+1) plus the neighbours'
+    halves of its two boundary bands (`band` = reach + margin cells): every neural point a sample of the slab can
+    reach.  The selection is by voxel cell, so a voxel is held completely or not at all and every rank that holds
+    it derives the same neural point from it."""
+    cell = axis_cells(points, resolution, axis)
+    b = boundaries.tolist()
+    world_size = len(b) + 1
+    keep = torch.ones(cell.shape, dtype=torch.bool, device=cell.device)
+    if rank > 0:
+        keep &= cell >= b[rank - 1] - band
+    if rank < world_size - 1:
+        keep &= cell <= b[rank] + band - 1
+    return keep
+
+
+def hash_owner_mask(slots: torch.Tensor, buffer_size: int) -> torch.Tensor:
+    """Which of the points inserted in this order end up OWNING their voxel-hash slot (the last writer of a slot
+    wins, NeuralPoints._store_slots): the reference reaches a neural point only through its slot, so a point that
+    lost its slot to a colliding voxel is dead weight.  A partitioned map is cut from the owners only -- with the
+    losers dropped on every rank, each rank's private hash table answers every probe exactly like the one global
+    table of a single process would (a collision whose two voxels sit on different ranks would otherwise keep
+    both alive)."""
+    slots = torch.remainder(slots, int(buffer_size))
+    srt, perm = torch.sort(slots, stable=True)
+    last = torch.ones(srt.shape, dtype=torch.bool, device=slots.device)
+    last[:-1] = srt[1:] != srt[:-1]
+    keep = torch.zeros(slots.shape, dtype=torch.bool, device=slots.device)
+    keep[perm[last]] = True
+    return keep
+
+
+def voxel_keys(points: torch.Tensor, resolution: float) -> torch.Tensor:
+    """One int64 per point that identifies its voxel (21 bits per axis): the rank-independent name of a neural
+    point of a partitioned map."""
+    from .utils.tools import ieee_div
+
+    c = torch.floor(ieee_div(points, float(resolution))).to(torch.int64) + (1 << 20)
+    return (c[:, 0] << 42) | (c[:, 1] << 21) | c[:, 2]
+
+
 class SpatialShards:
     """Slab partition of the local map along one axis, in voxel units.
 
@@ -124,19 +190,7 @@ class SpatialShards:
 
         cell = torch.floor(ieee_div(points[:, axis], self.resolution)).to(torch.int64)
         if boundaries is None:
-            if world_size > 1:
-                q = torch.arange(1, world_size, device=dev, dtype=torch.float32) / world_size
-                srt = torch.sort(cell).values
-                pick = (q * (srt.numel() - 1)).long()
-                # equal point counts per slab; a clustered map can repeat a quantile: keep exactly world-1 strictly
-                # increasing boundaries by bumping repeats (the slabs in between are then empty, which is valid)
-                bnd = srt[pick].tolist()
-                for i in range(1, len(bnd)):
-                    if bnd[i] <= bnd[i - 1]:
-                        bnd[i] = bnd[i - 1] + 1
-                boundaries = torch.tensor(bnd, dtype=torch.int64, device=dev)
-            else:
-                boundaries = torch.empty(0, dtype=torch.int64, device=dev)
+            boundaries = slab_boundaries(cell, world_size)
         self.boundaries = boundaries.to(device=dev, dtype=torch.int64).contiguous()
         band = reach + margin
         self.band = int(band)
@@ -180,6 +234,69 @@ class SpatialShards:
         contrib = torch.where(mine, features, torch.zeros_like(features))
         dist.all_reduce(contrib, op=dist.ReduceOp.SUM, group=group)
         features.copy_(contrib)
+
+
+def peer_row_tables(shards: SpatialShards, rank: int, points: torch.Tensor, rows_total: int, group=None):
+    """Row translation of a PARTITIONED map (ClidTrainFusedArgs.peer_row): (lower, upper) int32 [rows_total] tables
+    giving, for every local row in the band shared with the lower / upper slab neighbour, that neural point's row
+    in the neighbour's table (-1 elsewhere); None on the sides without a neighbour.  `points` is this rank's
+    local neural-point table.  Both sides of a boundary hold exactly the voxels of its band, so sorting the band
+    rows by voxel key gives both ranks the same order; the row lists travel once through torch.distributed."""
+    _, world_size = world()
+    left, right = shards.neighbour_rows(rank)
+    mine = []
+    for rows in (left, right):
+        if rows is None:
+            mine.append(None)
+            continue
+        key = voxel_keys(points[rows], shards.resolution)
+        order = torch.argsort(key)
+        mine.append((key[order].cpu(), rows[order].to(torch.int32).cpu()))
+    table = [None] * world_size
+    if world_size > 1:
+        dist.all_gather_object(table, mine, group=group)
+    else:
+        table[0] = mine
+    out = []
+    for side, peer in ((0, rank - 1), (1, rank + 1)):
+        if mine[side] is None or peer < 0 or peer >= world_size:
+            out.append(None)
+            continue
+        theirs = table[peer][1 - side]  # my lower band is the neighbour's upper band
+        if theirs is None or not torch.equal(theirs[0], mine[side][0]):
+            raise RuntimeError(f"rank {rank} and rank {peer} hold different voxels in the band they share: the "
+                               "partitions were not cut from the same map")
+        tab = torch.full((rows_total,), -1, dtype=torch.int32, device=points.device)
+        tab[mine[side][1].to(points.device).long()] = theirs[1].to(points.device)
+        out.append(tab)
+    return tuple(out)
+
+
+def exchange_band_values(shards: SpatialShards, rank: int, points: torch.Tensor, values: torch.Tensor, op: str,
+                         group=None) -> None:
+    """Once per mapping() call on a PARTITIONED map: complete the per-row side effects of the band rows with the
+    slab neighbours' (op 'sum': certainty increments, 'max': ts_update).  `values` [rows] is updated in place."""
+    _, world_size = world()
+    if world_size == 1:
+        return
+    left, right = shards.neighbour_rows(rank)
+    mine = []
+    for rows in (left, right):
+        if rows is None:
+            mine.append(None)
+            continue
+        order = torch.argsort(voxel_keys(points[rows], shards.resolution))
+        mine.append((rows[order], values[rows[order]].cpu()))
+    table = [None] * world_size
+    dist.all_gather_object(table, [None if m is None else m[1] for m in mine], group=group)
+    for side, peer in ((0, rank - 1), (1, rank + 1)):
+        if mine[side] is None or peer < 0 or peer >= world_size or table[peer][1 - side] is None:
+            continue
+        rows, theirs = mine[side][0], table[peer][1 - side].to(values.device)
+        if op == "sum":
+            values[rows] += theirs
+        else:
+            values[rows] = torch.maximum(values[rows], theirs)
 
 
 class NeighbourExchange:
@@ -256,7 +373,14 @@ class PeerLink:
             raise ValueError("PeerLink covers one box (<= 8 GPUs)")
         self.device = torch.device(device)
         self.stride = (int(n_small) + 31) // 32 * 32
-        grad_bytes = (rows * feat_dim * 4 + 255) // 256 * 256
+        # every rank lays its allocation out alike (a rank addresses its peers' buffers by offset): with a PARTITIONED
+        # map the ranks' tables differ in length, so the layout follows the longest one
+        layout_rows = int(rows)
+        if self.world > 1:
+            all_rows = [None] * self.world
+            dist.all_gather_object(all_rows, int(rows), group=group)
+            layout_rows = max(all_rows)
+        grad_bytes = (layout_rows * feat_dim * 4 + 255) // 256 * 256
         slots_bytes = (max(self.world, 1) * self.stride * 4 + 255) // 256 * 256
         self._off = {"grad0": 0, "grad1": grad_bytes, "slots": 2 * grad_bytes, "flags": 2 * grad_bytes + slots_bytes}
         total = 2 * grad_bytes + slots_bytes + 256

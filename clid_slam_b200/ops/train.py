@@ -141,6 +141,7 @@ class FusedTrainer:
         # multi-GPU over peer memory (attach_peers): dist.PeerLink + the slab geometry of this rank
         self.peer = None
         self._peer_geom = None
+        self._peer_rows = None
 
     # ------------------------------------------------------------------
     def _shifted(self, x: torch.Tensor, eik_index: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -319,10 +320,12 @@ class FusedTrainer:
         return loss
 
     # ------------------------------------------------------------------ multi-GPU over peer memory
-    def attach_peers(self, shards, group=None) -> None:
+    def attach_peers(self, shards, group=None, peer_rows=None) -> None:
         """Spatially sharded training without NCCL on the data path (dist.PeerLink): the fused kernel adds
         boundary-band gradients straight into the slab neighbours' tables over NVLink, [decoder gradients | loss]
-        are all-reduced by a one-shot peer-memory kernel pair, everything stays inside the step's CUDA graph."""
+        are all-reduced by a one-shot peer-memory kernel pair, everything stays inside the step's CUDA graph.
+        peer_rows: (lower, upper) row-translation tables of a PARTITIONED map (dist.peer_row_tables); None when every
+        rank holds the whole map (rows are numbered alike)."""
         from .. import dist as _dist
 
         rank, world = _dist.world()
@@ -335,6 +338,7 @@ class FusedTrainer:
         lo = (b[rank - 1] - reach_band, b[rank - 1] + reach_band - 1) if rank > 0 else None
         hi = (b[rank] - reach_band, b[rank] + reach_band - 1) if rank < world - 1 else None
         self._peer_geom = (int(shards.axis), lo, hi, rank, world)
+        self._peer_rows = peer_rows  # kept alive: the kernels read them every step
         if self.touched is not None:  # band rows may receive gradient from the neighbour only
             left, right = shards.neighbour_rows(rank)
             for rows in (left, right):
@@ -352,6 +356,12 @@ class FusedTrainer:
         if hi is not None:
             a.peer_grad[1] = self.peer.grad_ptr(rank + 1, parity)
             a.peer_band[2], a.peer_band[3] = hi
+        if self._peer_rows is not None:
+            for side, tab in enumerate(self._peer_rows):
+                if tab is not None:
+                    if tab.numel() != self.rows or tab.dtype != torch.int32:
+                        raise ValueError("peer_rows tables must be int32 [rows of the local feature table + padding]")
+                    a.peer_row[side] = tab.data_ptr()
 
     def _peer_all_reduce(self, loss: torch.Tensor) -> None:
         """[decoder gradients | loss] summed over ranks through peer memory (also the barrier after which every

@@ -43,3 +43,23 @@ def sample_batch(anchor_points: torch.Tensor, n: int, generator: torch.Generator
     weight = torch.where(is_front | is_behind, -weight, weight)
     ts = torch.zeros(n, dtype=torch.int32, device=dev)
     return x.contiguous(), label, weight, ts
+
+
+def voxel_features(points: torch.Tensor, resolution: float, dim: int, std: float) -> torch.Tensor:
+    """[n, dim] pseudo-random features that are a function of each point's VOXEL only (not of its row or of the
+    generator state): ranks of a partitioned map that hold the same voxel initialise it alike."""
+    from .utils.tools import ieee_div
+
+    c = torch.floor(ieee_div(points, float(resolution)))
+    ch = torch.arange(dim, device=points.device, dtype=torch.float32)
+    phase = c[:, 0:1] * 12.9898 + c[:, 1:2] * 78.233 + c[:, 2:3] * 37.719 + ch * 1.618
+    return std * 1.41421 * torch.sin(phase * 43.0)
+
+
+def set_voxel_features(npm, std: float) -> None:
+    """Overwrite the map's (global and local-window) geometric features with voxel_features."""
+    d = npm.geo_feature_dim
+    with torch.no_grad():
+        npm.geo_features[:-1] = voxel_features(npm.neural_points, npm.resolution, d, std)
+        npm.local_geo_features.data[:-1] = voxel_features(npm.local_neural_points, npm.resolution, d, std)
+    npm._touch()

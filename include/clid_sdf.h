@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CLID_ABI_VERSION 3
+#define CLID_ABI_VERSION 4
 #define CLID_MAX_LEVELS 3   /* hidden layers of the decoder MLP */
 #define CLID_MAX_KNN 8      /* query_nn_k */
 #define CLID_MAX_KC 256     /* probed cells per query */
@@ -265,6 +265,10 @@ typedef struct ClidTrainFusedArgs {
   int32_t peer_axis;     /* 0..2: axis the slabs are cut along                                                   */
   int32_t peer_band[4];  /* inclusive cell ranges [lo0, lo1] / [hi0, hi1] of the band shared with the lower /
                             upper neighbour, in voxel cells floor(p[axis] / resolution) of the NEURAL POINT       */
+  const int32_t* peer_row[2]; /* PARTITIONED map (every rank holds only its slab plus the neighbours' halves of its
+                            bands, so the same neural point has a different row on either side): [n_gather+1]
+                            row of each local row in the lower / upper neighbour's table, -1 where the neighbour
+                            does not hold it.  NULL: the tables are replicated, rows are numbered alike.      */
   void* scratch;         /* clid_train_fused_scratch_bytes(n, numerical) bytes of device scratch, or NULL.
                             With it every evaluated point writes its 64-byte decoder-gradient row
                             [delta z + s tau ; delta | activation bits] there and the caller reduces the

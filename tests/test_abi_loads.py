@@ -31,7 +31,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_version_and_error_string(lib):
-    assert lib.clid_version() == 3
+    assert lib.clid_version() == 4
     rc = lib.clid_query_forward(None, None, None, None, 5, 0, None, None)
     assert rc == -1
     assert b"NULL" in lib.clid_last_error()
