@@ -16,11 +16,14 @@ loops are timed with CUDA events, the L2 flushed before every step: device-resid
 host-pinned inputs staged every step with the loss read back every step (`e2e`), and a call-by-call
 replay with events around the dominant kernel (`roofline`).
 
-For N > 1 launch with torchrun (one rank per GPU): samples and neural points are sharded by map slab,
-every rank takes 131072 samples of its slab per step (weak scaling); per step one 3 kB NCCL all-reduce
-[decoder gradients | loss] and a neighbour send/recv of the boundary-band feature gradients
-(clid_slam_b200/dist.py).  `--sharding replicated` keeps the map replicated and all-reduces the dense
-feature gradient instead.
+For N > 1 launch with torchrun (one rank per GPU): samples and neural points are partitioned by map slab -- every
+rank builds and holds only its slab plus the neighbours' halves of its boundary bands (per-rank memory ~ M/N + halo)
+and takes 131072 samples of its slab per step (weak scaling).  Boundary-band feature gradients are added straight
+into the slab neighbour's table by the fused kernel over NVLink peer memory (rows translated into its numbering),
+[decoder gradients | loss] are all-reduced by a one-shot peer-memory kernel pair, the step is one CUDA graph, no NCCL
+on the data path (clid_slam_b200/dist.py).  `--sharding peer` keeps the whole map on every rank, `--sharding spatial`
+exchanges through NCCL, `--sharding replicated` all-reduces the dense feature gradient.  `--workload subt` is
+BASELINE configs[4] (4 M neural points, SubT-MRS shapes).
 """
 from __future__ import annotations
 
@@ -38,6 +41,7 @@ sys.path.insert(0, ROOT)
 
 BATCH = 131072
 SIDE, SHEETS = 520, 4
+SUBT_SIDE = 1000  # 4 sheets x 1000^2 = 4 M neural points (BASELINE configs[4])
 L2_FLUSH_BYTES = 256 << 20
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
@@ -56,11 +60,16 @@ def parse_args():
                          "total, split over the GPUs (strong)")
     ap.add_argument("--no-shipped-config", action="store_true", help="skip the configs[1] leg (process_frame + mapping(10))")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity gate against the oracle")
-    ap.add_argument("--sharding", default="peer", choices=["peer", "spatial", "replicated"],
-                    help="N > 1: slab-partitioned samples and neural points; 'peer' (default): band gradients added straight "
+    ap.add_argument("--workload", default="configs2", choices=["configs2", "subt"],
+                    help="configs2 (default, the configuration the metric is quoted on): 1.08 M neural points, ncd128 shapes; "
+                         "subt: BASELINE configs[4], 4 M neural points, SubT-MRS shapes (LayerNorm on the features)")
+    ap.add_argument("--sharding", default="partition", choices=["peer", "partition", "spatial", "replicated"],
+                    help="N > 1: slab-partitioned samples and neural points; 'peer': every rank holds the whole map, band gradients added straight "
                          "into the slab neighbours' tables by the fused kernel and [decoder grads | loss] all-reduced by a "
                          "one-shot kernel pair, both over NVLink peer memory, one CUDA graph per step, no NCCL on the data "
-                         "path; 'spatial': NCCL all-reduce + neighbour send/recv between two graphs; 'replicated': "
+                         "path; 'partition' (default): the same step on a PARTITIONED map -- every rank builds and holds only its slab "
+                         "plus the halves of its boundary bands (per-rank memory ~ M/N + halo), band rows translated into "
+                         "the neighbour's numbering; 'spatial': NCCL all-reduce + neighbour send/recv between two graphs; 'replicated': "
                          "any-sample-anywhere with a dense feature-gradient all-reduce")
     return ap.parse_args()
 
@@ -126,28 +135,50 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ native arm
-def build_world(device, mode):
+def build_world(device, mode, workload="configs2", partition=None):
+    """The synthetic world of the benchmark.  partition = (rank, world): build only this rank's part of the map (its
+    slab plus the neighbours' halves of its boundary bands, cut from the hash-slot owners of the one-point-per-voxel
+    cloud, clid_slam_b200/dist.py) -- no rank ever holds the whole neural-point table."""
     import torch
 
     from clid_slam_b200.config import ncd128
     from clid_slam_b200.model.decoder import Decoder
     from clid_slam_b200.model.neural_points import NeuralPoints
-    from clid_slam_b200.synth import wavy_sheets
+    from clid_slam_b200.synth import set_voxel_features, wavy_sheets
 
     torch.manual_seed(42)
     cfg = ncd128()
     cfg.device = device
     cfg.feature_std = 0.05          # the default 0.0 makes every feature exactly zero (SURVEY 8c gotchas)
-    cfg.local_map_radius = 1.0e4    # the whole ~1 M-point map is the local window (configs[2])
+    cfg.local_map_radius = 1.0e4    # the whole map is the local window (configs[2])
     cfg.numerical_grad = mode == "numerical"
     cfg.gradient_decimation = 10 if cfg.numerical_grad else 1
+    side = SIDE
+    if workload == "subt":          # config/run_SubT_MRS.yaml: ncd128 shapes + layer_norm_on, 4 M neural points
+        cfg.layer_norm_on = True
+        cfg.free_sample_begin_ratio = 0.8
+        side = SUBT_SIDE
     dec = Decoder(cfg, cfg.geo_mlp_hidden_dim, cfg.geo_mlp_level, 1)
     npm = NeuralPoints(cfg)
     npm.travel_dist = torch.zeros(1, device=device)
     gen = torch.Generator(device=device).manual_seed(1)
-    pts = wavy_sheets(SIDE, SHEETS, cfg.voxel_size_m, gen, device=device)
+    pts = wavy_sheets(side, SHEETS, cfg.voxel_size_m, gen, device=device)
+    geom = None
+    if partition is not None:
+        from clid_slam_b200.dist import axis_cells, hash_owner_mask, partition_mask, slab_boundaries
+        from clid_slam_b200.utils.tools import voxel_down_sample_torch
+
+        rank, world = partition
+        pts = pts[voxel_down_sample_torch(pts, cfg.voxel_size_m)]
+        pts = pts[hash_owner_mask(npm._slots_of(pts), npm.buffer_size)]
+        axis = int(torch.argmax(pts.amax(0) - pts.amin(0)).item())
+        bnd = slab_boundaries(axis_cells(pts, cfg.voxel_size_m, axis), world)
+        geom = (axis, bnd, int(pts.shape[0]))
+        pts = pts[partition_mask(pts, cfg.voxel_size_m, axis, bnd, rank, cfg.num_nei_cells + 1)].contiguous()
     npm.update(pts, torch.zeros(3, device=device), torch.eye(3, device=device), 0)
-    return cfg, dec, npm
+    if partition is not None:
+        set_voxel_features(npm, cfg.feature_std)  # a function of the voxel: every rank that holds it starts alike
+    return cfg, dec, npm, geom
 
 
 def _xlwt(batch):
@@ -196,16 +227,21 @@ def run_native(args):
         dist.barrier()
     _lib.load()
 
-    cfg, dec, npm = build_world(device, args.mode)
+    partitioned = world > 1 and args.sharding == "partition"
+    cfg, dec, npm, geom = build_world(device, args.mode, args.workload, (rank, world) if partitioned else None)
     gen = torch.Generator(device=device).manual_seed(1000 + rank)
     n_batches = 4  # rotate a few batches so no step sees the previous step's exact access pattern
     shards = None
-    if world > 1 and args.sharding in ("spatial", "peer"):
+    if world > 1 and args.sharding in ("spatial", "peer", "partition"):
         # slab partition along the longest map axis; a rank's samples are those whose voxel lies in
         # its slab (what a per-rank replay pool would hand out), see clid_slam_b200/dist.py
         from clid_slam_b200.dist import SpatialShards
 
-        shards = SpatialShards(npm.local_neural_points, cfg.voxel_size_m, reach=cfg.num_nei_cells, world_size=world)
+        if partitioned:
+            shards = SpatialShards(npm.local_neural_points, cfg.voxel_size_m, reach=cfg.num_nei_cells, world_size=world,
+                                   axis=geom[0], boundaries=geom[1])
+        else:
+            shards = SpatialShards(npm.local_neural_points, cfg.voxel_size_m, reach=cfg.num_nei_cells, world_size=world)
         own_points = npm.neural_points[shards.row_owner[:-1] == rank]
         batches = []
         for _ in range(n_batches):
@@ -241,8 +277,12 @@ def run_native(args):
         parity = parity_gate(npm, dec, cfg, *_xlwt(batches[0]))
 
     trainer = FusedTrainer(cfg, npm, dec)
-    peer_mode = world > 1 and args.sharding == "peer"
-    if peer_mode:
+    peer_mode = world > 1 and args.sharding in ("peer", "partition")
+    if partitioned:
+        from clid_slam_b200.dist import peer_row_tables
+
+        trainer.attach_peers(shards, peer_rows=peer_row_tables(shards, rank, npm.local_neural_points, trainer.rows))
+    elif peer_mode:
         trainer.attach_peers(shards)
     n_global = BATCH * world
     nd_global = 0
@@ -434,6 +474,12 @@ def run_native(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms = float(t[0]), float(t[1])
+    map_rows_per_rank = [int(npm.count())]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, int(npm.count()))
+        map_rows_per_rank = gathered
+    map_rows_total = geom[2] if partitioned else int(npm.count())
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -466,12 +512,23 @@ def run_native(args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": "BASELINE configs[2]: 131072 samples/batch/GPU, 1.08M neural points (4 wavy sheets, "
-                            "0.4 m voxels), ncd128 decoder 11->64->1, Kc=81, K=6, brick index, "
-                            f"{args.mode} eikonal gradient",
-                "samples_per_step": samples_per_step, "neural_points": int(npm.count()),
+                "workload": ("BASELINE configs[2]: 131072 samples/batch/GPU, 1.08M neural points (4 wavy sheets, "
+                             "0.4 m voxels), ncd128 decoder 11->64->1, Kc=81, K=6, brick index, "
+                             f"{args.mode} eikonal gradient" if args.workload == "configs2" else
+                             f"BASELINE configs[4]: SubT-MRS shapes (ncd128 decoder 11->64->1, LayerNorm on the features, "
+                             f"0.4 m voxels, Kc=81, K=6), {map_rows_total} neural points in total (4 wavy sheets), "
+                             f"{BATCH} samples/batch/GPU, brick index, {args.mode} eikonal gradient"),
+                "samples_per_step": samples_per_step, "neural_points": map_rows_total,
+                "neural_points_per_rank": map_rows_per_rank,
                 "mean_valid_candidates": mean_nn, "l2": "flushed before every timed step (256 MiB write, then 256 MiB read so evictions are clean)",
                 "parallelism": ("single GPU" if world == 1 else
+                                f"x{world}: PARTITIONED map -- every rank builds and holds only its slab plus the neighbours' "
+                                f"halves of its boundary bands ({map_rows_per_rank} rows per rank of {map_rows_total} in "
+                                f"total), samples belong to the rank of their slab; boundary-band feature gradients are "
+                                f"added into the slab neighbour's table (rows translated into its numbering) by the fused "
+                                f"kernel over NVLink peer memory, [decoder grads | loss] all-reduced by a one-shot "
+                                f"peer-memory kernel pair, one CUDA graph per step, no NCCL on the data path"
+                                if partitioned else
                                 f"x{world}: samples and neural points sharded by map slab; boundary-band feature gradients "
                                 f"({int(shards.shared_rows.numel())} band rows in total) are added into the slab neighbour's "
                                 f"table by the fused kernel over NVLink peer memory, [decoder grads | loss] all-reduced by a "

@@ -10,7 +10,7 @@ from clid_slam_b200.synth import sample_batch
 rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"]); world = int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(local); device = f"cuda:{local}"
 dist.init_process_group("nccl", device_id=torch.device(device))
-cfg, dec, npm = B.build_world(device, "analytic")
+cfg, dec, npm, _ = B.build_world(device, "analytic")
 gen = torch.Generator(device=device).manual_seed(1000 + rank)
 shards = SpatialShards(npm.local_neural_points, cfg.voxel_size_m, reach=cfg.num_nei_cells, world_size=world)
 own = npm.neural_points[shards.row_owner[:-1] == rank]

@@ -19,7 +19,7 @@ def test_parity_gate_on_the_benchmark_world(mode):
     from clid_slam_b200.synth import sample_batch
     from oracle.bridge import TOL, parity_gate
 
-    cfg, dec, npm = bench.build_world("cuda:0", mode)
+    cfg, dec, npm, _ = bench.build_world("cuda:0", mode)
     assert npm.count() > 1_000_000 and int(npm.buffer_size) == 50_000_000
     gen = torch.Generator(device="cuda:0").manual_seed(1000)
     x, label, weight, ts = sample_batch(npm.neural_points, 16384, gen)

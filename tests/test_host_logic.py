@@ -334,3 +334,72 @@ def test_slab_boundaries_of_a_clustered_map_stay_strictly_increasing():
     assert len(shards.band_rows) == 3
     owner = shards.owner_of(pts)
     assert int(owner.min()) >= 0 and int(owner.max()) <= 3
+
+
+def test_hash_owner_mask_keeps_the_last_writer_of_every_slot():
+    slots = torch.tensor([5, 3, 5, 7, 3, 3, -2, 8])
+    keep = cdist.hash_owner_mask(slots, 10)  # -2 wraps to slot 8: the later point wins it
+    assert keep.tolist() == [False, False, True, True, False, True, False, True]
+
+
+def _partition_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        gen = torch.Generator().manual_seed(3)
+        # one point per voxel of a 60 x 9 x 2 slab of space, in scrambled insertion order (the same on every rank)
+        gx, gy, gz = torch.meshgrid(torch.arange(60), torch.arange(9), torch.arange(2), indexing="ij")
+        cells = torch.stack((gx, gy, gz), -1).reshape(-1, 3).float()
+        pts = (cells + 0.1 + 0.8 * torch.rand(cells.shape, generator=gen))[torch.randperm(cells.shape[0], generator=gen)]
+        res, reach = 1.0, 2
+        axis = 0
+        bnd = cdist.slab_boundaries(cdist.axis_cells(pts, res, axis), world)
+        mine = pts[cdist.partition_mask(pts, res, axis, bnd, rank, reach + 1)]
+        shards = cdist.SpatialShards(mine, res, reach=reach, world_size=world, axis=axis, boundaries=bnd)
+        tabs = cdist.peer_row_tables(shards, rank, mine, mine.shape[0] + 1)
+        # certainty-like side effect: every rank adds (rank + 1) to the band rows it shares, then the bands are completed
+        delta = torch.zeros(mine.shape[0])
+        for rows in shards.neighbour_rows(rank):
+            if rows is not None:
+                delta[rows] += float(rank + 1)
+        cdist.exchange_band_values(shards, rank, mine, delta, "sum")
+        torch.save({"points": mine, "tabs": tabs, "owner": shards.row_owner, "bnd": bnd, "delta": delta,
+                    "bands": shards.neighbour_rows(rank)}, os.path.join(out_dir, f"p{rank}.pt"))
+    finally:
+        torch.distributed.destroy_process_group()
+
+
+def test_partitioned_map_tables_and_row_translation_with_three_gloo_ranks():
+    """Every rank holds its slab plus the halves of its bands; the owned rows tile the map; the translation tables map a
+    band row to the row of the SAME voxel in the neighbour's table and are -1 everywhere else."""
+    world = 3
+    port = 33500 + os.getpid() % 2000
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_partition_worker, args=(world, port, tmp), nprocs=world, join=True)
+        outs = [torch.load(os.path.join(tmp, f"p{r}.pt")) for r in range(world)]
+    total = 60 * 9 * 2
+    owned = [o["points"][o["owner"][:-1] == r] for r, o in enumerate(outs)]
+    keys = torch.cat([cdist.voxel_keys(p, 1.0) for p in owned])
+    assert keys.numel() == total and torch.unique(keys).numel() == total  # tiles the map, nothing twice
+    assert all(o["points"].shape[0] < 0.6 * total for o in outs)          # nobody holds the whole map
+    for r, o in enumerate(outs):
+        lo, hi = o["tabs"]
+        assert (lo is None) == (r == 0) and (hi is None) == (r == world - 1)
+        for tab, peer in ((lo, r - 1), (hi, r + 1)):
+            if tab is None:
+                continue
+            assert tab.dtype == torch.int32 and tab.numel() == o["points"].shape[0] + 1 and int(tab[-1]) == -1
+            rows = torch.nonzero(tab >= 0).flatten()
+            band = 3 * 2 * 9 * 2  # (reach + margin) cells either side of the boundary, 9 x 2 voxels per cell layer
+            assert rows.numel() == band
+            mine_keys = cdist.voxel_keys(o["points"][rows], 1.0)
+            theirs_keys = cdist.voxel_keys(outs[peer]["points"][tab[rows].long()], 1.0)
+            assert torch.equal(mine_keys, theirs_keys)
+        # band side effects: both contributors' increments on both sides, nothing on private rows
+        left, right = o["bands"]
+        expect = torch.zeros(o["points"].shape[0])
+        if left is not None:
+            expect[left] += float(r + 1) + float(r)
+        if right is not None:
+            expect[right] += float(r + 1) + float(r + 2)
+        assert torch.equal(o["delta"], expect)
