@@ -363,7 +363,8 @@ class PeerLink:
     belongs to the importing device with lazy peer access to the exporter -- memory imported under another
     device's context is not reachable from this device's kernels."""
 
-    def __init__(self, rows: int, feat_dim: int, n_small: int, device: torch.device, group=None):
+    def __init__(self, rows: int, feat_dim: int, n_small: int, device: torch.device, group=None,
+                 capacity_rows: Optional[int] = None):
         import ctypes as C
 
         from . import _lib
@@ -375,11 +376,13 @@ class PeerLink:
         self.stride = (int(n_small) + 31) // 32 * 32
         # every rank lays its allocation out alike (a rank addresses its peers' buffers by offset): with a PARTITIONED
         # map the ranks' tables differ in length, so the layout follows the longest one
-        layout_rows = int(rows)
+        # capacity_rows > rows: room for view_rows() to follow a table that changes from call to call (Mapper)
+        layout_rows = max(int(rows), int(capacity_rows or 0))
         if self.world > 1:
             all_rows = [None] * self.world
-            dist.all_gather_object(all_rows, int(rows), group=group)
+            dist.all_gather_object(all_rows, layout_rows, group=group)
             layout_rows = max(all_rows)
+        self.capacity_rows, self.feat_dim, self.group = layout_rows, int(feat_dim), group
         grad_bytes = (layout_rows * feat_dim * 4 + 255) // 256 * 256
         slots_bytes = (max(self.world, 1) * self.stride * 4 + 255) // 256 * 256
         self._off = {"grad0": 0, "grad1": grad_bytes, "slots": 2 * grad_bytes, "flags": 2 * grad_bytes + slots_bytes}
@@ -424,6 +427,41 @@ class PeerLink:
                     self.base_of[r] = int(ptr.value)
             torch.cuda.synchronize(self.device)
             dist.barrier(group=group)  # nobody publishes before everybody has opened everything
+
+    def view_rows(self, rows: int) -> None:
+        """Re-shape the two gradient tables for a feature table of `rows` rows (<= capacity_rows) and clear them.
+        Collective: every rank calls it between steps (the barrier keeps a neighbour's late remote adds of the
+        previous call out of the cleared tables)."""
+        if rows > self.capacity_rows:
+            raise ValueError(f"{rows} rows exceed the link's capacity of {self.capacity_rows}")
+        if self.world > 1:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+        nbytes = rows * self.feat_dim * 4
+        self.grad = [self.buf[self._off[k]:self._off[k] + nbytes].view(torch.float32).view(rows, self.feat_dim)
+                     for k in ("grad0", "grad1")]
+        for g in self.grad:
+            g.zero_()
+        if self.world > 1:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+
+    def close(self) -> None:
+        """Unmap the peers' allocations and free this rank's (collective: nobody may still be stepping)."""
+        from . import _lib
+
+        lib = _lib.load()
+        if self.world > 1:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+        with torch.cuda.device(self.device):
+            for ptr in self._opened:
+                lib.clid_ipc_close(ptr)
+            self._opened = []
+            if self._base:
+                self.grad, self.slots, self.flags, self.buf = [], None, None, None
+                lib.clid_peer_free(self._base)
+                self._base = 0
 
     def ptr(self, rank: int, name: str) -> int:
         """Device address of buffer `name` ('grad0' | 'grad1' | 'slots' | 'flags') of `rank`, valid on this device."""

@@ -320,19 +320,26 @@ class FusedTrainer:
         return loss
 
     # ------------------------------------------------------------------ multi-GPU over peer memory
-    def attach_peers(self, shards, group=None, peer_rows=None) -> None:
+    def attach_peers(self, shards, group=None, peer_rows=None, link=None) -> None:
         """Spatially sharded training without NCCL on the data path (dist.PeerLink): the fused kernel adds
         boundary-band gradients straight into the slab neighbours' tables over NVLink, [decoder gradients | loss]
         are all-reduced by a one-shot peer-memory kernel pair, everything stays inside the step's CUDA graph.
         peer_rows: (lower, upper) row-translation tables of a PARTITIONED map (dist.peer_row_tables); None when every
-        rank holds the whole map (rows are numbered alike)."""
+        rank holds the whole map (rows are numbered alike).  link: an existing dist.PeerLink to reuse (Mapper keeps
+        one across mapping() calls; its tables are re-shaped to this trainer's rows)."""
         from .. import dist as _dist
 
         rank, world = _dist.world()
         if not shards.pairwise:
             raise ValueError("slabs narrower than two bands: a band row would have three contributors")
         n_small = (self.dec_grad.numel() if self.dec_grad is not None else 0) + 3
-        self.peer = _dist.PeerLink(self.rows, self.feat_grad.shape[1], n_small, self.device, group=group)
+        if link is not None:
+            if link.stride < n_small:
+                raise ValueError("the PeerLink's all-reduce slots are too short for this decoder")
+            link.view_rows(self.rows)
+            self.peer = link
+        else:
+            self.peer = _dist.PeerLink(self.rows, self.feat_grad.shape[1], n_small, self.device, group=group)
         b = shards.boundaries.tolist()
         reach_band = shards.band
         lo = (b[rank - 1] - reach_band, b[rank - 1] + reach_band - 1) if rank > 0 else None

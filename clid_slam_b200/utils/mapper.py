@@ -64,6 +64,12 @@ class Mapper:
         self.native_loop = os.environ.get("CLID_NATIVE_LOOP", "1") != "0"
         self.last_losses = None        # [iters,3] device tensor (total, bce, eikonal) of the last mapping() call
         self.last_host_ms = None       # host wall time of the last native-loop mapping() call: set-up / loop enqueue
+        # multi-GPU (one process per GPU, set_shards): slab partition of the CURRENT local map and, for a partitioned
+        # map, the band-row translation tables; the peer-memory link is kept across mapping() calls
+        self.shards = None
+        self.shard_peer_rows = None
+        self.shard_group = None
+        self._peer_link = None
 
         dev, f32 = self.device, self.dtype
         self.coord_pool = torch.empty((0, 3), device=dev, dtype=f32)
@@ -262,6 +268,64 @@ class Mapper:
 
     train = mapping  # BASELINE.json's name for the same entry point
 
+    # ------------------------------------------------------------------ multi-GPU
+    def set_shards(self, shards, peer_rows=None, group=None) -> None:
+        """Run mapping() sharded over the ranks of torch.distributed (clid_slam_b200/dist.py): `shards` is the
+        SpatialShards of the current local map; every rank trains on the replay-pool samples of its own slab
+        (config.bs // world of them per iteration), band gradients and [decoder gradients | loss] cross NVLink
+        peer memory inside the step.  peer_rows: dist.peer_row_tables(...) when every rank holds only its part of
+        the map (partitioned), None when the map is replicated.  The shards describe one state of the local map:
+        call again (or set_shards(None)) after NeuralPoints.update / reset_local_map."""
+        self.shards, self.shard_peer_rows, self.shard_group = shards, peer_rows, group
+
+    def _mapping_sharded(self, iter_count: int) -> None:
+        from .. import dist as _dist
+
+        cfg, npm, dev = self.config, self.neural_points, self.device
+        rank, world = _dist.world()
+        shards, tabs = self.shards, self.shard_peer_rows
+        npm.brick_index(True)
+        trainer = _train.FusedTrainer(cfg, npm, self.geo_mlp)
+        n_small = (trainer.dec_grad.numel() if trainer.dec_grad is not None else 0) + 3
+        if self._peer_link is not None and (self._peer_link.capacity_rows < trainer.rows or self._peer_link.stride < n_small):
+            self._peer_link.close()
+            self._peer_link = None
+        if self._peer_link is None:
+            self._peer_link = _dist.PeerLink(trainer.rows, npm.geo_feature_dim, n_small, torch.device(dev),
+                                             group=self.shard_group, capacity_rows=int(trainer.rows * 1.5) + 1024)
+        trainer.attach_peers(shards, group=self.shard_group, peer_rows=tabs, link=self._peer_link)
+
+        pool = self.global_coord_pool[: self.pool_sample_count]
+        own = torch.nonzero(shards.owner_of(pool) == rank).flatten()
+        bs_rank = max(1, cfg.bs // world)
+        n_global = bs_rank * world
+        nd_global = world * ((bs_rank + cfg.gradient_decimation - 1) // cfg.gradient_decimation) if trainer.numerical else 0
+        cert_before = npm.local_point_certainties.clone()
+        history = []
+        for _ in range(iter_count):
+            if own.numel() > 0:
+                index = own[torch.randint(0, own.numel(), (bs_rank,), device=dev)]
+            else:  # a slab without samples still takes part in the step's all-reduce
+                index = own
+            loss = trainer.iteration(pool[index], self.sdf_label_pool[index], self.time_pool[index], self.weight_pool[index],
+                                     n_global=n_global, nd_global=nd_global)
+            history.append(loss.clone())
+            self.total_iter += 1
+        trainer.peer.check()
+        # per-row side effects of the whole call (neural_points.py:708-733), completed across ranks once
+        if tabs is not None:
+            delta = npm.local_point_certainties - cert_before
+            _dist.exchange_band_values(shards, rank, npm.local_neural_points, delta, "sum", group=self.shard_group)
+            npm.local_point_certainties.copy_(cert_before + delta)
+            _dist.exchange_band_values(shards, rank, npm.local_neural_points, npm.local_point_ts_update, "max",
+                                       group=self.shard_group)
+        else:
+            _dist.reduce_side_effects(npm.local_point_certainties, cert_before, npm.local_point_ts_update, group=self.shard_group)
+            shards.gather_features(npm.local_geo_features.data, rank, group=self.shard_group)
+        self.last_losses = torch.stack(history) if history else None
+        del trainer.losses[:]
+        self._log_losses()
+
     def _batch_in_global_frame(self):
         coord, sdf_label, ts, _, sem_label, color_label, weight = self.get_batch(global_coord=not self.ba_done_flag)
         if self.ba_done_flag:
@@ -271,6 +335,11 @@ class Mapper:
     def _mapping_fused(self, iter_count: int) -> None:
         import time
 
+        if self.shards is not None:
+            from .. import dist as _dist
+
+            if _dist.world()[1] > 1:
+                return self._mapping_sharded(iter_count)
         t0 = time.perf_counter()
         self.neural_points.brick_index(True)  # (re)built here when the map changed since the last query: one small read-back
         trainer = _train.FusedTrainer(self.config, self.neural_points, self.geo_mlp)
