@@ -16,7 +16,7 @@ static int launch_query_tc(const QueryParams& p, cudaStream_t stream) {
   // registers, 4 x 43 KB of shared memory fit, and 4 x 128 TMEM columns are exactly the SM's 512 (measured: 592 CTAs
   // resident at once, same duration as the 4-CTA FMA kernel; a 148-CTA grid takes twice as long).
   constexpr int blocks_per_sm = 512 / tc::kTmemCols;
-  static_assert(blocks_per_sm == CLID_QUERY_MIN_BLOCKS, "register budget and TMEM budget must agree");
+  static_assert(blocks_per_sm >= CLID_QUERY_MIN_BLOCKS, "the TMEM budget (4 x 128 columns) must cover the register-budgeted CTAs per SM");
   static_assert(smem * blocks_per_sm <= 220 * 1024, "shared memory of the resident CTAs");
   const int64_t want = (p.n + kQueryThreads - 1) / kQueryThreads;
   const int64_t cap = (int64_t)info.sm_count * blocks_per_sm;
