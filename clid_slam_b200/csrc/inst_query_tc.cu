@@ -1,5 +1,7 @@
 // query_forward_tc_kernel instantiations (query_fwd_tc.cuh): brick-index search, 64 x 1 decoder on tcgen05.
 #include "launch.h"
+#include "search.cuh"
+#if CLID_QUERY_THREADS == 128
 #include "query_fwd_tc.cuh"
 
 namespace clid {
@@ -32,3 +34,10 @@ int dispatch_query_tc(const QueryParams& p, cudaStream_t stream) {
 }
 
 }  // namespace clid
+#else  // experiment builds with another CTA size: the tensor-core kernel maps one TMEM lane per thread of a 128-thread CTA
+namespace clid {
+int dispatch_query_tc(const QueryParams&, cudaStream_t) {
+  return set_error(CLID_EUNSUPPORTED, "query_forward_tc_kernel is built for 128-thread CTAs");
+}
+}  // namespace clid
+#endif

@@ -30,7 +30,7 @@ enum SearchKind { kSearchHashed = 0, kSearchBricks = 1 };
 // dynamic shared memory of the search phase behind the decoder weights, in floats
 template <int kSearch>
 constexpr int search_smem_floats() {
-  return kSearch == kSearchHashed ? 2 * CLID_MAX_KC : 2 * 64 * kBrickSlots + (int)(sizeof(BrickScratch) / sizeof(float));
+  return kSearch == kSearchHashed ? 2 * CLID_MAX_KC : 2 * 64 * kBrickSlots + (int)(sizeof(BrickScratch) / sizeof(float)) + kStage * 4 * kQueryThreads;
 }
 
 template <int H, int L, int K, int kSearch>
@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
   int64_t* cell_mod = reinterpret_cast<int64_t*>(smem + kDecFloats);  // hashed: per-cell hash residues
   uint64_t* stencil = reinterpret_cast<uint64_t*>(smem + kDecFloats);  // bricks: 64 x 8 neighbourhood stencils
   BrickScratch& scratch = *reinterpret_cast<BrickScratch*>(smem + kDecFloats + 2 * 64 * kBrickSlots);
+  float4* stage_col = reinterpret_cast<float4*>(&scratch + 1) + threadIdx.x;  // kStage record slots per lane (search.cuh)
   const ClidMap& m = p.map;
 
   // asynchronous prologue (common.cuh): stencil by one TMA bulk copy, decoder by cp.async element copies, both
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
     top.init();
     int count = 0;
     if (!stencil_ready) { mbar_wait(&stage.stencil, 0); stencil_ready = true; }
-    if constexpr (kSearch == kSearchBricks) count = search_bricks<K, kQueryThreads>(m, p.bricks, stencil, &scratch.want[0][threadIdx.x], live, px, py, pz, top);
+    if constexpr (kSearch == kSearchBricks) count = search_bricks<K, kQueryThreads>(m, p.bricks, stencil, &scratch.want[0][threadIdx.x], stage_col, live, px, py, pz, top);
     else if (live) count = search_hashed<K>(m, cell_mod, px, py, pz, local, time_filter, top);
     if (!live) continue;
 

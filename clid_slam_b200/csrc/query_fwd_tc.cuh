@@ -18,7 +18,7 @@ namespace clid {
 // dynamic shared memory: tc::Shared | fp32 decoder (MlpLayout<64,1>, sign safeguard) | stencil | brick cursor columns
 constexpr int kTcSharedFloats = (int)((sizeof(tc::Shared) + 15) / 16) * 4;
 constexpr size_t query_tc_smem_bytes() {
-  return (size_t)(kTcSharedFloats + MlpLayout<tc::kH, 1>::kFloats + search_smem_floats<kSearchBricks>()) * sizeof(float);
+  return (size_t)(kTcSharedFloats + MlpLayout<tc::kH, 1>::kFloats + search_smem_floats<kSearchBricks>() - kStage * 4 * kQueryThreads) * sizeof(float);  // this kernel never stages records
 }
 
 // CTA-level tile draw: static first round (tile = blockIdx.x), then tickets from the map's work counter, drawn by
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
     TopK<K> top;
     top.init();
     if (!stencil_ready) { mbar_wait(&stage.stencil, 0); stencil_ready = true; }
-    const int count = search_bricks<K, kQueryThreads>(m, p.bricks, stencil, &scratch.want[0][threadIdx.x], live, px, py, pz, top);
+    const int count = search_bricks<K, kQueryThreads, false>(m, p.bricks, stencil, &scratch.want[0][threadIdx.x], nullptr, live, px, py, pz, top);
 
     // ---- neighbour rows, offsets and inverse-distance weights (as query_forward_kernel; dead lanes have no neighbours)
     int row[K];

@@ -150,15 +150,23 @@ constexpr int kWalkBatch = CLID_WALK_BATCH;
 #define CLID_PF_FEATURES 1  // L2 prefetch of the feature row of every candidate that enters the top-K
 #endif
 
+#ifndef CLID_STAGE_RECORDS
+#define CLID_STAGE_RECORDS 0  // > 0: candidate records are staged through shared memory by cp.async (LDGSTS), this many
+                              // slots per lane and chunk; the walk then ranks out of shared memory (see search_bricks)
+#endif
+constexpr int kStage = CLID_STAGE_RECORDS;
+
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 struct BrickScratch {  // [slot][thread] columns of a 128-thread CTA
   uint32_t want[kHalfSlots][kQueryThreads];
   uint32_t occ[kHalfSlots][kQueryThreads];
   int base[kHalfSlots][kQueryThreads];
 };
 
-template <int K, int kStride>
+template <int K, int kStride, bool kStaged = (kStage > 0)>
 __device__ __forceinline__ int search_bricks(const ClidMap& m, const ClidBricks& b, const uint64_t* stencil,
-                                           uint32_t* col, bool live, float px, float py, float pz,
+                                           uint32_t* col, float4* stg, bool live, float px, float py, float pz,
                                            TopK<K>& top) {
   const int rx = cell_of(px, m.resolution) - b.origin[0] - b.reach;
   const int ry = cell_of(py, m.resolution) - b.origin[1] - b.reach;
@@ -253,6 +261,54 @@ __device__ __forceinline__ int search_bricks(const ClidMap& m, const ClidBricks&
       }
     }
   };
+  if constexpr (kStaged) {
+  // Staged walk: a lane pops up to kStage candidates and hands every record to the async copy unit
+  // (cp.async 16 B, global -> this lane's column of shared memory: no destination registers, so all of them are
+  // in flight at once), waits ONCE for the whole chunk and ranks it out of shared memory in batches of four.
+  // A neighbourhood of ~19 candidates costs one or two global round trips instead of four or five.
+  constexpr int kSt = kStaged ? kStage : 4;
+  while (__any_sync(0xffffffffu, w != 0)) {
+    int rec[kSt];
+#pragma unroll
+    for (int j = 0; j < kSt; ++j) {
+      rec[j] = -1;
+      if (w) {
+        const int bit = __ffs(w) - 1;
+        w &= w - 1;
+        rec[j] = base + __popc(occ & ((1u << bit) - 1u));
+        cp_async16(reinterpret_cast<float*>(stg + j * kStride), reinterpret_cast<const float*>(records + rec[j]));
+        if (w == 0 && left > 1) {
+          --left;
+          sp += kStride;
+          w = sp[0]; occ = sp[kHalfSlots * kStride]; base = (int)sp[2 * kHalfSlots * kStride];
+        }
+      }
+    }
+    cp_async_wait_all();
+#pragma unroll
+    for (int j0 = 0; j0 < kSt; j0 += 4) {
+      if (!__any_sync(0xffffffffu, rec[j0] >= 0)) break;  // slots fill in order: nobody has a candidate from j0 on
+      float4 r[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) r[jj] = stg[(j0 + jj) * kStride];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = j0 + jj;
+        const float d2 = dist2_torch(r[jj].x - px, r[jj].y - py, r[jj].z - pz);
+        if (rec[j] >= 0 && !(d2 > m.max_valid_dist2)) {
+          ++count;
+          if (d2 < top.d[K - 1]) {
+#if CLID_PF_FEATURES
+            prefetch_l2(m.gather_features + (int64_t)__float_as_int(r[jj].w) * kFeat);
+#endif
+            top.insert(d2, rec[j]);
+          }
+        }
+      }
+    }
+  }
+  return count;
+  }
 #if CLID_WALK_PIPELINE
   // software pipeline of depth two: the loads of the next batch are in flight while this one is ranked
   // (the exposed wait on the record loads was 11 % of the kernel's stall samples, profiles/r2a_*)

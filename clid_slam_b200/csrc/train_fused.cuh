@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
   int64_t* cell_mod = reinterpret_cast<int64_t*>(smem + Lay::kFloats);
   uint64_t* stencil = reinterpret_cast<uint64_t*>(smem + Lay::kFloats);
   BrickScratch& scratch = *reinterpret_cast<BrickScratch*>(smem + Lay::kFloats + 2 * 64 * kBrickSlots);
+  float4* stage_col = reinterpret_cast<float4*>(&scratch + 1) + threadIdx.x;  // kStage record slots per lane (search.cuh)
   float* sm_c = smem + Lay::kFloats + kSearchFloats;                            // [warps][32][12]
   uint32_t* sm_m = reinterpret_cast<uint32_t*>(sm_c + kWarps * 32 * kInPad);     // [warps][32][words]
   float* sm_red = reinterpret_cast<float*>(sm_m + kWarps * 32 * kMaskWords);     // [warps][H][12] partial Gd
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
     top.init();
     int count = 0;
     if (!stencil_ready) { mbar_wait(&stage.stencil, 0); stencil_ready = true; }
-    if constexpr (kSearch == kSearchBricks) count = search_bricks<K, kQueryThreads>(m, p.bricks, stencil, &scratch.want[0][threadIdx.x], live, px, py, pz, top);
+    if constexpr (kSearch == kSearchBricks) count = search_bricks<K, kQueryThreads>(m, p.bricks, stencil, &scratch.want[0][threadIdx.x], stage_col, live, px, py, pz, top);
     else if (live) count = search_hashed<K>(m, cell_mod, px, py, pz, local, time_filter, top);
 
     float c[kInPad];

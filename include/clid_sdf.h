@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CLID_ABI_VERSION 4
+#define CLID_ABI_VERSION 5
 #define CLID_MAX_LEVELS 3   /* hidden layers of the decoder MLP */
 #define CLID_MAX_KNN 8      /* query_nn_k */
 #define CLID_MAX_KC 256     /* probed cells per query */
@@ -367,6 +367,115 @@ CLID_API int clid_brick_keys(const int32_t* cells, const uint8_t* keep, int64_t 
 CLID_API int clid_brick_fill(const int64_t* sorted_keys, const int64_t* order, int64_t n_kept, const float* points,
                              const int32_t* dims3, float* records, ClidBrickHeader* headers, uint32_t* hood,
                              clid_stream_t stream);
+
+/* ---- per-frame map maintenance --------------------------------------------------------------
+ * Native bodies of NeuralPoints.update / reset_local_map / assign_local_to_global and of voxel_down_sample_torch.
+ * Every order-dependent result follows the reference's sequential CPU semantics (the numbering of new and local
+ * points is element order, the last duplicate wins a hash slot, ties in a voxel go to the smaller index).
+ * The compactions share one workspace: clid_scan_workspace_bytes(n) bytes, 16-byte aligned, contents opaque except
+ * for its FIRST TWO int64: {number of selected elements, selection used}, valid once the call has completed. */
+CLID_API size_t clid_scan_workspace_bytes(int64_t n);
+
+/* utils/tools.py:639-682 voxel_down_sample_torch (value == NULL) and :685-724 voxel_down_sample_min_value_torch,
+ * two calls around the caller's STABLE ascending sort of `keys`:
+ *   clid_voxel_keys  keys [n] i64 = voxel key * 1024 + level, level = trunc(d / max(d) * 999) of the distance to the
+ *                    voxel centre (or of `value`); stats [8] i32 scratch, stats[7] != 0 afterwards means the voxel
+ *                    key does not fit (span >= 2^17 cells): use another path
+ *   clid_voxel_pick  out[0 .. count) = source index (`order` of the sort) of the first element of every voxel run,
+ *                    in ascending voxel order = the reference's return value; count = workspace int64[0];
+ *                    flags [n] u8 and selected [n] i64 are scratch */
+CLID_API int clid_voxel_keys(const float* points, const float* value, int64_t n, float voxel_size, int32_t* stats,
+                             int64_t* keys, clid_stream_t stream);
+CLID_API int clid_voxel_pick(const int64_t* sorted_keys, const int64_t* order, int64_t n, void* workspace,
+                             size_t workspace_bytes, uint8_t* flags, int64_t* selected, int64_t* out,
+                             clid_stream_t stream);
+
+/* model/neural_points.py:340-385 NeuralPoints.update between the down-sampling and the torch.cat growth.
+ *   clid_map_insert_probe   per candidate: hash slot, current owner, "fresh" = slot empty | owner farther than
+ *                           sqrt(far2) | owner last updated more than diff_travel_dist_local ago (ts_update != NULL),
+ *                           or every candidate when all_fresh; rank [n] = position among the fresh candidates
+ *                           (-1 otherwise); workspace int64[0] = number of new points
+ *   clid_map_insert_commit  new_points [n_new,3], new_ts_create / new_ts_update [n_new] = the rows the caller
+ *                           appends; buffer_pt_index[slot] = m + rank (fresh) or the old owner, the LAST candidate
+ *                           of a repeated slot winning (the reference's sequential index_put) */
+typedef struct ClidInsertArgs {
+  const float* cand;            /* [n,3] down-sampled scan points                  */
+  int64_t n;
+  int64_t* buffer_pt_index;     /* [buffer_size], updated by the commit            */
+  int64_t buffer_size;
+  int64_t primes[3];
+  const float* neural_points;   /* [m,3]                                           */
+  const int32_t* ts_update;     /* [m] point_ts_update, NULL without temporal map  */
+  const float* travel_dist;     /* [n_travel]                                      */
+  int64_t m;                    /* points in the map before the insert             */
+  int64_t n_travel;
+  int32_t cur_ts;
+  int32_t all_fresh;            /* empty map or cur_ts == reboot_ts                */
+  float resolution;
+  float far2;                   /* 3 * resolution^2                                */
+  float diff_travel_dist_local;
+  int64_t* slot;                /* [n] scratch, probe -> commit                    */
+  int64_t* owner;               /* [n] scratch, probe -> commit                    */
+  uint8_t* fresh;               /* [n] out                                         */
+  int64_t* rank;                /* [n] out                                         */
+  void* workspace;
+  size_t workspace_bytes;
+} ClidInsertArgs;
+CLID_API int clid_map_insert_probe(const ClidInsertArgs* args, clid_stream_t stream);
+CLID_API int clid_map_insert_commit(const ClidInsertArgs* args, float* new_points, int32_t* new_ts_create,
+                                    int32_t* new_ts_update, clid_stream_t stream);
+
+/* model/neural_points.py:439-536 NeuralPoints.reset_local_map.
+ *   clid_local_window_select  window predicate per point (travel-distance or time-stamp window on ts_create or the
+ *                             mid stamp, optional reboot test, fewer than 100 points in the window -> all points;
+ *                             then within sqrt(radius2) of the sensor) -> global2local [m+1] (-1 = not local, entry m
+ *                             = -1), local_mask [m+1] u8 (entry m = 1), gids [count] ascending global ids;
+ *                             count = workspace int64[0]
+ *   clid_local_window_gather  local_* copies of the selected rows (local_features gets count + 1 rows: the padding row)
+ *   clid_local_window_scatter NeuralPoints.assign_local_to_global (:538-549): the inverse copy of features (incl.
+ *                             the padding row), certainties and ts_update */
+typedef struct ClidWindowArgs {
+  const float* neural_points;   /* [m,3]                                           */
+  const int32_t* ts_create;     /* [m]                                             */
+  const int32_t* ts_update;     /* [m], read when use_mid_ts                       */
+  const float* travel_dist;     /* NULL: |cur_ts - stamp| < diff_ts_local          */
+  int64_t m;
+  int64_t n_travel;
+  double sensor[3];
+  double radius2;               /* local_map_radius^2                              */
+  int32_t sensor_is_f64;        /* the position tensor was float64 (the distance is then taken in float64) */
+  int32_t temporal;             /* temporal_local_map_on                           */
+  int32_t use_mid_ts;
+  int32_t cur_ts;
+  int32_t reboot_test;          /* reboot_map                                      */
+  int32_t reboot_ts;
+  int32_t diff_ts_local;
+  float diff_travel_dist_local;
+  uint8_t* flags;               /* [m] scratch                                     */
+  int64_t* global2local;        /* [m+1] out                                       */
+  uint8_t* local_mask;          /* [m+1] out                                       */
+  int64_t* gids;                /* [m] out, first count entries                    */
+  void* workspace;
+  size_t workspace_bytes;
+} ClidWindowArgs;
+CLID_API int clid_local_window_select(const ClidWindowArgs* args, clid_stream_t stream);
+typedef struct ClidWindowRows {
+  const int64_t* gids;          /* [n_local]                                       */
+  int64_t n_local;
+  int64_t m;
+  float* neural_points;         /* [m,3]   global arrays (read by gather, written by scatter where noted) */
+  float* point_orientations;    /* [m,4]                                           */
+  float* point_certainties;     /* [m]     scatter target                          */
+  int32_t* point_ts_update;     /* [m]     scatter target                          */
+  float* geo_features;          /* [m+1,8] scatter target                          */
+  float* local_points;          /* [n_local,3]   gather targets                    */
+  float* local_orientations;    /* [n_local,4]                                     */
+  float* local_certainties;     /* [n_local]                                       */
+  int32_t* local_ts_update;     /* [n_local]                                       */
+  float* local_features;        /* [n_local+1,8]                                   */
+} ClidWindowRows;
+CLID_API int clid_local_window_gather(const ClidWindowRows* rows, clid_stream_t stream);
+CLID_API int clid_local_window_scatter(const ClidWindowRows* rows, clid_stream_t stream);
 
 /* ---- registration epilogue (utils/error_state_iekf.py:176-264 h_model, :303-309 update_iterated) ---------- */
 
