@@ -133,6 +133,39 @@ class ClidMappingArgs(C.Structure):
     ]
 
 
+class ClidInsertArgs(C.Structure):
+    _fields_ = [
+        ("cand", C.c_void_p), ("n", C.c_int64), ("buffer_pt_index", C.c_void_p), ("buffer_size", C.c_int64),
+        ("primes", C.c_int64 * 3), ("neural_points", C.c_void_p), ("ts_update", C.c_void_p), ("travel_dist", C.c_void_p),
+        ("m", C.c_int64), ("n_travel", C.c_int64), ("cur_ts", C.c_int32), ("all_fresh", C.c_int32),
+        ("resolution", C.c_float), ("far2", C.c_float), ("diff_travel_dist_local", C.c_float),
+        ("slot", C.c_void_p), ("owner", C.c_void_p), ("fresh", C.c_void_p), ("rank", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class ClidWindowArgs(C.Structure):
+    _fields_ = [
+        ("neural_points", C.c_void_p), ("ts_create", C.c_void_p), ("ts_update", C.c_void_p), ("travel_dist", C.c_void_p),
+        ("m", C.c_int64), ("n_travel", C.c_int64), ("sensor", C.c_double * 3), ("radius2", C.c_double),
+        ("sensor_is_f64", C.c_int32), ("temporal", C.c_int32), ("use_mid_ts", C.c_int32), ("cur_ts", C.c_int32),
+        ("reboot_test", C.c_int32), ("reboot_ts", C.c_int32), ("diff_ts_local", C.c_int32),
+        ("diff_travel_dist_local", C.c_float),
+        ("flags", C.c_void_p), ("global2local", C.c_void_p), ("local_mask", C.c_void_p), ("gids", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class ClidWindowRows(C.Structure):
+    _fields_ = [
+        ("gids", C.c_void_p), ("n_local", C.c_int64), ("m", C.c_int64),
+        ("neural_points", C.c_void_p), ("point_orientations", C.c_void_p), ("point_certainties", C.c_void_p),
+        ("point_ts_update", C.c_void_p), ("geo_features", C.c_void_p),
+        ("local_points", C.c_void_p), ("local_orientations", C.c_void_p), ("local_certainties", C.c_void_p),
+        ("local_ts_update", C.c_void_p), ("local_features", C.c_void_p),
+    ]
+
+
 _lib: Optional[C.CDLL] = None
 
 # every symbol include/clid_sdf.h declares: (name, restype, argtypes)
@@ -173,6 +206,20 @@ _SIGNATURES = [
      [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]),
     ("clid_brick_fill", C.c_int,
      [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("clid_scan_workspace_bytes", C.c_size_t, [C.c_int64]),
+    ("clid_voxel_keys", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("clid_voxel_pick", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("clid_map_insert_probe", C.c_int, [C.POINTER(ClidInsertArgs), C.c_void_p]),
+    ("clid_map_insert_commit", C.c_int, [C.POINTER(ClidInsertArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("clid_local_window_select", C.c_int, [C.POINTER(ClidWindowArgs), C.c_void_p]),
+    ("clid_local_window_gather", C.c_int, [C.POINTER(ClidWindowRows), C.c_void_p]),
+    ("clid_local_window_scatter", C.c_int, [C.POINTER(ClidWindowRows), C.c_void_p]),
+    ("clid_pool_filter_select", C.c_int,
+     [C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+      C.c_void_p]),
+    ("clid_compact_rows", C.c_int,
+     [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.c_void_p]),
     ("clid_region_sdf", C.c_int, [C.POINTER(ClidLocalCloud), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("clid_registration_terms", C.c_int,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.c_int32, C.c_float, C.c_float,

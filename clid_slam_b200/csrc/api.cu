@@ -15,6 +15,7 @@
 #include "peer.cuh"
 #include "mlp_l2.cuh"
 #include "feeder.cuh"
+#include "mapmaint.cuh"
 #include "train_fused.cuh"
 #include "decoder_tc.cuh"
 
@@ -118,6 +119,49 @@ static int elementwise_grid(int64_t work, int threads) {
   int64_t cap = (int64_t)info.sm_count * 16;
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
+
+
+// ---- per-frame map maintenance (mapmaint.cuh) -------------------------------------------------------------------
+namespace {
+// workspace layout: result int64[2] | offsets int64[nb] | sums int32[2 nb]
+struct ScanSpace {
+  int64_t* result;
+  int64_t* offsets;
+  int32_t* sums;
+  int64_t nb;
+};
+size_t scan_space_bytes(int64_t n) {
+  const int64_t nb = scan_blocks(n > 0 ? n : 1);
+  return (size_t)(2 + nb) * sizeof(int64_t) + (size_t)(2 * nb) * sizeof(int32_t) + 16;
+}
+int scan_space(void* ws, size_t bytes, int64_t n, ScanSpace* out) {
+  if (!ws || !aligned16(ws)) return set_error(CLID_EINVAL, "workspace is NULL or not 16-byte aligned");
+  if (bytes < scan_space_bytes(n)) return set_error(CLID_EINVAL, "workspace of %zu bytes, clid_scan_workspace_bytes(%lld) = %zu", bytes, (long long)n, scan_space_bytes(n));
+  out->nb = scan_blocks(n);
+  out->result = static_cast<int64_t*>(ws);
+  out->offsets = out->result + 2;
+  out->sums = reinterpret_cast<int32_t*>(out->offsets + out->nb);
+  return CLID_OK;
+}
+// flags [n] -> rank / selected / mask of the selection the rule picks; three launches
+int run_flag_scan(const uint8_t* flags, int64_t n, const ScanSpace& sp, ScanRule rule, int64_t* rank, int64_t* selected,
+                  uint8_t* mask, cudaStream_t s) {
+  flag_block_sums_kernel<<<(int)sp.nb, kScanThreads, 0, s>>>(flags, n, sp.sums);
+  flag_block_offsets_kernel<<<1, kScanThreads, 0, s>>>(sp.sums, sp.nb, rule, sp.offsets, sp.result);
+  flag_ranks_kernel<<<(int)sp.nb, kScanThreads, 0, s>>>(flags, n, sp.offsets, sp.result, rank, selected, mask);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "flag scan launch");
+  return CLID_OK;
+}
+__global__ void fill_i32_kernel(int32_t* p, int32_t a0, int32_t a1, int32_t a2, int32_t a3, int32_t a4, int32_t a5, int32_t a6, int32_t a7, int n) {
+  const int32_t v[8] = {a0, a1, a2, a3, a4, a5, a6, a7};
+  if (threadIdx.x < n) p[threadIdx.x] = v[threadIdx.x];
+}
+__global__ void window_tail_kernel(int64_t* g2l, uint8_t* mask, int64_t m) {
+  g2l[m] = -1;  // the padding row is "local" for the mask and unreachable through the remap
+  mask[m] = 1;
+}
+}  // namespace
 
 }  // namespace clid
 
@@ -509,6 +553,192 @@ int clid_brick_fill(const int64_t* sorted_keys, const int64_t* order, int64_t n_
   brick_header_fix_kernel<<<elementwise_grid(nb, 256), 256, 0, s>>>(headers, nb);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "brick fill kernels launch");
+  return CLID_OK;
+}
+
+size_t clid_scan_workspace_bytes(int64_t n) { return scan_space_bytes(n); }
+
+int clid_voxel_keys(const float* points, const float* value, int64_t n, float voxel_size, int32_t* stats, int64_t* keys,
+                    clid_stream_t stream) {
+  if (!points || !stats || !keys) return set_error(CLID_EINVAL, "a required pointer is NULL");
+  if (n <= 0) return n < 0 ? set_error(CLID_EINVAL, "n = %lld", (long long)n) : CLID_OK;
+  if (!(voxel_size > 0.f)) return set_error(CLID_EINVAL, "voxel_size must be positive");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  fill_i32_kernel<<<1, 32, 0, s>>>(stats, INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, INT_MIN, 0, 8);
+  voxel_stats_kernel<<<elementwise_grid(n, 256), 256, 0, s>>>(points, n, voxel_size, stats);
+  if (value) {
+    // value mode ranks by `value / value.max()`: the maximum replaces the centre-distance maximum in stats[6]
+    fill_i32_kernel<<<1, 32, 0, s>>>(stats + 6, INT_MIN, 0, 0, 0, 0, 0, 0, 0, 1);
+    ordered_max_kernel<<<elementwise_grid(n, 256), 256, 0, s>>>(value, n, stats + 6);
+  }
+  voxel_keys_kernel<<<elementwise_grid(n, 256), 256, 0, s>>>(points, value, stats + 6, n, voxel_size, stats, keys);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "voxel key kernels launch");
+  return CLID_OK;
+}
+
+int clid_voxel_pick(const int64_t* sorted_keys, const int64_t* order, int64_t n, void* workspace, size_t workspace_bytes,
+                    uint8_t* flags, int64_t* selected, int64_t* out, clid_stream_t stream) {
+  if (!sorted_keys || !order || !flags || !selected || !out) return set_error(CLID_EINVAL, "a required pointer is NULL");
+  if (n <= 0) return set_error(CLID_EINVAL, "n = %lld", (long long)n);
+  ScanSpace sp;
+  if (int rc = scan_space(workspace, workspace_bytes, n, &sp)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  voxel_heads_kernel<<<elementwise_grid(n, 256), 256, 0, s>>>(sorted_keys, n, flags);
+  if (int rc = run_flag_scan(flags, n, sp, ScanRule{nullptr, 0}, nullptr, selected, nullptr, s)) return rc;
+  voxel_pick_kernel<<<elementwise_grid(n, 256), 256, 0, s>>>(selected, sp.result, order, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "voxel pick kernels launch");
+  return CLID_OK;
+}
+
+static int insert_params(const ClidInsertArgs* a, InsertParams* p) {
+  if (!a) return set_error(CLID_EINVAL, "args is NULL");
+  if (a->n <= 0) return set_error(CLID_EINVAL, "n = %lld", (long long)a->n);
+  if (!a->cand || !a->buffer_pt_index || a->buffer_size <= 0 || !a->slot || !a->owner || !a->fresh || !a->rank)
+    return set_error(CLID_EINVAL, "a required pointer is NULL");
+  if (!(a->resolution > 0.f)) return set_error(CLID_EINVAL, "resolution must be positive");
+  if (!a->all_fresh && (a->m <= 0 || !a->neural_points)) return set_error(CLID_EINVAL, "a non-empty map needs neural_points");
+  if (!a->all_fresh && a->ts_update && (!a->travel_dist || a->cur_ts < 0 || a->cur_ts >= a->n_travel))
+    return set_error(CLID_EINVAL, "travel-distance test without travel_dist / cur_ts");
+  memset(p, 0, sizeof(*p));
+  p->cand = a->cand; p->n = a->n; p->table = a->buffer_pt_index; p->buffer_size = a->buffer_size;
+  for (int i = 0; i < 3; ++i) p->primes[i] = a->primes[i];
+  p->neural_points = a->neural_points; p->ts_update = a->all_fresh ? nullptr : a->ts_update; p->travel_dist = a->travel_dist;
+  p->m = a->m; p->cur_ts = a->cur_ts; p->all_fresh = a->all_fresh; p->resolution = a->resolution; p->far2 = a->far2;
+  p->diff_travel_dist_local = a->diff_travel_dist_local;
+  p->slot = a->slot; p->owner = a->owner; p->fresh = a->fresh;
+  return CLID_OK;
+}
+
+int clid_map_insert_probe(const ClidInsertArgs* a, clid_stream_t stream) {
+  InsertParams p;
+  if (int rc = insert_params(a, &p)) return rc;
+  ScanSpace sp;
+  if (int rc = scan_space(a->workspace, a->workspace_bytes, a->n, &sp)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  insert_probe_kernel<<<elementwise_grid(a->n, 256), 256, 0, s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "insert_probe_kernel launch");
+  return run_flag_scan(a->fresh, a->n, sp, ScanRule{nullptr, 0}, a->rank, nullptr, nullptr, s);
+}
+
+int clid_map_insert_commit(const ClidInsertArgs* a, float* new_points, int32_t* new_ts_create, int32_t* new_ts_update,
+                           clid_stream_t stream) {
+  InsertParams p;
+  if (int rc = insert_params(a, &p)) return rc;
+  if (!new_points || !new_ts_create || !new_ts_update) return set_error(CLID_EINVAL, "the rows to append are NULL");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  insert_bid_kernel<<<elementwise_grid(a->n, 256), 256, 0, s>>>(a->slot, a->n, a->buffer_pt_index);
+  insert_commit_kernel<<<elementwise_grid(a->n, 256), 256, 0, s>>>(p, a->rank, new_points, new_ts_create, new_ts_update);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "insert commit kernels launch");
+  return CLID_OK;
+}
+
+int clid_local_window_select(const ClidWindowArgs* a, clid_stream_t stream) {
+  if (!a) return set_error(CLID_EINVAL, "args is NULL");
+  if (a->m <= 0) return set_error(CLID_EINVAL, "m = %lld", (long long)a->m);
+  if (!a->neural_points || !a->flags || !a->global2local || !a->local_mask || !a->gids)
+    return set_error(CLID_EINVAL, "a required pointer is NULL");
+  if (a->temporal) {
+    if (!a->ts_create || (a->use_mid_ts && !a->ts_update)) return set_error(CLID_EINVAL, "temporal window without time stamps");
+    if (a->travel_dist && (a->cur_ts < 0 || a->cur_ts >= a->n_travel)) return set_error(CLID_EINVAL, "cur_ts outside travel_dist");
+  }
+  ScanSpace sp;
+  if (int rc = scan_space(a->workspace, a->workspace_bytes, a->m, &sp)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  WindowParams p;
+  memset(&p, 0, sizeof(p));
+  p.neural_points = a->neural_points; p.ts_create = a->ts_create; p.ts_update = a->ts_update; p.travel_dist = a->travel_dist;
+  p.m = a->m;
+  for (int i = 0; i < 3; ++i) p.sensor[i] = a->sensor[i];
+  p.radius2 = a->radius2; p.sensor_is_f64 = a->sensor_is_f64; p.temporal = a->temporal; p.use_mid_ts = a->use_mid_ts;
+  p.cur_ts = a->cur_ts; p.reboot_ts = a->reboot_test ? a->reboot_ts : INT_MIN; p.diff_ts_local = a->diff_ts_local;
+  p.diff_travel_dist_local = a->diff_travel_dist_local; p.flags = a->flags;
+  // the in-window count lives in the first sum slot until the block sums overwrite it: keep it in result[1]'s low half
+  int32_t* n_in_time = reinterpret_cast<int32_t*>(sp.result + 1);
+  fill_i32_kernel<<<1, 32, 0, s>>>(n_in_time, 0, 0, 0, 0, 0, 0, 0, 0, 2);
+  p.n_in_time = n_in_time;
+  window_flags_kernel<<<elementwise_grid(a->m, 256), 256, 0, s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "window_flags_kernel launch");
+  // fewer than 100 points inside the time window: the reference takes every point (in range) instead (:477-481)
+  ScanRule rule{a->temporal ? n_in_time : nullptr, 100};
+  if (int rc = run_flag_scan(a->flags, a->m, sp, rule, a->global2local, a->gids, a->local_mask, s)) return rc;
+  window_tail_kernel<<<1, 1, 0, s>>>(a->global2local, a->local_mask, a->m);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "window_tail_kernel launch");
+  return CLID_OK;
+}
+
+static int check_rows(const ClidWindowRows* r) {
+  if (!r) return set_error(CLID_EINVAL, "rows is NULL");
+  if (r->n_local < 0 || r->m < 0) return set_error(CLID_EINVAL, "n_local = %lld, m = %lld", (long long)r->n_local, (long long)r->m);
+  if ((r->n_local > 0 && !r->gids) || !r->geo_features || !r->local_features) return set_error(CLID_EINVAL, "a required pointer is NULL");
+  if (!aligned16(r->geo_features) || !aligned16(r->local_features)) return set_error(CLID_EINVAL, "feature arrays must be 16-byte aligned");
+  return CLID_OK;
+}
+
+int clid_local_window_gather(const ClidWindowRows* r, clid_stream_t stream) {
+  if (int rc = check_rows(r)) return rc;
+  if (r->n_local > 0 && (!r->neural_points || !r->point_orientations || !r->point_certainties || !r->point_ts_update ||
+                         !r->local_points || !r->local_orientations || !r->local_certainties || !r->local_ts_update))
+    return set_error(CLID_EINVAL, "a required pointer is NULL");
+  if (r->n_local > 0 && (!aligned16(r->point_orientations) || !aligned16(r->local_orientations)))
+    return set_error(CLID_EINVAL, "orientation arrays must be 16-byte aligned");
+  WindowGather g;
+  g.gids = r->gids; g.n_local = r->n_local; g.neural_points = r->neural_points; g.orientations = r->point_orientations;
+  g.certainties = r->point_certainties; g.ts_update = r->point_ts_update; g.geo_features = r->geo_features; g.m = r->m;
+  g.local_points = r->local_points; g.local_orientations = r->local_orientations; g.local_certainties = r->local_certainties;
+  g.local_ts_update = r->local_ts_update; g.local_features = r->local_features;
+  window_gather_kernel<<<elementwise_grid(r->n_local + 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(g);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "window_gather_kernel launch");
+  return CLID_OK;
+}
+
+int clid_local_window_scatter(const ClidWindowRows* r, clid_stream_t stream) {
+  if (int rc = check_rows(r)) return rc;
+  if (r->n_local > 0 && (!r->point_certainties || !r->point_ts_update || !r->local_certainties || !r->local_ts_update))
+    return set_error(CLID_EINVAL, "a required pointer is NULL");
+  window_scatter_kernel<<<elementwise_grid(r->n_local + 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      r->gids, r->n_local, r->m, r->local_features, r->local_certainties, r->local_ts_update, r->geo_features,
+      r->point_certainties, r->point_ts_update);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "window_scatter_kernel launch");
+  return CLID_OK;
+}
+
+int clid_pool_filter_select(const float* global_coord, int64_t n, const double* sensor3, double radius2, int32_t sensor_is_f64,
+                            uint8_t* flags, int64_t* rank, void* workspace, size_t workspace_bytes, clid_stream_t stream) {
+  if (!global_coord || !sensor3 || !flags || !rank) return set_error(CLID_EINVAL, "a required pointer is NULL");
+  if (n <= 0) return set_error(CLID_EINVAL, "n = %lld", (long long)n);
+  ScanSpace sp;
+  if (int rc = scan_space(workspace, workspace_bytes, n, &sp)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  pool_flags_kernel<<<elementwise_grid(n, 256), 256, 0, s>>>(global_coord, n, sensor3[0], sensor3[1], sensor3[2], radius2,
+                                                            sensor_is_f64, flags);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "pool_flags_kernel launch");
+  return run_flag_scan(flags, n, sp, ScanRule{nullptr, 0}, rank, nullptr, nullptr, s);
+}
+
+int clid_compact_rows(const int64_t* rank, int64_t n, const void* const* src, void* const* dst, const int32_t* words,
+                      int32_t n_arrays, clid_stream_t stream) {
+  if (!rank || !src || !dst || !words) return set_error(CLID_EINVAL, "a required pointer is NULL");
+  if (n <= 0) return n < 0 ? set_error(CLID_EINVAL, "n = %lld", (long long)n) : CLID_OK;
+  if (n_arrays < 1 || n_arrays > kCompactArrays) return set_error(CLID_EINVAL, "n_arrays %d outside 1..%d", n_arrays, kCompactArrays);
+  CompactParams p;
+  memset(&p, 0, sizeof(p));
+  p.rank = rank; p.n = n; p.n_arrays = n_arrays;
+  for (int a = 0; a < n_arrays; ++a) {
+    if (!src[a] || !dst[a] || words[a] < 1) return set_error(CLID_EINVAL, "array %d: NULL pointer or words < 1", a);
+    p.src[a] = static_cast<const uint32_t*>(src[a]); p.dst[a] = static_cast<uint32_t*>(dst[a]); p.words[a] = words[a];
+  }
+  compact_rows_kernel<<<elementwise_grid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "compact_rows_kernel launch");
   return CLID_OK;
 }
 

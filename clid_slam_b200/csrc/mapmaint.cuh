@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(256) window_flags_kernel(const WindowParams p)
     bool in_time = true;
     if (p.temporal) {
       int32_t stamp = p.ts_create[i];
-      if (p.use_mid_ts) stamp = (int32_t)(((float)stamp + (float)p.ts_update[i]) / 2.0f);  // (a + b) / 2 in fp32, truncated
+      if (p.use_mid_ts) stamp = (int32_t)((float)(stamp + p.ts_update[i]) / 2.0f);  // ((a + b) / 2).int(): fp32 quotient, truncated
       if (p.travel_dist) in_time = fabsf(td_cur - p.travel_dist[stamp]) < p.diff_travel_dist_local;
       else in_time = abs(p.cur_ts - stamp) < p.diff_ts_local;
       if (p.reboot_ts != INT_MIN) in_time = in_time && stamp >= p.reboot_ts;
@@ -406,6 +406,45 @@ __global__ void __launch_bounds__(256) window_scatter_kernel(const int64_t* __re
     if (r < n_local) {
       certainties[g] = local_certainties[r];
       ts_update[g] = local_ts_update[r];
+    }
+  }
+}
+
+// ---- replay-pool filter (utils/mapper.py:420-459) -----------------------------------------------------------------
+// flag = the sample lies within sqrt(radius2) of the sensor (window_radius); fp64 when the pose tensor was float64
+__global__ void __launch_bounds__(256) pool_flags_kernel(const float* __restrict__ coord, int64_t n, double sx, double sy, double sz,
+                                                         double radius2, int is_f64, uint8_t* __restrict__ flags) {
+  const float fx = (float)sx, fy = (float)sy, fz = (float)sz, r2f = (float)radius2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = coord[3 * i], y = coord[3 * i + 1], z = coord[3 * i + 2];
+    bool keep;
+    if (is_f64) {
+      const double dx = (double)x - sx, dy = (double)y - sy, dz = (double)z - sz;
+      keep = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)) < radius2;
+    } else {
+      keep = dist2_torch(x - fx, y - fy, z - fz) < r2f;
+    }
+    flags[i] = keep ? 1 : 0;
+  }
+}
+
+// dst[rank[i]] = src[i] for the selected rows of up to kCompactArrays arrays whose rows are `words` 32-bit words
+constexpr int kCompactArrays = 8;
+struct CompactParams {
+  const int64_t* rank;
+  int64_t n;
+  const uint32_t* src[kCompactArrays];
+  uint32_t* dst[kCompactArrays];
+  int32_t words[kCompactArrays];
+  int32_t n_arrays;
+};
+__global__ void __launch_bounds__(256) compact_rows_kernel(const CompactParams p) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = p.rank[i];
+    if (r < 0) continue;
+    for (int a = 0; a < p.n_arrays; ++a) {
+      const int w = p.words[a];
+      for (int k = 0; k < w; ++k) p.dst[a][r * w + k] = p.src[a][i * w + k];
     }
   }
 }

@@ -168,6 +168,8 @@ class NeuralPoints(nn.Module):
         res = self.resolution
         keep = voxel_down_sample_torch(points, res)
         cand = points[keep]
+        if cand.is_cuda and cand.dtype == torch.float32 and cand.shape[0] > 0:
+            return self._update_native(cand, sensor_position, sensor_orientation, cur_ts)
         slots = self._slots_of(cand)
         owner = self.buffer_pt_index[slots]
 
@@ -208,6 +210,26 @@ class NeuralPoints(nn.Module):
         self.reset_local_map(sensor_position, sensor_orientation, cur_ts, reboot_map=True)
         return new_point_ratio
 
+    def _update_native(self, cand: torch.Tensor, sensor_position, sensor_orientation, cur_ts: int) -> float:
+        """update() on a CUDA map: probe / numbering / table store in csrc/mapmaint.cuh (ops/mapmaint.py), the
+        feature draw stays torch.randn (the reference's generator stream)."""
+        from ..ops import mapmaint as _mm
+
+        dev, f32 = self.device, self.dtype
+        n_new = _mm.insert(self, cand, cur_ts)
+        ident = torch.zeros((n_new, 4), dtype=f32, device=dev)
+        ident[:, 0] = 1.0
+        self.point_orientations = torch.cat((self.point_orientations, ident), 0)
+        fresh_feat = self.geo_feature_std * torch.randn(n_new + 1, self.geo_feature_dim, device=dev, dtype=f32)
+        self.geo_features = torch.cat((self.geo_features[:-1], fresh_feat), 0)
+        if self.color_features is not None:
+            fresh_col = self.color_feature_std * torch.randn(n_new + 1, self.color_feature_dim, device=dev, dtype=f32)
+            self.color_features = torch.cat((self.color_features[:-1], fresh_col), 0)
+        self.point_certainties = torch.cat((self.point_certainties, torch.zeros(n_new, device=dev, dtype=f32)), 0)
+        self._touch()
+        self.reset_local_map(sensor_position, sensor_orientation, cur_ts, reboot_map=True)
+        return n_new / cand.shape[0]
+
     def reset_local_map(self, sensor_position: torch.Tensor, sensor_orientation: torch.Tensor, cur_ts: int,
                         use_travel_dist: bool = True, diff_ts_local: int = 50, reboot_map: bool = False) -> None:
         """Select the local window (travel-distance window on the creation stamp AND within
@@ -218,6 +240,15 @@ class NeuralPoints(nn.Module):
         self.max_ts = max(self.max_ts, cur_ts)
         dev = self.device
         m = self.count()
+
+        if m > 0 and self.neural_points.is_cuda and self.neural_points.dtype == torch.float32:
+            from ..ops import mapmaint as _mm
+
+            _mm.local_window(self, sensor_position, cur_ts, use_travel_dist, diff_ts_local, reboot_map)
+            if self.color_features is not None:
+                self.local_color_features = nn.Parameter(self.color_features[self.local_mask])
+            self.local_orientation = sensor_orientation
+            return
 
         if self.temporal_local_map_on:
             if self.config.use_mid_ts:
@@ -262,6 +293,15 @@ class NeuralPoints(nn.Module):
     def assign_local_to_global(self) -> None:
         """Write the trained local window back (model/neural_points.py:538-549)."""
         mask = self.local_mask
+        gids = getattr(self, "_local_gids", None)
+        if (self.geo_features.is_cuda and gids is not None and gids.is_cuda and gids.numel() == self.local_count()
+                and self.local_geo_features.shape[0] == gids.numel() + 1 and self.geo_features.dtype == torch.float32):
+            from ..ops import mapmaint as _mm
+
+            _mm.assign_local_to_global(self)
+            if self.color_features is not None:
+                self.color_features[mask] = self.local_color_features.data
+            return
         self.geo_features[mask] = self.local_geo_features.data
         if self.color_features is not None:
             self.color_features[mask] = self.local_color_features.data

@@ -103,6 +103,12 @@ def _argmin_per_voxel(key: torch.Tensor, rank: torch.Tensor) -> torch.Tensor:
 def voxel_down_sample_torch(points: torch.Tensor, voxel_size: float) -> torch.Tensor:
     """Indices of the point closest to each occupied voxel's centre, distance quantised to
     1000 levels with ties going to the smaller index (utils/tools.py:639-682)."""
+    if points.is_cuda and points.dtype == torch.float32 and points.shape[0] > 0:
+        from ..ops import mapmaint as _mm  # keys -> stable sort -> run heads (csrc/mapmaint.cuh)
+
+        native = _mm.voxel_down_sample(points, voxel_size)
+        if native is not None:
+            return native
     levels = 1000
     cell_f, key = _voxel_keys(points, voxel_size)
     centre = (cell_f + 0.5) * voxel_size
@@ -113,6 +119,12 @@ def voxel_down_sample_torch(points: torch.Tensor, voxel_size: float) -> torch.Te
 
 def voxel_down_sample_min_value_torch(points: torch.Tensor, voxel_size: float, value: torch.Tensor) -> torch.Tensor:
     """Indices of the point with the smallest `value` in each voxel (utils/tools.py:685-724)."""
+    if points.is_cuda and points.dtype == torch.float32 and value.dtype == torch.float32 and points.shape[0] > 0:
+        from ..ops import mapmaint as _mm
+
+        native = _mm.voxel_down_sample(points, voxel_size, value)
+        if native is not None:
+            return native
     levels = 1000
     _, key = _voxel_keys(points, voxel_size)
     rank = (value / value.max() * (levels - 1)).long()

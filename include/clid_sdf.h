@@ -477,6 +477,18 @@ typedef struct ClidWindowRows {
 CLID_API int clid_local_window_gather(const ClidWindowRows* rows, clid_stream_t stream);
 CLID_API int clid_local_window_scatter(const ClidWindowRows* rows, clid_stream_t stream);
 
+/* Replay-pool filter of Mapper.process_frame (utils/mapper.py:420-459): keep the samples within sqrt(radius2) of the
+ * sensor, in pool order.
+ *   clid_pool_filter_select  flags [n] u8, rank [n] i64 (position among the kept, -1 otherwise); kept count =
+ *                            workspace int64[0]
+ *   clid_compact_rows        dst[a][rank[i]] = src[a][i] for every kept row of n_arrays (<= 8) arrays whose rows are
+ *                            words[a] 32-bit words (coord / global_coord: 3, labels, weights, time stamps: 1) */
+CLID_API int clid_pool_filter_select(const float* global_coord, int64_t n, const double* sensor3, double radius2,
+                                     int32_t sensor_is_f64, uint8_t* flags, int64_t* rank, void* workspace,
+                                     size_t workspace_bytes, clid_stream_t stream);
+CLID_API int clid_compact_rows(const int64_t* rank, int64_t n, const void* const* src, void* const* dst,
+                               const int32_t* words, int32_t n_arrays, clid_stream_t stream);
+
 /* ---- registration epilogue (utils/error_state_iekf.py:176-264 h_model, :303-309 update_iterated) ---------- */
 
 /* What IEKFOM.update_iterated needs from h_model, reduced on the device: with, per scan point i,

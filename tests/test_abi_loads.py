@@ -31,7 +31,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_version_and_error_string(lib):
-    assert lib.clid_version() == 4
+    assert lib.clid_version() == 5
     rc = lib.clid_query_forward(None, None, None, None, 5, 0, None, None)
     assert rc == -1
     assert b"NULL" in lib.clid_last_error()
@@ -56,7 +56,8 @@ def test_struct_sizes_match_the_header(lib):
     #include <stdio.h>
     #include "clid_sdf.h"
     int main(void) {
-      printf("%zu %zu %zu %zu\n", sizeof(ClidMap), sizeof(ClidDecoder), sizeof(ClidQueryOut), sizeof(ClidBricks));
+      printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(ClidMap), sizeof(ClidDecoder), sizeof(ClidQueryOut), sizeof(ClidBricks),
+             sizeof(ClidInsertArgs), sizeof(ClidWindowArgs), sizeof(ClidWindowRows));
       return 0;
     }"""
     with tempfile.TemporaryDirectory() as tmp:
@@ -65,7 +66,8 @@ def test_struct_sizes_match_the_header(lib):
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c_path, "-o", exe])
         sizes = [int(v) for v in subprocess.check_output([exe]).split()]
     assert sizes == [C.sizeof(_lib.ClidMap), C.sizeof(_lib.ClidDecoder), C.sizeof(_lib.ClidQueryOut),
-                     C.sizeof(_lib.ClidBricks)]
+                     C.sizeof(_lib.ClidBricks), C.sizeof(_lib.ClidInsertArgs), C.sizeof(_lib.ClidWindowArgs),
+                     C.sizeof(_lib.ClidWindowRows)]
 
 
 def test_product_refuses_cpu_tensors():
