@@ -216,8 +216,9 @@ _SIGNATURES = [
     ("clid_local_window_gather", C.c_int, [C.POINTER(ClidWindowRows), C.c_void_p]),
     ("clid_local_window_scatter", C.c_int, [C.POINTER(ClidWindowRows), C.c_void_p]),
     ("clid_pool_filter_select", C.c_int,
-     [C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
-      C.c_void_p]),
+     [C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.c_double, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+      C.c_size_t, C.c_void_p]),
+    ("clid_table_store", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     ("clid_compact_rows", C.c_int,
      [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.c_void_p]),
     ("clid_region_sdf", C.c_int, [C.POINTER(ClidLocalCloud), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -710,15 +710,16 @@ int clid_local_window_scatter(const ClidWindowRows* r, clid_stream_t stream) {
   return CLID_OK;
 }
 
-int clid_pool_filter_select(const float* global_coord, int64_t n, const double* sensor3, double radius2, int32_t sensor_is_f64,
-                            uint8_t* flags, int64_t* rank, void* workspace, size_t workspace_bytes, clid_stream_t stream) {
+int clid_pool_filter_select(const float* global_coord, int64_t n, const double* sensor3, double radius, int32_t sensor_is_f64,
+                            int32_t use_norm, uint8_t* flags, int64_t* rank, void* workspace, size_t workspace_bytes,
+                            clid_stream_t stream) {
   if (!global_coord || !sensor3 || !flags || !rank) return set_error(CLID_EINVAL, "a required pointer is NULL");
   if (n <= 0) return set_error(CLID_EINVAL, "n = %lld", (long long)n);
   ScanSpace sp;
   if (int rc = scan_space(workspace, workspace_bytes, n, &sp)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  pool_flags_kernel<<<elementwise_grid(n, 256), 256, 0, s>>>(global_coord, n, sensor3[0], sensor3[1], sensor3[2], radius2,
-                                                            sensor_is_f64, flags);
+  pool_flags_kernel<<<elementwise_grid(n, 256), 256, 0, s>>>(global_coord, n, sensor3[0], sensor3[1], sensor3[2], radius,
+                                                            radius * radius, sensor_is_f64, use_norm, flags);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "pool_flags_kernel launch");
   return run_flag_scan(flags, n, sp, ScanRule{nullptr, 0}, rank, nullptr, nullptr, s);
@@ -739,6 +740,18 @@ int clid_compact_rows(const int64_t* rank, int64_t n, const void* const* src, vo
   compact_rows_kernel<<<elementwise_grid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "compact_rows_kernel launch");
+  return CLID_OK;
+}
+
+int clid_table_store(const int64_t* slot, const int64_t* value, int64_t n, int64_t value_base, int64_t* buffer_pt_index,
+                     int64_t buffer_size, clid_stream_t stream) {
+  if (!slot || !buffer_pt_index || buffer_size <= 0) return set_error(CLID_EINVAL, "slot / table is NULL or empty");
+  if (n <= 0) return n < 0 ? set_error(CLID_EINVAL, "n = %lld", (long long)n) : CLID_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  table_bid_kernel<<<elementwise_grid(n, 256), 256, 0, s>>>(slot, n, buffer_size, buffer_pt_index);
+  table_commit_kernel<<<elementwise_grid(n, 256), 256, 0, s>>>(slot, value, n, buffer_size, value_base, buffer_pt_index);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "table store kernels launch");
   return CLID_OK;
 }
 

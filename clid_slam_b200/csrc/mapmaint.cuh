@@ -412,15 +412,22 @@ __global__ void __launch_bounds__(256) window_scatter_kernel(const int64_t* __re
 
 // ---- replay-pool filter (utils/mapper.py:420-459) -----------------------------------------------------------------
 // flag = the sample lies within sqrt(radius2) of the sensor (window_radius); fp64 when the pose tensor was float64
+// use_norm: compare the distance itself, torch.norm(p - sensor) < radius (LocalPointCloudMap.update_map)
 __global__ void __launch_bounds__(256) pool_flags_kernel(const float* __restrict__ coord, int64_t n, double sx, double sy, double sz,
-                                                         double radius2, int is_f64, uint8_t* __restrict__ flags) {
+                                                         double radius, double radius2, int is_f64, int use_norm,
+                                                         uint8_t* __restrict__ flags) {
   const float fx = (float)sx, fy = (float)sy, fz = (float)sz, r2f = (float)radius2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float x = coord[3 * i], y = coord[3 * i + 1], z = coord[3 * i + 2];
     bool keep;
     if (is_f64) {
       const double dx = (double)x - sx, dy = (double)y - sy, dz = (double)z - sz;
-      keep = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)) < radius2;
+      const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+      keep = use_norm ? __dsqrt_rn(d2) < radius : d2 < radius2;
+    } else if (use_norm) {
+      // torch.norm of an fp32 tensor on the reference's device (CPU) accumulates in double and rounds once
+      const double dx = (double)(x - fx), dy = (double)(y - fy), dz = (double)(z - fz);
+      keep = (float)__dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz))) < (float)radius;
     } else {
       keep = dist2_torch(x - fx, y - fy, z - fz) < r2f;
     }
@@ -446,6 +453,26 @@ __global__ void __launch_bounds__(256) compact_rows_kernel(const CompactParams p
       const int w = p.words[a];
       for (int k = 0; k < w; ++k) p.dst[a][r * w + k] = p.src[a][i * w + k];
     }
+  }
+}
+
+// ---- table[slot] = value with the LAST element of a repeated slot winning (sequential index_put) ------------------
+// slots may be negative (torch.fmod keeps the sign; a negative index wraps once)
+__global__ void __launch_bounds__(256) table_bid_kernel(const int64_t* __restrict__ slot, int64_t n, int64_t buffer_size,
+                                                        int64_t* __restrict__ table) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t s = slot[i];
+    s = s < 0 ? s + buffer_size : s;
+    atomicMin(reinterpret_cast<long long*>(table + s), (long long)(-2 - i));
+  }
+}
+__global__ void __launch_bounds__(256) table_commit_kernel(const int64_t* __restrict__ slot, const int64_t* __restrict__ value,
+                                                           int64_t n, int64_t buffer_size, int64_t value_base,
+                                                           int64_t* __restrict__ table) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t s = slot[i];
+    s = s < 0 ? s + buffer_size : s;
+    if (table[s] == -2 - i) table[s] = value ? value[i] : value_base + i;
   }
 }
 

@@ -20,6 +20,11 @@ PRIMES_LOCAL = (73856093, 19349663, 83492791)  # model/local_point_cloud_map.py:
 
 
 def _store_last_wins(table: torch.Tensor, slots: torch.Tensor, values: torch.Tensor) -> None:
+    if table.is_cuda:
+        from ..ops import mapmaint as _mm  # bid / commit kernels (csrc/mapmaint.cuh)
+
+        _mm.table_store(table, slots, values)
+        return
     slots = torch.remainder(slots, table.shape[0])
     uniq, inverse = torch.unique(slots, return_inverse=True)
     pos = torch.arange(slots.shape[0], device=slots.device)
@@ -62,8 +67,14 @@ class LocalPointCloudMap:
         """Insert a scan, drop points farther than map_size from the sensor, rebuild the hash
         (model/local_point_cloud_map.py:58-72)."""
         self.insert_points(points)
-        near = torch.norm(self.local_point_cloud_map - sensor_position, dim=-1) < self.map_size
-        self.local_point_cloud_map = self.local_point_cloud_map[near]
+        cloud = self.local_point_cloud_map
+        if cloud.is_cuda and cloud.dtype == torch.float32 and cloud.shape[0] > 0:
+            from ..ops import mapmaint as _mm  # flag + scan + compaction on the device, one read-back
+
+            (self.local_point_cloud_map,), _, _, _ = _mm.pool_filter(cloud, sensor_position, self.map_size, [cloud], 0, use_norm=True)
+        else:
+            near = torch.norm(cloud - sensor_position, dim=-1) < self.map_size
+            self.local_point_cloud_map = cloud[near]
         table = torch.full((self.buffer_size,), -1, dtype=self.idx_dtype, device=self.device)
         ids = torch.arange(self.local_point_cloud_map.shape[0], device=self.device)
         _store_last_wins(table, self.voxel_hash(self.local_point_cloud_map), ids)

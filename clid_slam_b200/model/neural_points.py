@@ -152,6 +152,11 @@ class NeuralPoints(nn.Module):
     def _store_slots(self, slots: torch.Tensor, values: torch.Tensor) -> None:
         """table[slots] = values where the LAST occurrence of a repeated slot wins (what the
         reference's sequential CPU index_put does; CUDA index_put is unordered)."""
+        if slots.is_cuda:
+            from ..ops import mapmaint as _mm  # bid / commit kernels (csrc/mapmaint.cuh)
+
+            _mm.table_store(self.buffer_pt_index, slots, values)
+            return
         slots = torch.remainder(slots, int(self.buffer_size))  # fmod's negative slots wrap to the same entries
         uniq, inverse = torch.unique(slots, return_inverse=True)
         pos = torch.arange(slots.shape[0], device=slots.device)

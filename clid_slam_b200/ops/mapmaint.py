@@ -179,7 +179,19 @@ def assign_local_to_global(npm) -> None:
     _lib.check(lib.clid_local_window_scatter(C.byref(r), _lib.current_stream(feats.device)), "clid_local_window_scatter")
 
 
-def pool_filter(global_coord: torch.Tensor, origin: torch.Tensor, radius: float, arrays, n_tail: int):
+def table_store(table: torch.Tensor, slots: torch.Tensor, values: torch.Tensor | None, value_base: int = 0) -> None:
+    """table[slots] = values (values None: value_base + position), the last occurrence of a repeated slot winning."""
+    n = slots.shape[0]
+    if n == 0:
+        return
+    slots = slots.contiguous()
+    vals = None if values is None else values.contiguous()
+    _lib.check(_lib.load().clid_table_store(_lib.ptr(slots, _I64, "slots"), _lib.ptr(vals, _I64, "values"), n, int(value_base),
+                                            _lib.ptr(table, _I64, "buffer_pt_index"), table.shape[0],
+                                            _lib.current_stream(table.device)), "clid_table_store")
+
+
+def pool_filter(global_coord: torch.Tensor, origin: torch.Tensor, radius: float, arrays, n_tail: int, use_norm: bool = False):
     """Replay-pool filter of Mapper.process_frame (utils/mapper.py:420-459): the rows of every array in `arrays`
     (all [n] or [n, 3], 4-byte elements) whose sample lies within `radius` of `origin`, in pool order.
     Returns (kept arrays, kept count, kept count among the last n_tail rows)."""
@@ -193,8 +205,8 @@ def pool_filter(global_coord: torch.Tensor, origin: torch.Tensor, radius: float,
     ws = _workspace(n, dev)
     pos = origin.detach().to("cpu", torch.float64)
     sensor = (C.c_double * 3)(float(pos[0]), float(pos[1]), float(pos[2]))
-    _lib.check(lib.clid_pool_filter_select(_lib.ptr(gc, _F32, "global_coord_pool"), n, sensor, float(radius) ** 2,
-                                           int(origin.dtype == torch.float64), flags.data_ptr(), rank.data_ptr(),
+    _lib.check(lib.clid_pool_filter_select(_lib.ptr(gc, _F32, "global_coord_pool"), n, sensor, float(radius),
+                                           int(origin.dtype == torch.float64), int(use_norm), flags.data_ptr(), rank.data_ptr(),
                                            ws.data_ptr(), ws.numel() * 8, stream), "clid_pool_filter_select")
     head = torch.cat((ws[:1], flags[n - n_tail:].sum(dtype=_I64).reshape(1))).cpu()  # the one read-back
     n_keep, n_tail_keep = int(head[0]), int(head[1])

@@ -177,7 +177,9 @@ class Mapper:
         else:
             self.global_coord_pool = torch.cat((self.global_coord_pool, transform_torch(coord, cur_pose_torch)), 0)
 
-        if (frame_id + 1) % cfg.pool_filter_freq == 0:
+        if (frame_id + 1) % cfg.pool_filter_freq == 0 and self._filter_pool_native(origin, normal_label, sem_label, color_label):
+            pass  # compacted by clid_pool_filter_select / clid_compact_rows (ops/mapmaint.py)
+        elif (frame_id + 1) % cfg.pool_filter_freq == 0:
             d2 = ((self.global_coord_pool - origin) ** 2).sum(-1)
             keep = d2 < cfg.window_radius**2
             kept_idx = torch.nonzero(keep).squeeze(-1)
@@ -228,6 +230,25 @@ class Mapper:
                     self.adaptive_iter_offset = 5
                     if frame_id > cfg.freeze_after_frame and ratio > cfg.new_sample_ratio_restart:
                         self.adaptive_iter_offset = 10
+
+    def _filter_pool_native(self, origin, normal_label, sem_label, color_label) -> bool:
+        """The pool filter of process_frame (utils/mapper.py:420-459) as one flag + scan + compaction on the device.
+        False (the torch ops below run instead) on CPU pools, with auxiliary label pools, or when the kept samples
+        exceed pool_capacity (the reference then discards at random through torch.randint)."""
+        cfg = self.config
+        gc = self.global_coord_pool
+        if (not gc.is_cuda or gc.dtype != torch.float32 or gc.shape[0] == 0
+                or normal_label is not None or sem_label is not None or color_label is not None):
+            return False
+        from ..ops import mapmaint as _mm
+
+        arrays = [self.coord_pool, gc, self.sdf_label_pool, self.weight_pool, self.time_pool]
+        outs, n_keep, n_tail_keep, _ = _mm.pool_filter(gc, origin, cfg.window_radius, arrays, self.cur_sample_count)
+        if n_keep > cfg.pool_capacity:
+            return False
+        self.coord_pool, self.global_coord_pool, self.sdf_label_pool, self.weight_pool, self.time_pool = outs
+        self.cur_sample_count, self.pool_sample_count = n_tail_keep, n_keep
+        return True
 
     # ------------------------------------------------------------------ batches
     def get_batch(self, global_coord=False):

@@ -480,14 +480,23 @@ CLID_API int clid_local_window_scatter(const ClidWindowRows* rows, clid_stream_t
 /* Replay-pool filter of Mapper.process_frame (utils/mapper.py:420-459): keep the samples within sqrt(radius2) of the
  * sensor, in pool order.
  *   clid_pool_filter_select  flags [n] u8, rank [n] i64 (position among the kept, -1 otherwise); kept count =
- *                            workspace int64[0]
+ *                            workspace int64[0].  use_norm == 0: sum of squares < radius^2 (the pool filter);
+ *                            use_norm != 0: torch.norm(p - sensor) < radius with the CPU kernel's rounding
+ *                            (LocalPointCloudMap.update_map, model/local_point_cloud_map.py:58-72)
  *   clid_compact_rows        dst[a][rank[i]] = src[a][i] for every kept row of n_arrays (<= 8) arrays whose rows are
  *                            words[a] 32-bit words (coord / global_coord: 3, labels, weights, time stamps: 1) */
-CLID_API int clid_pool_filter_select(const float* global_coord, int64_t n, const double* sensor3, double radius2,
-                                     int32_t sensor_is_f64, uint8_t* flags, int64_t* rank, void* workspace,
-                                     size_t workspace_bytes, clid_stream_t stream);
+CLID_API int clid_pool_filter_select(const float* global_coord, int64_t n, const double* sensor3, double radius,
+                                     int32_t sensor_is_f64, int32_t use_norm, uint8_t* flags, int64_t* rank,
+                                     void* workspace, size_t workspace_bytes, clid_stream_t stream);
 CLID_API int clid_compact_rows(const int64_t* rank, int64_t n, const void* const* src, void* const* dst,
                                const int32_t* words, int32_t n_arrays, clid_stream_t stream);
+
+/* buffer_pt_index[slot[i]] = value[i] (value == NULL: value_base + i) where the LAST element of a repeated slot wins:
+ * what the reference's sequential CPU index_put leaves behind (model/neural_points.py:392, :911-925 recreate_hash,
+ * model/local_point_cloud_map.py:52-56, :66-72); CUDA index_put is unordered.  slot may hold torch.fmod's negative
+ * remainders.  The touched table entries must not hold values below -1 on entry. */
+CLID_API int clid_table_store(const int64_t* slot, const int64_t* value, int64_t n, int64_t value_base,
+                              int64_t* buffer_pt_index, int64_t buffer_size, clid_stream_t stream);
 
 /* ---- registration epilogue (utils/error_state_iekf.py:176-264 h_model, :303-309 update_iterated) ---------- */
 

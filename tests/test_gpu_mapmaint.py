@@ -160,3 +160,115 @@ def test_large_map_window_is_exact():
     slots = npm._slots_of(npm.neural_points) % int(npm.buffer_size)
     owners = npm.buffer_pt_index[slots]
     assert (owners >= 0).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32_pose", "f64_pose"])
+def test_native_pool_filter_equals_the_torch_ops(dtype):
+    from clid_slam_b200.ops import mapmaint as mm
+
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    n, n_tail = 300_001, 7000
+    gc = (torch.rand(n, 3, generator=gen, device="cuda") - 0.5) * 150.0
+    coord = torch.rand(n, 3, generator=gen, device="cuda")
+    label = torch.rand(n, generator=gen, device="cuda")
+    weight = torch.rand(n, generator=gen, device="cuda") - 0.5
+    stamp = torch.randint(0, 90, (n,), generator=gen, device="cuda", dtype=torch.int32)
+    origin = torch.tensor([3.0, -2.0, 0.5], device="cuda", dtype=dtype)
+    radius = 50.0
+    outs, n_keep, n_tail_keep, flags = mm.pool_filter(gc, origin, radius, [coord, gc, label, weight, stamp], n_tail)
+    d2 = ((gc - origin) ** 2).sum(-1)  # utils/mapper.py:421-423 (float64 when the pose is float64)
+    keep = d2 < radius**2
+    if dtype == torch.float64:
+        assert torch.equal(flags.bool(), keep)
+    keep = flags.bool()  # fp32: torch's CUDA reduction may round a d2 within an ulp of the radius differently
+    assert int((keep != (d2 < radius**2)).sum()) <= 2
+    assert n_keep == int(keep.sum()) and n_tail_keep == int(keep[-n_tail:].sum()) and 0 < n_keep < n
+    for got, src in zip(outs, [coord, gc, label, weight, stamp]):
+        assert got.dtype == src.dtype and torch.equal(got, src[keep])
+
+
+def test_process_frame_with_the_native_pool_filter_equals_the_torch_filter(monkeypatch):
+    """Two mappers on the same scans, one with the native filter switched off: identical pools and counters."""
+    import numpy as np
+
+    from clid_slam_b200.config import ncd128
+    from clid_slam_b200.model.decoder import Decoder
+    from clid_slam_b200.model.local_point_cloud_map import LocalPointCloudMap
+    from clid_slam_b200.utils.mapper import Mapper
+    from test_gpu_mapper_flow import FakeDataset, _scan
+
+    pools = []
+    for native in (True, False):
+        torch.manual_seed(42)
+        cfg = ncd128()
+        cfg.device, cfg.use_pin_mapper = "cuda", True
+        cfg.buffer_size, cfg.local_buffer_size = 2_000_003, 500_009
+        cfg.pool_filter_freq, cfg.window_radius = 1, 14.0  # every frame drops the far samples
+        dec = Decoder(cfg, cfg.geo_mlp_hidden_dim, cfg.geo_mlp_level, 1)
+        npm = NeuralPoints(cfg)
+        ds = FakeDataset(3)
+        mapper = Mapper(cfg, ds, npm, LocalPointCloudMap(cfg), dec)
+        if not native:
+            monkeypatch.setattr(mapper, "_filter_pool_native", lambda *a, **k: False)
+        gen = torch.Generator(device="cuda").manual_seed(5)
+        torch.cuda.manual_seed(9)
+        for frame in range(3):
+            ds.processed_frame = frame
+            pose = torch.eye(4, device="cuda", dtype=torch.float64)
+            pose[0, 3] = 2.0 * frame
+            ds.gt_poses[frame, 0, 3] = 2.0 * frame
+            npm.travel_dist = torch.arange(frame + 1, device="cuda", dtype=torch.float32) * 2.0
+            mapper.process_frame(_scan(gen, "cuda"), None, pose, frame)
+        pools.append((mapper.coord_pool, mapper.global_coord_pool, mapper.sdf_label_pool, mapper.weight_pool,
+                      mapper.time_pool, mapper.pool_sample_count, mapper.cur_sample_count, mapper.new_idx))
+    a, b = pools
+    assert a[5] == b[5] and a[6] == b[6] and 0 < a[5]
+    for x, y in zip(a[:5], b[:5]):
+        assert torch.equal(x, y)
+    assert torch.equal(a[7], b[7])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32_pose", "f64_pose"])
+def test_local_point_cloud_map_on_the_gpu_equals_the_host_logic(dtype):
+    """LocalPointCloudMap.update_map (model/local_point_cloud_map.py:35-72): insert, range filter, hash rebuild --
+    the CUDA map (native down-sampling, table store, compaction) holds the same points in the same order and the
+    same table as the torch ops on CPU; a small table forces repeated slots."""
+    from clid_slam_b200.model.local_point_cloud_map import LocalPointCloudMap
+
+    clouds = []
+    for device in ("cpu", "cuda"):
+        cfg = ncd128()
+        cfg.device, cfg.local_buffer_size, cfg.local_map_size = device, 20_011, 18.0
+        clouds.append(LocalPointCloudMap(cfg))
+    cpu, gpu = clouds
+    gen = torch.Generator().manual_seed(3)
+    for frame in range(5):
+        centre = torch.tensor([4.0 * frame, -1.0 * frame, 0.2])
+        pts = (torch.rand(25_000, 3, generator=gen) - 0.5) * torch.tensor([50.0, 40.0, 3.0]) + centre
+        cpu.update_map(centre.to(dtype), pts)
+        gpu.update_map(centre.to(dtype).cuda(), pts.cuda())
+        assert gpu.local_point_cloud_map.shape[0] > 1000
+        assert torch.equal(cpu.local_point_cloud_map, gpu.local_point_cloud_map.cpu())
+        assert torch.equal(cpu.buffer_pt_index, gpu.buffer_pt_index.cpu())
+
+
+def test_recreate_hash_on_the_gpu_equals_the_host_logic():
+    """NeuralPoints.recreate_hash (model/neural_points.py:840-929) after a prune: min-value down-sampling and the
+    last-writer-wins table store run natively on the GPU."""
+    cpu, gpu = _twin_maps(200_003)
+    gen = torch.Generator().manual_seed(0)
+    pts = oc.wavy_sheets(60, 2, cpu.resolution, gen)
+    cpu.travel_dist, gpu.travel_dist = torch.zeros(4), torch.zeros(4, device="cuda")
+    cpu.update(pts, torch.zeros(3), torch.eye(3), 0)
+    gpu.update(pts.cuda(), torch.zeros(3, device="cuda"), torch.eye(3, device="cuda"), 0)
+    cert = torch.rand(cpu.count(), generator=gen) * 4
+    cpu.point_certainties, gpu.point_certainties = cert.clone(), cert.cuda()
+    gpu.geo_features = cpu.geo_features.cuda()
+    for with_ts, kept in ((True, True), (False, True), (False, False)):
+        assert cpu.prune_map(1.0, min_prune_count=10, global_prune=True) == gpu.prune_map(1.0, min_prune_count=10, global_prune=True)
+        cpu.recreate_hash(torch.zeros(3), torch.eye(3), kept_points=kept, with_ts=with_ts, cur_ts=0)
+        gpu.recreate_hash(torch.zeros(3, device="cuda"), torch.eye(3, device="cuda"), kept_points=kept, with_ts=with_ts, cur_ts=0)
+        _same_state(cpu, gpu)
+        assert torch.equal(cpu.geo_features, gpu.geo_features.cpu())
+        cpu.point_certainties *= 0.7
+        gpu.point_certainties *= 0.7
