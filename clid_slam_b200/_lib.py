@@ -166,6 +166,17 @@ class ClidWindowRows(C.Structure):
     ]
 
 
+class ClidRaySampleArgs(C.Structure):
+    _fields_ = [
+        ("points", C.c_void_p), ("depth", C.c_void_p), ("randn_surf", C.c_void_p), ("rand_front", C.c_void_p),
+        ("rand_behind", C.c_void_p), ("n_points", C.c_int64), ("n_surf", C.c_int32), ("n_front", C.c_int32),
+        ("n_behind", C.c_int32), ("surface_sample_range_m", C.c_float), ("margin", C.c_float),
+        ("free_sample_begin_ratio", C.c_float), ("free_sample_end_dist_m", C.c_float), ("weight_top", C.c_float),
+        ("dist_weight_scale", C.c_float), ("max_range", C.c_float),
+        ("dist_weight_on", C.c_int32), ("coord", C.c_void_p), ("disp", C.c_void_p), ("weight", C.c_void_p),
+    ]
+
+
 _lib: Optional[C.CDLL] = None
 
 # every symbol include/clid_sdf.h declares: (name, restype, argtypes)
@@ -218,6 +229,10 @@ _SIGNATURES = [
     ("clid_pool_filter_select", C.c_int,
      [C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.c_double, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
       C.c_size_t, C.c_void_p]),
+    ("clid_ray_samples", C.c_int, [C.POINTER(ClidRaySampleArgs), C.c_void_p]),
+    ("clid_ray_labels", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("clid_flag_ranks", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     ("clid_table_store", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     ("clid_compact_rows", C.c_int,
      [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.c_void_p]),

@@ -755,6 +755,49 @@ int clid_table_store(const int64_t* slot, const int64_t* value, int64_t n, int64
   return CLID_OK;
 }
 
+int clid_ray_samples(const ClidRaySampleArgs* a, clid_stream_t stream) {
+  if (!a) return set_error(CLID_EINVAL, "args is NULL");
+  if (a->n_points <= 0) return a->n_points < 0 ? set_error(CLID_EINVAL, "n_points = %lld", (long long)a->n_points) : CLID_OK;
+  if (!a->points || !a->depth || !a->coord || !a->disp || !a->weight) return set_error(CLID_EINVAL, "a required pointer is NULL");
+  if (a->n_surf < 0 || a->n_front < 0 || a->n_behind < 0) return set_error(CLID_EINVAL, "negative sample counts");
+  if ((a->n_surf && !a->randn_surf) || (a->n_front && !a->rand_front) || (a->n_behind && !a->rand_behind))
+    return set_error(CLID_EINVAL, "random numbers are NULL");
+  RaySampleParams p;
+  memset(&p, 0, sizeof(p));
+  p.points = a->points; p.depth = a->depth; p.randn_surf = a->randn_surf; p.rand_front = a->rand_front; p.rand_behind = a->rand_behind;
+  p.P = a->n_points; p.n_surf = a->n_surf; p.n_front = a->n_front; p.n_behind = a->n_behind;
+  p.sigma = a->surface_sample_range_m;
+  p.margin_sigma = a->margin;
+  p.begin_ratio = a->free_sample_begin_ratio; p.end_dist = a->free_sample_end_dist_m;
+  p.weight_top = a->weight_top;
+  p.inv_max_range = 1.0f / a->max_range; p.weight_scale = a->dist_weight_scale; p.dist_weight_on = a->dist_weight_on;
+  p.coord = a->coord; p.disp = a->disp; p.weight = a->weight;
+  ray_samples_kernel<<<elementwise_grid(a->n_points, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "ray_samples_kernel launch");
+  return CLID_OK;
+}
+
+int clid_ray_labels(const float* disp, const float* dist, const uint8_t* reachable, int64_t n_points, int32_t samples_per_ray,
+                    int32_t n_surf, float* label, uint8_t* keep, clid_stream_t stream) {
+  if (!disp || !label || !keep || (n_surf > 0 && (!dist || !reachable))) return set_error(CLID_EINVAL, "a required pointer is NULL");
+  if (n_points <= 0) return n_points < 0 ? set_error(CLID_EINVAL, "n_points = %lld", (long long)n_points) : CLID_OK;
+  if (samples_per_ray < 1 || n_surf < 0 || n_surf >= samples_per_ray) return set_error(CLID_EINVAL, "samples_per_ray %d, n_surf %d", samples_per_ray, n_surf);
+  ray_labels_kernel<<<elementwise_grid(n_points * samples_per_ray, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      disp, dist, reachable, n_points, samples_per_ray, n_surf, label, keep);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "ray_labels_kernel launch");
+  return CLID_OK;
+}
+
+int clid_flag_ranks(const uint8_t* flags, int64_t n, int64_t* rank, void* workspace, size_t workspace_bytes, clid_stream_t stream) {
+  if (!flags || !rank) return set_error(CLID_EINVAL, "a required pointer is NULL");
+  if (n <= 0) return set_error(CLID_EINVAL, "n = %lld", (long long)n);
+  ScanSpace sp;
+  if (int rc = scan_space(workspace, workspace_bytes, n, &sp)) return rc;
+  return run_flag_scan(flags, n, sp, ScanRule{nullptr, 0}, rank, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
 int clid_registration_terms(const float* pc_imu, const float* sdf, const float* grad, const int32_t* nn_count, int64_t n,
                             const float* rot9, int32_t min_nn, float min_grad, float max_grad, double* out28,
                             uint8_t* valid_out, clid_stream_t stream) {

@@ -456,6 +456,97 @@ __global__ void __launch_bounds__(256) compact_rows_kernel(const CompactParams p
   }
 }
 
+// ---- DataSampler.sample / sample_pin: the ray samples (utils/data_sampler.py:35-140, :283-345) ------------------------
+// One thread per scan point: its 1 + n_surf + n_front + n_behind samples, written ray-major (the reference builds
+// them block by block with ~30 eager ops and transposes at the end).  The random numbers are drawn by the caller
+// (torch.randn / torch.rand in the reference's order: surface, front, behind; element j * P + i belongs to sample j of
+// point i) and every arithmetic step keeps torch's fp32 rounding (separate multiply / add, the divisions torch does).
+struct RaySampleParams {
+  const float* points;     // [P,3] sensor frame
+  const float* depth;      // [P]   |point| (torch.linalg.norm by the caller)
+  const float* randn_surf; // [n_surf * P]
+  const float* rand_front; // [n_front * P]
+  const float* rand_behind;// [n_behind * P]
+  int64_t P;
+  int32_t n_surf, n_front, n_behind;
+  float sigma;             // surface_sample_range_m
+  float margin_sigma;      // 2 sigma: free-space samples keep this far from the surface
+  float begin_ratio;       // free_sample_begin_ratio
+  float end_dist;          // free_sample_end_dist_m
+  float weight_top;        // 1 + dist_weight_scale / 2
+  float inv_max_range;     // 1 / max_range (torch's CUDA division by a python scalar multiplies by the reciprocal)
+  float weight_scale;      // dist_weight_scale
+  int32_t dist_weight_on;
+  float* coord;            // [P * S, 3] ray-major
+  float* disp;             // [P * S]    displacement along the ray (label = -disp)
+  float* weight;           // [P * S]
+};
+
+__global__ void __launch_bounds__(256) ray_samples_kernel(const RaySampleParams p) {
+  const int S = 1 + p.n_surf + p.n_front + p.n_behind;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.P; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = p.points[3 * i], y = p.points[3 * i + 1], z = p.points[3 * i + 2];
+    const float d = p.depth[i];
+    float w_near = 1.0f;
+    if (p.dist_weight_on) w_near = __fsub_rn(p.weight_top, __fmul_rn(__fmul_rn(d, p.inv_max_range), p.weight_scale));
+    float* c = p.coord + (i * S) * 3;
+    float* dp = p.disp + i * S;
+    float* w = p.weight + i * S;
+    int s = 0;
+    c[0] = x; c[1] = y; c[2] = z; dp[0] = 0.f; w[0] = w_near;  // the end point itself (ratio 1)
+    ++s;
+    for (int j = 0; j < p.n_surf; ++j, ++s) {
+      const float ds = __fmul_rn(p.randn_surf[(int64_t)j * p.P + i], p.sigma);
+      const float r = __fadd_rn(__fdiv_rn(ds, d), 1.0f);
+      c[3 * s] = __fmul_rn(x, r); c[3 * s + 1] = __fmul_rn(y, r); c[3 * s + 2] = __fmul_rn(z, r);
+      dp[s] = ds; w[s] = w_near;
+    }
+    {
+      // python_scalar / tensor is tensor.reciprocal() * scalar in torch
+      const float hi = __fsub_rn(1.0f, __fmul_rn(__frcp_rn(d), p.margin_sigma));
+      const float span = __fsub_rn(hi, p.begin_ratio);
+      for (int j = 0; j < p.n_front; ++j, ++s) {
+        const float r = __fadd_rn(__fmul_rn(p.rand_front[(int64_t)j * p.P + i], span), p.begin_ratio);
+        c[3 * s] = __fmul_rn(x, r); c[3 * s + 1] = __fmul_rn(y, r); c[3 * s + 2] = __fmul_rn(z, r);
+        dp[s] = __fmul_rn(__fsub_rn(r, 1.0f), d); w[s] = -1.0f;
+      }
+    }
+    {
+      const float hi = __fadd_rn(__fmul_rn(__frcp_rn(d), p.end_dist), 1.0f);
+      const float lo = __fadd_rn(1.0f, __fmul_rn(__frcp_rn(d), p.margin_sigma));
+      const float span = __fsub_rn(hi, lo);
+      for (int j = 0; j < p.n_behind; ++j, ++s) {
+        const float r = __fadd_rn(__fmul_rn(p.rand_behind[(int64_t)j * p.P + i], span), lo);
+        c[3 * s] = __fmul_rn(x, r); c[3 * s + 1] = __fmul_rn(y, r); c[3 * s + 2] = __fmul_rn(z, r);
+        dp[s] = __fmul_rn(__fsub_rn(r, 1.0f), d); w[s] = -1.0f;
+      }
+    }
+  }
+}
+
+// labels and keep flags of DataSampler.sample (utils/data_sampler.py:347-377): a near-surface sample takes the
+// region-specific distance (row i * n_surf + j of `dist` / `reachable`), signed by the side it was drawn on, and is
+// dropped when no stored point is in reach; every other sample keeps label = -disp
+__global__ void __launch_bounds__(256) ray_labels_kernel(const float* __restrict__ disp, const float* __restrict__ dist,
+                                                         const uint8_t* __restrict__ reachable, int64_t P, int S, int n_surf,
+                                                         float* __restrict__ label, uint8_t* __restrict__ keep) {
+  const int64_t total = P * S;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / S;
+    const int s = (int)(t - i * S);
+    const float ds = disp[t];
+    float lab = -ds;
+    uint8_t k = 1;
+    if (s >= 1 && s <= n_surf) {
+      const int64_t r = i * n_surf + (s - 1);
+      lab = ds < 0.f ? dist[r] : -dist[r];
+      k = reachable[r];
+    }
+    label[t] = lab;
+    keep[t] = k;
+  }
+}
+
 // ---- table[slot] = value with the LAST element of a repeated slot winning (sequential index_put) ------------------
 // slots may be negative (torch.fmod keeps the sign; a negative index wraps once)
 __global__ void __launch_bounds__(256) table_bid_kernel(const int64_t* __restrict__ slot, int64_t n, int64_t buffer_size,

@@ -222,3 +222,67 @@ def pool_filter(global_coord: torch.Tensor, origin: torch.Tensor, radius: float,
         words = (C.c_int32 * k)(*[int(a[0].numel()) for a in srcs])
         _lib.check(lib.clid_compact_rows(rank.data_ptr(), n, src_p, dst_p, words, k, stream), "clid_compact_rows")
     return outs, n_keep, n_tail_keep, flags
+
+
+def ray_samples(cfg, points: torch.Tensor):
+    """The ray samples of DataSampler.sample / sample_pin (utils/data_sampler.py:35-140) in ONE launch: returns
+    (coord [P*S,3], disp [P*S], weight [P*S]) ray-major.  The random numbers come from torch's generator in the
+    reference's order, so a seeded run draws the samples the torch ops draw."""
+    lib = _lib.load()
+    dev = points.device
+    pts = points.contiguous()
+    count = pts.shape[0]
+    n_surf, n_front, n_behind = int(cfg.surface_sample_n), int(cfg.free_front_n), int(cfg.free_behind_n)
+    per_ray = 1 + n_surf + n_front + n_behind
+    depth = torch.linalg.norm(pts, dim=1)
+    randn_surf = torch.randn(count * n_surf, 1, device=dev)
+    rand_front = torch.rand(count * n_front, 1, device=dev)
+    rand_behind = torch.rand(count * n_behind, 1, device=dev)
+    coord = torch.empty((count * per_ray, 3), dtype=_F32, device=dev)
+    disp = torch.empty(count * per_ray, dtype=_F32, device=dev)
+    weight = torch.empty(count * per_ray, dtype=_F32, device=dev)
+    a = _lib.ClidRaySampleArgs()
+    a.points, a.depth = _lib.ptr(pts, _F32, "points"), depth.data_ptr()
+    a.randn_surf, a.rand_front, a.rand_behind = randn_surf.data_ptr(), rand_front.data_ptr(), rand_behind.data_ptr()
+    a.n_points, a.n_surf, a.n_front, a.n_behind = count, n_surf, n_front, n_behind
+    sigma = float(cfg.surface_sample_range_m)
+    a.surface_sample_range_m, a.margin = sigma, 2.0 * sigma
+    a.free_sample_begin_ratio, a.free_sample_end_dist_m = float(cfg.free_sample_begin_ratio), float(cfg.free_sample_end_dist_m)
+    a.weight_top = 1 + float(cfg.dist_weight_scale) * 0.5
+    a.dist_weight_scale, a.max_range, a.dist_weight_on = float(cfg.dist_weight_scale), float(cfg.max_range), int(bool(cfg.dist_weight_on))
+    a.coord, a.disp, a.weight = coord.data_ptr(), disp.data_ptr(), weight.data_ptr()
+    _lib.check(lib.clid_ray_samples(C.byref(a), _lib.current_stream(dev)), "clid_ray_samples")
+    return coord, disp, weight, per_ray
+
+
+def region_labelled_samples(cfg, points: torch.Tensor, local_point_cloud_map, cur_pose_torch):
+    """DataSampler.sample on the device (utils/data_sampler.py:260-402): ray samples, region-specific labels of the
+    near-surface samples, unreachable samples dropped.  Returns (coord, sdf_label, weight)."""
+    from ..utils.tools import transform_torch
+
+    lib = _lib.load()
+    dev = points.device
+    stream = _lib.current_stream(dev)
+    coord, disp, weight, per_ray = ray_samples(cfg, points)
+    count, n_surf = points.shape[0], int(cfg.surface_sample_n)
+    near = coord.view(count, per_ray, 3)[:, 1:1 + n_surf, :].reshape(-1, 3)
+    dist, reachable = local_point_cloud_map.region_specific_sdf_estimation(transform_torch(near, cur_pose_torch))
+    reach_u8 = reachable.to(_U8).contiguous()
+    dist = dist.contiguous()
+    n = count * per_ray
+    label = torch.empty(n, dtype=_F32, device=dev)
+    keep = torch.empty(n, dtype=_U8, device=dev)
+    _lib.check(lib.clid_ray_labels(disp.data_ptr(), dist.data_ptr(), reach_u8.data_ptr(), count, per_ray, n_surf,
+                                   label.data_ptr(), keep.data_ptr(), stream), "clid_ray_labels")
+    rank = torch.empty(n, dtype=_I64, device=dev)
+    ws = _workspace(n, dev)
+    _lib.check(lib.clid_flag_ranks(keep.data_ptr(), n, rank.data_ptr(), ws.data_ptr(), ws.numel() * 8, stream), "clid_flag_ranks")
+    n_keep = _count(ws)
+    outs = [torch.empty((n_keep, 3), dtype=_F32, device=dev), torch.empty(n_keep, dtype=_F32, device=dev),
+            torch.empty(n_keep, dtype=_F32, device=dev)]
+    if n_keep > 0:
+        src_p = (C.c_void_p * 3)(coord.data_ptr(), label.data_ptr(), weight.data_ptr())
+        dst_p = (C.c_void_p * 3)(*[o.data_ptr() for o in outs])
+        words = (C.c_int32 * 3)(3, 1, 1)
+        _lib.check(lib.clid_compact_rows(rank.data_ptr(), n, src_p, dst_p, words, 3, stream), "clid_compact_rows")
+    return outs[0], outs[1], outs[2]

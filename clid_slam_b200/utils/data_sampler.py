@@ -24,6 +24,18 @@ class DataSampler:
         sem | None, color | None, weight [P*S]).  Label = -(displacement along the ray); weight
         sign flags free-space samples (negative)."""
         cfg, dev = self.config, self.dev
+        if (points_torch.is_cuda and points_torch.dtype == torch.float32 and points_torch.shape[0] > 0
+                and normal_torch is None and sem_label_torch is None and color_torch is None
+                and not getattr(cfg, "behind_dropoff_on", False)):
+            from ..ops import mapmaint as _mm  # one launch instead of ~30 eager ops (csrc/mapmaint.cuh)
+
+            coord, disp, weight, _ = _mm.ray_samples(cfg, points_torch)
+            return coord, -disp, None, None, None, weight
+        return self._sample_pin_torch(points_torch, normal_torch, sem_label_torch, color_torch)
+
+    def _sample_pin_torch(self, points_torch, normal_torch=None, sem_label_torch=None, color_torch=None):
+        """sample_pin() with torch ops (host logic; what the CPU tests pin against the reference's fixtures)."""
+        cfg, dev = self.config, self.dev
         sigma = cfg.surface_sample_range_m
         n_surf, n_front, n_behind = cfg.surface_sample_n, cfg.free_front_n, cfg.free_behind_n
         per_ray = 1 + n_surf + n_front + n_behind
@@ -93,6 +105,15 @@ class DataSampler:
         (``region_specific_sdf_estimation``: point-to-plane distance where a plane fits, nearest
         point distance otherwise), signed by the side of the surface the sample was drawn on;
         samples with no stored point in reach are dropped.  Returns (coord, sdf_label, weight)."""
+        cfg, dev = self.config, self.dev
+        if points_torch.is_cuda and points_torch.dtype == torch.float32 and points_torch.shape[0] > 0:
+            from ..ops import mapmaint as _mm  # ray samples, labels and compaction as kernels (csrc/mapmaint.cuh)
+
+            return _mm.region_labelled_samples(cfg, points_torch, local_point_cloud_map, cur_pose_torch)
+        return self._sample_torch(points_torch, local_point_cloud_map, cur_pose_torch)
+
+    def _sample_torch(self, points_torch, local_point_cloud_map, cur_pose_torch):
+        """sample() with torch ops (host logic; what the CPU tests pin against the reference's fixtures)."""
         cfg, dev = self.config, self.dev
         sigma = cfg.surface_sample_range_m
         n_surf, n_front, n_behind = cfg.surface_sample_n, cfg.free_front_n, cfg.free_behind_n

@@ -491,6 +491,42 @@ CLID_API int clid_pool_filter_select(const float* global_coord, int64_t n, const
 CLID_API int clid_compact_rows(const int64_t* rank, int64_t n, const void* const* src, void* const* dst,
                                const int32_t* words, int32_t n_arrays, clid_stream_t stream);
 
+/* Ray samples of DataSampler.sample_pin / sample (utils/data_sampler.py:35-140, :283-345): for every scan point its
+ * 1 + n_surf + n_front + n_behind samples, ray-major.  The caller draws the random numbers in the reference's order
+ * (randn for the surface samples, rand for the front and the behind free-space samples; element j * P + i = sample j
+ * of point i) and passes depth = |point|.  coord [P*S,3], disp [P*S] (label = -disp), weight [P*S] (negative =
+ * free space). */
+typedef struct ClidRaySampleArgs {
+  const float* points;          /* [P,3] sensor frame                              */
+  const float* depth;           /* [P]                                             */
+  const float* randn_surf;      /* [n_surf * P]                                    */
+  const float* rand_front;      /* [n_front * P]                                   */
+  const float* rand_behind;     /* [n_behind * P]                                  */
+  int64_t n_points;
+  int32_t n_surf, n_front, n_behind;
+  float surface_sample_range_m;
+  float margin;                 /* 2 * surface_sample_range_m: free-space samples keep this far from the surface */
+  float free_sample_begin_ratio;
+  float free_sample_end_dist_m;
+  float weight_top;             /* 1 + dist_weight_scale / 2                       */
+  float dist_weight_scale;
+  float max_range;
+  int32_t dist_weight_on;
+  float* coord;
+  float* disp;
+  float* weight;
+} ClidRaySampleArgs;
+CLID_API int clid_ray_samples(const ClidRaySampleArgs* args, clid_stream_t stream);
+/* Labels of DataSampler.sample (:347-377): near-surface samples (slots 1..n_surf of every ray) take +-dist (row
+ * i * n_surf + j of the region-specific distances, sign = side of the surface) and keep = reachable; the others
+ * label = -disp, keep = 1.  label / keep [P*S]. */
+CLID_API int clid_ray_labels(const float* disp, const float* dist, const uint8_t* reachable, int64_t n_points,
+                             int32_t samples_per_ray, int32_t n_surf, float* label, uint8_t* keep, clid_stream_t stream);
+/* rank [n] (position among the elements with flags[i] & 1, -1 otherwise) and their count in workspace int64[0]:
+ * the compaction index for clid_compact_rows */
+CLID_API int clid_flag_ranks(const uint8_t* flags, int64_t n, int64_t* rank, void* workspace, size_t workspace_bytes,
+                             clid_stream_t stream);
+
 /* buffer_pt_index[slot[i]] = value[i] (value == NULL: value_base + i) where the LAST element of a repeated slot wins:
  * what the reference's sequential CPU index_put leaves behind (model/neural_points.py:392, :911-925 recreate_hash,
  * model/local_point_cloud_map.py:52-56, :66-72); CUDA index_put is unordered.  slot may hold torch.fmod's negative

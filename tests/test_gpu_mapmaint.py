@@ -272,3 +272,39 @@ def test_recreate_hash_on_the_gpu_equals_the_host_logic():
         assert torch.equal(cpu.geo_features, gpu.geo_features.cpu())
         cpu.point_certainties *= 0.7
         gpu.point_certainties *= 0.7
+
+
+@pytest.mark.parametrize("run_file", ["ncd128", "subt"])
+def test_native_ray_sampler_draws_the_samples_of_the_torch_ops(run_file):
+    """DataSampler.sample_pin / sample on the GPU (utils/data_sampler.py:16-402): with the same seed the kernels
+    return, bit for bit, what the chain of torch ops returns on the same device."""
+    from clid_slam_b200.model.local_point_cloud_map import LocalPointCloudMap
+    from clid_slam_b200.utils.data_sampler import DataSampler
+    from test_gpu_mapper_flow import _scan
+
+    cfg = ncd128()
+    cfg.device, cfg.local_buffer_size = "cuda", 500_009
+    if run_file == "subt":  # config/run_SubT_MRS.yaml:19: other begin ratio, more samples per ray
+        cfg.free_sample_begin_ratio, cfg.surface_sample_n, cfg.free_front_n, cfg.free_sample_end_dist_m = 0.8, 3, 3, 0.8
+    sampler = DataSampler(cfg)
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    scan = _scan(gen, "cuda", 20_000)
+
+    torch.manual_seed(7)
+    want = sampler._sample_pin_torch(scan)
+    torch.manual_seed(7)
+    got = sampler.sample_pin(scan)
+    for name, a, b in zip(("coord", "label", "normal", "sem", "color", "weight"), got, want):
+        assert (a is None and b is None) or torch.equal(a, b), name
+
+    lpcm = LocalPointCloudMap(cfg)
+    pose = torch.eye(4, device="cuda", dtype=torch.float64)
+    pose[:3, 3] = torch.tensor([1.0, -2.0, 0.5])
+    lpcm.update_map(pose[:3, 3], tools.transform_torch(scan, pose))
+    torch.manual_seed(8)
+    want = sampler._sample_torch(scan, lpcm, pose)
+    torch.manual_seed(8)
+    got = sampler.sample(scan, lpcm, pose)
+    assert 0 < got[0].shape[0] < scan.shape[0] * 8 + 1
+    for name, a, b in zip(("coord", "label", "weight"), got, want):
+        assert a.shape == b.shape and torch.equal(a, b), name
