@@ -246,6 +246,10 @@ __device__ __forceinline__ void stage_decoder(float* sm, const ClidDecoder& dec)
 // (even-unit, odd-unit) partial sums, 11 packed FMAs per pair, folded once at the end.  Per unit: 11 FFMA2
 // instead of 12 FFMA2 + 3 FADD + pairing MOVs, and 4 LDS instead of 5.  Optionally records the activation
 // pattern as bit masks (unit j -> bit j % 32 of word j / 32) for the backward's decoder-gradient fold.
+#ifndef CLID_MLP_UNROLL
+#define CLID_MLP_UNROLL 4  // unit pairs per iteration of the rolled decoder loop
+#endif
+constexpr int kMlpUnroll = CLID_MLP_UNROLL;
 template <int H, bool kMask>
 __device__ __forceinline__ void mlp_l1_pairs(const float* __restrict__ sm, const float (&z)[kIn], float slope,
                                              float& out, float (&a)[kIn], uint32_t* __restrict__ mask) {
@@ -261,7 +265,7 @@ __device__ __forceinline__ void mlp_l1_pairs(const float* __restrict__ sm, const
 #pragma unroll
   for (int jw = 0; jw < H / 32; ++jw) {
     uint32_t bits = 0u;
-#pragma unroll 4
+#pragma unroll kMlpUnroll
     for (int pp = 0; pp < 16; ++pp) {
       const int p = jw * 16 + pp;
       const float4 r0 = w[p * 6 + 0], r1 = w[p * 6 + 1], r2 = w[p * 6 + 2];
