@@ -107,3 +107,30 @@ def test_install_aliases_reference_module_names():
     )
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr
+
+
+def test_map_maintenance_entries_validate_their_arguments(lib):
+    """SURVEY 8f entry points: sizes and NULL / range checks happen on the host, before any launch."""
+    from clid_slam_b200 import _lib
+
+    small, big = lib.clid_scan_workspace_bytes(1), lib.clid_scan_workspace_bytes(4_000_000)
+    assert 16 <= small < big < 1 << 20, "the scan workspace grows with the element count (one entry per 2048 elements)"
+    assert lib.clid_voxel_keys(None, None, 10, 0.4, None, None, None) == -1 and b"NULL" in lib.clid_last_error()
+    assert lib.clid_map_insert_probe(None, None) == -1
+    a = _lib.ClidInsertArgs()
+    a.n = 5
+    assert lib.clid_map_insert_probe(C.byref(a), None) == -1 and b"NULL" in lib.clid_last_error()
+    w = _lib.ClidWindowArgs()
+    assert lib.clid_local_window_select(C.byref(w), None) == -1 and b"m = 0" in lib.clid_last_error()
+    r = _lib.ClidWindowRows()
+    assert lib.clid_local_window_gather(C.byref(r), None) == -1
+    assert lib.clid_table_store(None, None, 3, 0, None, 0, None) == -1
+    assert lib.clid_table_store(None, None, 0, 0, None, 0, None) == -1, "a NULL table is refused even for zero rows"
+    assert lib.clid_compact_rows(None, 3, None, None, None, 1, None) == -1
+    rs = _lib.ClidRaySampleArgs()
+    assert lib.clid_ray_samples(C.byref(rs), None) == 0, "zero scan points: nothing to do"
+    rs.n_points = 4
+    assert lib.clid_ray_samples(C.byref(rs), None) == -1 and b"NULL" in lib.clid_last_error()
+    assert lib.clid_ray_labels(None, None, None, 4, 8, 4, None, None, None) == -1
+    assert lib.clid_flag_ranks(None, 4, None, None, 0, None) == -1
+    assert lib.clid_pool_filter_select(None, 4, None, 1.0, 0, 0, None, None, None, 0, None) == -1
