@@ -189,9 +189,6 @@ def test_native_pool_filter_equals_the_torch_ops(dtype):
 
 def test_process_frame_with_the_native_pool_filter_equals_the_torch_filter(monkeypatch):
     """Two mappers on the same scans, one with the native filter switched off: identical pools and counters."""
-    import numpy as np
-
-    from clid_slam_b200.config import ncd128
     from clid_slam_b200.model.decoder import Decoder
     from clid_slam_b200.model.local_point_cloud_map import LocalPointCloudMap
     from clid_slam_b200.utils.mapper import Mapper
