@@ -64,6 +64,14 @@ struct TileScheduler {
       if ((int64_t)ticket == remaining + stride - 1) atomicExch(counter, 0);  // last ticket of the launch
     }
   }
+  // the tile the NEXT call of next() will return (-1: none), without consuming it; reads the ticket drawn one tile
+  // ahead, so call it well after next() (the atomic's round trip) -- used to prefetch the next tile's inputs
+  __device__ __forceinline__ int64_t peek() const {
+    if (counter == nullptr) return next_static < n_tiles ? next_static : -1;
+    if (remaining <= 0) return -1;
+    const int t = __shfl_sync(0xffffffffu, ticket, 0);
+    return (int64_t)t >= remaining ? -1 : stride + (int64_t)t;
+  }
   // returns the tile index for this warp or -1 when the work is exhausted (warp-uniform)
   __device__ __forceinline__ int64_t next() {
     if (counter == nullptr || first) {

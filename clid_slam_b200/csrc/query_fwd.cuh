@@ -45,6 +45,14 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
   float4* stage_col = reinterpret_cast<float4*>(&scratch + 1) + threadIdx.x;  // kStage record slots per lane (search.cuh)
   const ClidMap& m = p.map;
 
+  // the first tile's coordinates are requested before anything else: their cold miss overlaps the prologue
+  TileScheduler sched(p.map.work_counter, p.n);
+  const int64_t tile0 = sched.next();
+  float x0 = 0.f, y0 = 0.f, z0 = 0.f;
+  if (tile0 >= 0 && tile0 * 32 + (threadIdx.x & 31) < p.n) {
+    const float* xp = p.x + 3 * (tile0 * 32 + (threadIdx.x & 31));
+    x0 = xp[0]; y0 = xp[1]; z0 = xp[2];
+  }
   // asynchronous prologue (common.cuh): stencil by one TMA bulk copy, decoder by cp.async element copies, both
   // completing on mbarriers that are only waited on where the data is first used
   __shared__ StageBarriers stage;
@@ -69,18 +77,29 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
   const int knn = m.knn;
 
   // warp-uniform trip count: every lane stays in the loop so warp votes see full warps
-  TileScheduler sched(p.map.work_counter, p.n);
-  for (int64_t tile = sched.next(); tile >= 0; tile = sched.next()) {
+  bool first_tile = true;
+  for (int64_t tile = tile0; tile >= 0; tile = sched.next()) {
     const int64_t q = tile * 32 + (threadIdx.x & 31);
     const bool live = q < p.n;
-    float px = 0.f, py = 0.f, pz = 0.f;
-    if (live) { px = p.x[3 * q]; py = p.x[3 * q + 1]; pz = p.x[3 * q + 2]; }
+    float px = x0, py = y0, pz = z0;
+    if (!first_tile) {
+      px = py = pz = 0.f;
+      if (live) { px = p.x[3 * q]; py = p.x[3 * q + 1]; pz = p.x[3 * q + 2]; }
+    }
+    first_tile = false;
     TopK<K> top;
     top.init();
     int count = 0;
     if (!stencil_ready) { mbar_wait(&stage.stencil, 0); stencil_ready = true; }
     if constexpr (kSearch == kSearchBricks) count = search_bricks<K, kQueryThreads>(m, p.bricks, stencil, &scratch.want[0][threadIdx.x], stage_col, live, px, py, pz, top);
     else if (live) count = search_hashed<K>(m, cell_mod, px, py, pz, local, time_filter, top);
+#if CLID_PF_NEXT_TILE
+    {  // the next tile's coordinates travel towards L2 during the blend and the decoder (their load is otherwise a cold
+       // miss at the head of the tile); the ticket was drawn at the head of this tile, its round trip is long over
+      const int64_t nt = sched.peek();
+      if (nt >= 0 && nt * 32 + (threadIdx.x & 31) < p.n) prefetch_l2(p.x + 3 * (nt * 32 + (threadIdx.x & 31)));
+    }
+#endif
     if (!live) continue;
 
     // ---- neighbour rows, offsets and inverse-distance weights (neural_points.py:653-706)
@@ -126,10 +145,10 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
     Moments mom;
     mom.clear();
 #pragma unroll
-    for (int k0 = 0; k0 < K; k0 += 3) {
-      float fb[3][kFeat], cb[3];
+    for (int k0 = 0; k0 < K; k0 += kFeatBatch) {
+      float fb[kFeatBatch][kFeat], cb[kFeatBatch];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
+      for (int j = 0; j < kFeatBatch; ++j) {
         if (k0 + j < K) {
           const int rr = row[k0 + j] < 0 ? 0 : row[k0 + j];  // invalid neighbours read row 0; the result is discarded
           load_feature_row256(m.gather_features, rr, fb[j]);
@@ -137,7 +156,7 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
         }
       }
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
+      for (int j = 0; j < kFeatBatch; ++j) {
         const int k = k0 + j;
         if (k < K && row[k] >= 0) {
           float (&f)[kFeat] = fb[j];
@@ -185,6 +204,7 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
     // ---- decoder + closed-form spatial gradient
     if constexpr (H > 0) {
       float o, a[kIn];
+
       if (!decoder_ready) { mbar_wait(&stage.decoder, 0); decoder_ready = true; }
       mlp_value_and_input_grad<H, L>(sm_dec, z, slope, o, a);
       const float s = p.dec.sdf_scale;

@@ -135,7 +135,9 @@ __device__ __forceinline__ int search_hashed(const ClidMap& m, const int64_t* __
 // 2-cell z halves, so at most 3 x 2 x 2 half-bricks can be non-empty.
 constexpr int kHalfSlots = 12;
 #ifndef CLID_WALK_BATCH
-#define CLID_WALK_BATCH 6   // measured 2 / 4 / 6 / 8: 61.5 / 58.4 / 57.4 / 57.4 us (forward, 131072 queries, cold L2)
+#define CLID_WALK_BATCH 7   // r1: 2 / 4 / 6 / 8: 61.5 / 58.4 / 57.4 / 57.4 us (forward, 131072 queries, cold L2); r2 (trimmed means of
+                            // 200 launches, the event clock ticks every 1.9 us): 6 / 7 / 11: 51.4 / 50.7 / 50.9 us -- a fully occupied
+                            // planar neighbourhood has 21 candidates = three batches of 7
 #endif
 constexpr int kWalkBatch = CLID_WALK_BATCH;
 #ifndef CLID_WALK_PIPELINE
@@ -146,8 +148,17 @@ constexpr int kWalkBatch = CLID_WALK_BATCH;
 #define CLID_PF_RECORDS 0   // L2 prefetch of the record lines of every non-empty half-brick: paid off with
                             // 16-B-per-iteration walks, no longer with 6 record loads in flight per lane
 #endif
+#ifndef CLID_FEAT_BATCH
+#define CLID_FEAT_BATCH 3   // feature rows of the top-K requested together before the first is blended
+#endif
+constexpr int kFeatBatch = CLID_FEAT_BATCH;
+#ifndef CLID_PF_NEXT_TILE
+#define CLID_PF_NEXT_TILE 1  // L2 prefetch of the next tile's coordinates (and of this tile's labels in training)
+#endif
 #ifndef CLID_PF_FEATURES
-#define CLID_PF_FEATURES 1  // L2 prefetch of the feature row of every candidate that enters the top-K
+#define CLID_PF_FEATURES 0  // L2 prefetch of the feature row of every candidate that enters the top-K: ~11 extra L1TEX requests per
+                            // query; trimmed means of 200 launches, on / off: forward 50.8 / 50.5 us cold, 45.5 / 43.9 warm,
+                            // training kernel 94.0 / 93.6 cold, 88.8 / 86.7 warm -- off (the same prefetch of the certainties: +3 us)
 #endif
 
 #ifndef CLID_STAGE_RECORDS

@@ -96,6 +96,12 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
   __shared__ float sm_scalar[3][kWarps];
 
   const ClidMap& m = p.map;
+#if CLID_PF_NEXT_TILE
+  {  // the first tile's coordinates start travelling towards L2 before the prologue (static first round: warp w takes tile w)
+    const int64_t q0 = ((int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5)) * (kNumerical ? kNumTileSamples : 32) + (threadIdx.x & 31);
+    if (q0 < p.n) prefetch_l2(p.x + 3 * q0);
+  }
+#endif
   // asynchronous prologue (common.cuh): TMA bulk copy of the stencil, cp.async copies of the decoder, mbarriers
   __shared__ StageBarriers stage;
   stage_barriers_init(stage);
@@ -163,6 +169,13 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
         if (role_variant == 5 || role_variant == 6) pz += sh;
       }
     }
+#if CLID_PF_NEXT_TILE
+    if (live && role_variant == 0) {  // read after the decoder, ~10 us from here: cold misses otherwise
+      prefetch_l2(p.label + q);
+      if (p.weight) prefetch_l2(p.weight + q);
+      if (p.ts) prefetch_l2(p.ts + q);
+    }
+#endif
     TopK<K> top;
     top.init();
     int count = 0;
@@ -170,6 +183,12 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
     if constexpr (kSearch == kSearchBricks) count = search_bricks<K, kQueryThreads>(m, p.bricks, stencil, &scratch.want[0][threadIdx.x], stage_col, live, px, py, pz, top);
     else if (live) count = search_hashed<K>(m, cell_mod, px, py, pz, local, time_filter, top);
 
+#if CLID_PF_NEXT_TILE
+    {  // the next tile's coordinates travel towards L2 during the blend and the decoder
+      const int64_t nt = sched.peek();
+      if (nt >= 0 && nt * tile_samples + role_sample < p.n) prefetch_l2(p.x + 3 * (nt * tile_samples + role_sample));
+    }
+#endif
     float c[kInPad];
 #pragma unroll
     for (int i = 0; i < kInPad; ++i) c[i] = 0.f;
@@ -228,13 +247,13 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
       // the analytic spatial gradient and the tangent input tau0 = s J r are linear in)
       if constexpr (!kNumerical) mom.clear();
 #pragma unroll
-      for (int k0 = 0; k0 < K; k0 += 3) {
-        float fb[3][kFeat];
+      for (int k0 = 0; k0 < K; k0 += kFeatBatch) {
+        float fb[kFeatBatch][kFeat];
 #pragma unroll
-        for (int j = 0; j < 3; ++j)
+        for (int j = 0; j < kFeatBatch; ++j)
           if (k0 + j < K) load_feature_row256(m.gather_features, row[k0 + j] < 0 ? 0 : row[k0 + j], fb[j]);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
+        for (int j = 0; j < kFeatBatch; ++j) {
           const int k = k0 + j;
           if (k < K && row[k] >= 0) {
             float (&f)[kFeat] = fb[j];
