@@ -413,7 +413,8 @@ def run_native(args):
     # ---- kernel-only timing for the roofline: the same step launched call by call (no graph) with
     # CUDA events around the dominant kernel, same L2 hygiene
     trainer.forward_events, trainer.backward_events = [], []
-    for i in range(min(args.steps, 30)):
+    torch.cuda._sleep(int(2e7))  # ~10 ms spin kernel: the host queues ahead, so the events see device time, not launch gaps
+    for i in range(min(args.steps, 50)):
         flush.zero_()
         x, label, weight, ts = batches[i % n_batches]
         trainer.iteration(x, label, ts, weight, n_global=n_global, nd_global=nd_global,
@@ -430,6 +431,7 @@ def run_native(args):
     x0 = batches[0][0]
     for i in range(3):
         fused.sdf_and_gradient(npm, dec, x0)
+    torch.cuda._sleep(int(2e7))
     for i in range(50):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
