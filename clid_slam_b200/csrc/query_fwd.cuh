@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(kQueryThreads, CLID_QUERY_MIN_BLOCKS) query_fo
 
   // warp-uniform trip count: every lane stays in the loop so warp votes see full warps
   bool first_tile = true;
+  stagger_start();
   for (int64_t tile = tile0; tile >= 0; tile = sched.next()) {
     const int64_t q = tile * 32 + (threadIdx.x & 31);
     const bool live = q < p.n;

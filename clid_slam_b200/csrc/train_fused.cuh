@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
   const int64_t n_tiles_work = (p.n + tile_samples - 1) / tile_samples;
 
   TileScheduler sched(p.map.work_counter, n_tiles_work * 32);  // the scheduler counts 32-slot tiles
+  stagger_start();
   for (int64_t tile = sched.next(); tile >= 0; tile = sched.next()) {
     const int64_t q = tile * tile_samples + role_sample;
     const bool live = q < p.n;
