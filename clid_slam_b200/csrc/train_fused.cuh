@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
   uint32_t* sm_m = reinterpret_cast<uint32_t*>(sm_c + kWarps * 32 * kInPad);     // [warps][32][words]
   float* sm_red = reinterpret_cast<float*>(sm_m + kWarps * 32 * kMaskWords);     // [warps][H][12] partial Gd
   __shared__ float sm_scalar[3][kWarps];
+  __shared__ float sm_sample[3][kFusedThreads];  // label, weight, ts of this lane's sample: staged by cp.async at the head of the tile
 
   const ClidMap& m = p.map;
 #if CLID_PF_NEXT_TILE
@@ -172,9 +173,11 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
     }
 #if CLID_PF_NEXT_TILE
     if (live && role_variant == 0) {  // read after the decoder, ~10 us from here: cold misses otherwise
-      prefetch_l2(p.label + q);
-      if (p.weight) prefetch_l2(p.weight + q);
-      if (p.ts) prefetch_l2(p.ts + q);
+      // asynchronous copies (no destination registers) instead of loads after the decoder: ~7 % of this kernel's
+      // stall samples were waits on these three cold 4-byte loads (profiles/r2_train_fused_regions.txt)
+      cp_async4(&sm_sample[0][threadIdx.x], p.label + q);
+      if (p.weight) cp_async4(&sm_sample[1][threadIdx.x], p.weight + q);
+      if (p.ts) cp_async4(&sm_sample[2][threadIdx.x], reinterpret_cast<const float*>(p.ts + q));
     }
 #endif
     TopK<K> top;
@@ -269,11 +272,18 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
 
       // side effects (neural_points.py:708-733); the shifted copies carry no timestamp
       // (Mapper.sdf queries without ts, mapper.py:968-969)
+      int32_t ts_q = 0;
+      const bool stamp = role_variant == 0 && p.ts && m.gather_ts_update;
+#if CLID_PF_NEXT_TILE
+      if (stamp) { cp_async_wait_all(); ts_q = __float_as_int(sm_sample[2][threadIdx.x]); }
+#else
+      if (stamp) ts_q = p.ts[q];
+#endif
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         if (row[k] >= 0) {
           atomicAdd(m.certainty_accum + row[k], w[k]);
-          if (role_variant == 0 && p.ts && m.gather_ts_update) atomicMax(m.gather_ts_update + row[k], p.ts[q]);
+          if (stamp) atomicMax(m.gather_ts_update + row[k], ts_q);
         }
       }
 
@@ -311,8 +321,16 @@ __global__ void __launch_bounds__(kFusedThreads, CLID_QUERY_MIN_BLOCKS) train_fu
     }
     if (live && role_variant == 0) {
       const float l = sdf / s;  // BCEWithLogits(pred / sigma, sigmoid(label / sigma))
-      const float t = 1.0f / (1.0f + expf(-(p.label[q] / s)));
-      const float wgt = (p.weighted && p.weight) ? fabsf(p.weight[q]) : 1.0f;
+#if CLID_PF_NEXT_TILE
+      cp_async_wait_all();
+      const float label_q = sm_sample[0][threadIdx.x];
+      const float weight_q = (p.weighted && p.weight) ? sm_sample[1][threadIdx.x] : 1.0f;
+#else
+      const float label_q = p.label[q];
+      const float weight_q = (p.weighted && p.weight) ? p.weight[q] : 1.0f;
+#endif
+      const float t = 1.0f / (1.0f + expf(-(label_q / s)));
+      const float wgt = (p.weighted && p.weight) ? fabsf(weight_q) : 1.0f;
       bce_sum += wgt * ((1.0f - t) * l + fmaxf(-l, 0.f) + log1pf(expf(-fabsf(l))));
       delta = wgt * (1.0f / (1.0f + expf(-l)) - t) * inv_n;
       if constexpr (!kNumerical) {
