@@ -29,6 +29,12 @@ def brick_flags(bricks) -> int:
 # csrc/decoder_tc.cuh).  Parity-green and measured at the speed of the fp32 FMA decoder, not above it (the kernel is
 # bound by the latency of its gather chain), so the FMA kernel stays the default.
 TC_DECODER = os.environ.get("CLID_TC_DECODER", "0") == "1"
+# The tiles of the persistent kernels are dealt round-robin (ClidMap.work_counter = NULL).  The dynamic alternative
+# (CLID_STATIC_TILES=0: a ticket counter, one atomicAdd per tile drawn one tile ahead) evens out per-tile cost
+# differences, but its atomic RETURNS a value, and in the training kernel that round trip queues behind the ~24
+# fire-and-forget reductions every sample sends to the same L2 atomic units: measured 131072 samples, cold L2:
+# training kernel 70.9 us with tickets, 62.9 us round-robin (forward, no other atomics: 45.9 us either way).
+STATIC_TILES = os.environ.get("CLID_STATIC_TILES", "1") == "1"
 
 _COUNTERS = {}
 _COUNTER_POOLS = {}
@@ -108,7 +114,7 @@ def map_struct(npm, query_locally: bool, certainty_accum: Optional[torch.Tensor]
     m.n_gather = pts.shape[0]
     m.feature_dim = int(npm.geo_feature_dim)
     m.knn = int(cfg.query_nn_k)
-    m.work_counter = _work_counter(npm, pts.device).data_ptr()
+    m.work_counter = None if STATIC_TILES else _work_counter(npm, pts.device).data_ptr()
     if cfg.layer_norm_on:
         flags |= _lib.LAYER_NORM
     return m, flags

@@ -120,10 +120,12 @@ typedef struct ClidMap {
   int32_t feature_dim;            /* 8                                                      */
   int32_t knn;                    /* query_nn_k <= CLID_MAX_KNN                             */
   const ClidBricks* bricks;       /* HOST pointer to a ClidBricks or NULL                   */
-  int32_t* work_counter;          /* 4 bytes of zero-initialised device scratch for the dynamic
-                                     tile scheduler (each warp fetches its next 32 queries with an
-                                     atomic; the kernel leaves it zero again), or NULL for a
-                                     static schedule.  One per stream of concurrent launches.   */
+  int32_t* work_counter;          /* NULL (recommended): tiles of 32 queries are dealt round-robin to
+                                     the resident warps.  Else 4 bytes of zero-initialised device scratch
+                                     for a dynamic tile scheduler (each warp draws its next tile with an
+                                     atomic; the kernel leaves it zero again; one per stream of concurrent
+                                     launches): evens out very uneven tiles, but the ticket's round trip
+                                     queues behind the training kernel's own reductions (slower there).  */
 } ClidMap;
 
 /* model/decoder.py:13-82: Linear(in->H) act [Linear(H->H) act]^(levels-1) Linear(H->1), x sdf_scale */
