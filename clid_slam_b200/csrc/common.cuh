@@ -38,6 +38,10 @@ __device__ __forceinline__ float dist2_torch(float dx, float dy, float dz) {
 // tail of a static schedule.  Every warp draws exactly one ticket past the end; the warp that draws
 // the last one (remaining + n_warps - 1) resets the counter for the next launch.  Without a
 // counter the tiles are dealt round-robin.
+#ifndef CLID_DYNAMIC_TILES
+#define CLID_DYNAMIC_TILES 0  // 1: honour ClidMap.work_counter (ticket scheduler); 0: the round-robin deal is compiled in and the
+                              // ticket path (its registers, its atomics) disappears from the kernels -- see ops/query.py
+#endif
 struct TileScheduler {
   int32_t* counter;
   int64_t n_tiles;
@@ -47,7 +51,7 @@ struct TileScheduler {
   int lane;
   int ticket;         // dynamic: the ticket drawn for the NEXT call (valid in lane 0)
   bool first;
-  __device__ __forceinline__ TileScheduler(int32_t* counter_, int64_t n) : counter(counter_) {
+  __device__ __forceinline__ TileScheduler(int32_t* counter_, int64_t n) : counter(CLID_DYNAMIC_TILES ? counter_ : nullptr) {
     n_tiles = (n + 31) >> 5;
     lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;

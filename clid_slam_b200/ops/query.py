@@ -30,7 +30,7 @@ def brick_flags(bricks) -> int:
 # bound by the latency of its gather chain), so the FMA kernel stays the default.
 TC_DECODER = os.environ.get("CLID_TC_DECODER", "0") == "1"
 # The tiles of the persistent kernels are dealt round-robin (ClidMap.work_counter = NULL).  The dynamic alternative
-# (CLID_STATIC_TILES=0: a ticket counter, one atomicAdd per tile drawn one tile ahead) evens out per-tile cost
+# (library built with -DCLID_DYNAMIC_TILES=1 and CLID_STATIC_TILES=0: a ticket counter, one atomicAdd per tile drawn one tile ahead) evens out per-tile cost
 # differences, but its atomic RETURNS a value, and in the training kernel that round trip queues behind the ~24
 # fire-and-forget reductions every sample sends to the same L2 atomic units: measured 131072 samples, cold L2:
 # training kernel 70.9 us with tickets, 62.9 us round-robin (forward, no other atomics: 45.9 us either way).
