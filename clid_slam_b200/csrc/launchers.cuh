@@ -1,11 +1,28 @@
 // Launch geometry and shape dispatch of the template kernels, shared by the inst_*.cu translation
 // units (one per search kind, so nvcc compiles the instantiations in parallel).
 #pragma once
+#include <cstdlib>
 #include "launch.h"
 #include "query_fwd.cuh"
 #include "train_fused.cuh"
 
 namespace clid {
+
+// The gathers of these kernels live in L1 (every byte of shared memory the driver reserves beyond what the resident
+// CTAs use is L1 they lose): ask for the smallest carve-out that holds `blocks` CTAs (+1 KB each the system reserves).
+// CLID_CARVEOUT (percent, developer knob) overrides.
+static int set_carveout(const void* kern, size_t smem, int blocks) {
+  int pct = -1;
+  if (const char* env = getenv("CLID_CARVEOUT")) pct = atoi(env);
+  if (pct < 0) {
+    const size_t need = (smem + 1024) * (size_t)blocks;
+    pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+  }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(carveout)");
+  return CLID_OK;
+}
 
 template <int H, int L, int K, int kSearch>
 static int launch_query(const QueryParams& p, cudaStream_t stream) {
@@ -24,6 +41,7 @@ static int launch_query(const QueryParams& p, cudaStream_t stream) {
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kThreads, smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     if (blocks_per_sm < 1) blocks_per_sm = 1;
+    if (int rc = set_carveout(reinterpret_cast<const void*>(kern), smem, blocks_per_sm)) return rc;
   }
   int64_t want = (p.n + kThreads - 1) / kThreads;
   int64_t cap = (int64_t)info.sm_count * blocks_per_sm;
@@ -71,6 +89,7 @@ static int launch_train_fused(const TrainFusedParams& p, cudaStream_t stream) {
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kFusedThreads, smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     if (blocks_per_sm < 1) blocks_per_sm = 1;
+    if (int rc = set_carveout(reinterpret_cast<const void*>(kern), smem, blocks_per_sm)) return rc;
   }
   const int64_t per_tile = kNumerical ? kNumTileSamples : 32;  // base samples per 32-lane tile
   const int64_t tiles = (p.n + per_tile - 1) / per_tile;
