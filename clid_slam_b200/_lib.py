@@ -204,6 +204,7 @@ _SIGNATURES = [
      [C.POINTER(ClidDecoder), C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p]),
     ("clid_adam_step", C.c_int, [C.POINTER(ClidAdamArgs), C.c_void_p]),
     ("clid_adam_advance", C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    ("clid_step_begin", C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     ("clid_enable_peer_access", C.c_int, [C.c_int32]),
     ("clid_peer_alloc", C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
     ("clid_peer_free", C.c_int, [C.c_void_p]),

@@ -400,6 +400,14 @@ int clid_adam_advance(void* step_state, float lr, float beta1, float beta2, clid
   return CLID_OK;
 }
 
+int clid_step_begin(void* step_state, float lr, float beta1, float beta2, float* loss3, clid_stream_t stream) {
+  if (!step_state || !loss3) return set_error(CLID_EINVAL, "step_state / loss3 is NULL");
+  adam_advance_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<AdamStepState*>(step_state), lr, beta1, beta2, loss3);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "adam_advance_kernel launch");
+  return CLID_OK;
+}
+
 static int check_peer(const ClidPeerArgs* a) {
   if (!a) return set_error(CLID_EINVAL, "peer args are NULL");
   if (a->world < 1 || a->world > 8 || a->rank < 0 || a->rank >= a->world) return set_error(CLID_EINVAL, "rank %d / world %d", a->rank, a->world);

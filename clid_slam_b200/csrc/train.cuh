@@ -360,7 +360,9 @@ __device__ __forceinline__ float adam_update(float p, float g, float& mm, float&
 
 #ifdef CLID_PLAIN_KERNELS
 // step += 1; bias corrections in double, as torch/optim/adam.py evaluates them on the host
-__global__ void adam_advance_kernel(AdamStepState* st, float lr, float beta1, float beta2) {
+// zero3 (optional): the iteration's loss accumulators [3], cleared by the same launch (clid_step_begin)
+__global__ void adam_advance_kernel(AdamStepState* st, float lr, float beta1, float beta2, float* zero3 = nullptr) {
+  if (zero3 != nullptr && blockIdx.x == 0 && threadIdx.x >= 1 && threadIdx.x <= 3) zero3[threadIdx.x - 1] = 0.f;
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     const int t = st->step + 1;
     st->step = t;

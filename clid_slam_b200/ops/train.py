@@ -193,6 +193,10 @@ class FusedTrainer:
             return loss
         if self.single_kernel and one_kernel_ok:
             defer = bool(apply_step and exchange and shards is None and not sync and self._want_overlap())
+            # with the device-side step counter the optimiser step of this iteration is announced at its head
+            # (clid_step_begin clears the loss and advances the counter in one launch): the advance is then not a
+            # node between the fused kernel and Adam
+            self._begin_step = bool(defer and self.step_state is not None)
             loss = self._iteration_single_kernel(x, label, ts, weight, n_global, nd_global, numerical, defer_reduce=defer)
             if not exchange:  # the caller runs pack / all-reduce / unpack / adam_step itself (StepPipeline)
                 self.losses.append(loss)
@@ -268,7 +272,16 @@ class FusedTrainer:
         """clid_train_fused: forward + loss + backward in one launch (analytic or numerical eikonal)."""
         npm, dec, lib, dev = self.npm, self.dec, self.lib, self.device
         n = x.shape[0]
-        loss = torch.zeros(3, dtype=torch.float32, device=dev)
+        if getattr(self, "_begin_step", False):
+            self._begin_step = False
+            loss = torch.empty(3, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                rc = lib.clid_step_begin(self.step_state.data_ptr(), float(self.cfg.lr), 0.9, 0.99, loss.data_ptr(),
+                                         _lib.current_stream(dev))
+            _lib.check(rc, "clid_step_begin")
+            self._advanced = True
+        else:
+            loss = torch.zeros(3, dtype=torch.float32, device=dev)
         label_f = label.contiguous().float()
         w = weight.contiguous().float() if weight is not None else None
         tsd = _q._prep_ts(ts, n)
@@ -610,15 +623,19 @@ class FusedTrainer:
     def adam_step(self) -> None:
         dev = self.device
         self.step += 1
+        advanced = getattr(self, "_advanced", False)  # iteration() advanced the device counter at its head
+        self._advanced = False
         if self._pending_reduce is None or self.dec_grad is None:
             self._reduce_pending()
-            self._adam_call(True, True, self.step)
+            self._adam_call(True, True, -1 if advanced else self.step)
             return
         # fork: [decoder-gradient reduction -> Adam on the decoder] beside [Adam on the feature rows]
         main = torch.cuda.current_stream(dev)
         side = self._side_stream
         step_arg = self.step
-        if self.step_state is not None:
+        if advanced:
+            step_arg = -1
+        elif self.step_state is not None:
             with torch.cuda.device(dev):
                 rc = self.lib.clid_adam_advance(self.step_state.data_ptr(), float(self.cfg.lr), 0.9, 0.99, main.cuda_stream)
             _lib.check(rc, "clid_adam_advance")

@@ -328,6 +328,10 @@ CLID_API int clid_adam_step(const ClidAdamArgs* args, clid_stream_t stream);
 /* step_state.step += 1 and the bias-correction scalars of the new step (what clid_adam_step does first when
  * step >= 0).  For callers that split one optimiser step over several clid_adam_step(step < 0) launches. */
 CLID_API int clid_adam_advance(void* step_state, float lr, float beta1, float beta2, clid_stream_t stream);
+/* The same advance at the HEAD of an iteration, clearing the iteration's loss accumulators loss3 [3] in the same launch
+ * (replaces a memset and keeps the advance out of the dependency chain fused kernel -> Adam): follow it with
+ * clid_train_fused and clid_adam_step(step < 0) launches. */
+CLID_API int clid_step_begin(void* step_state, float lr, float beta1, float beta2, float* loss3, clid_stream_t stream);
 
 /* ---- per-frame feeders ---------------------------------------------------------------------- */
 
