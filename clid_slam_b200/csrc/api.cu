@@ -873,7 +873,9 @@ int clid_mapping_run(const ClidMap* map, const ClidDecoder* dec, const ClidMappi
   d.weight = const_cast<float*>(t.weight); d.ts = const_cast<int32_t*>(t.ts);
   d.loss = t.loss;
   ClidAdamArgs adam = a->adam;
-  adam.step = 0;  // advance the device counter at every step
+  adam.step = -1;  // the draw kernel of every iteration advances the device counter (one launch less per iteration)
+  d.step_state = static_cast<AdamStepState*>(adam.step_state);
+  d.lr = adam.lr; d.beta1 = adam.beta1; d.beta2 = adam.beta2;
   for (int it = 0; it < a->iters; ++it) {
     d.offset = a->offset + (uint64_t)it;
     d.loss_prev_out = (it > 0 && a->loss_history) ? a->loss_history + 3 * (it - 1) : nullptr;

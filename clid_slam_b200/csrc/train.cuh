@@ -403,12 +403,23 @@ struct DrawParams {
   // bookkeeping of clid_mapping_run folded into the draw: loss of the previous iteration -> history, clear
   float* loss;
   float* loss_prev_out;
+  // ... and the optimiser's step-counter advance of the coming step (adam_advance_kernel), NULL = not here
+  AdamStepState* step_state;
+  float lr, beta1, beta2;
 };
 
 __global__ void __launch_bounds__(256) draw_batch_kernel(const DrawParams p) {
   if (p.loss != nullptr && blockIdx.x == 0 && threadIdx.x < 3) {
     if (p.loss_prev_out != nullptr) p.loss_prev_out[threadIdx.x] = p.loss[threadIdx.x];
     p.loss[threadIdx.x] = 0.f;
+  }
+  if (p.step_state != nullptr && blockIdx.x == 0 && threadIdx.x == 32) {
+    const int t = p.step_state->step + 1;
+    p.step_state->step = t;
+    const double bc1 = 1.0 - pow((double)p.beta1, (double)t);
+    const double bc2 = 1.0 - pow((double)p.beta2, (double)t);
+    p.step_state->step_size = (float)((double)p.lr / bc1);
+    p.step_state->bc2_sqrt = (float)sqrt(bc2);
   }
   const int64_t n_hist = p.n - p.pool.bs_new;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x) {

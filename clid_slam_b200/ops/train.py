@@ -476,7 +476,7 @@ class FusedTrainer:
         _lib.check(rc, "clid_mapping_run")
         self.step += iters
         # draw + fused + Adam advance + Adam [+ decoder-gradient reduction] per iteration, + the last loss copy
-        self.launches += iters * (4 + (1 if self.dec_grad is not None else 0)) + 1
+        self.launches += iters * (3 + (1 if self.dec_grad is not None else 0)) + 1  # draw (+ counter advance), fused, [reduce], Adam
         return history
 
     def _want_overlap(self) -> bool:
