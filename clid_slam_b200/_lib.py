@@ -30,6 +30,10 @@ TC_DECODER = 1 << 6
 _f32p = C.c_void_p  # device pointers travel as plain addresses
 
 
+class ClidBrickHeader(C.Structure):  # element type of ClidBricks.headers (the host only sizes the array)
+    _fields_ = [("mask", C.c_uint64), ("base", C.c_int32), ("count", C.c_int32)]
+
+
 class ClidBricks(C.Structure):
     _fields_ = [
         ("headers", C.c_void_p), ("hood", C.c_void_p), ("records", C.c_void_p), ("stencil", C.c_void_p),

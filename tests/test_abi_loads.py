@@ -46,28 +46,26 @@ def test_zero_queries_is_a_noop(lib):
 
 
 def test_struct_sizes_match_the_header(lib):
-    """Compile a tiny C program against the header and compare sizeof() with ctypes."""
+    """Compile a tiny C program against the header and compare sizeof() of EVERY struct with its ctypes mirror."""
     import subprocess
     import tempfile
 
     from clid_slam_b200 import _lib
 
-    src = r"""
-    #include <stdio.h>
-    #include "clid_sdf.h"
-    int main(void) {
-      printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(ClidMap), sizeof(ClidDecoder), sizeof(ClidQueryOut), sizeof(ClidBricks),
-             sizeof(ClidInsertArgs), sizeof(ClidWindowArgs), sizeof(ClidWindowRows));
-      return 0;
-    }"""
+    header = open(os.path.join(ROOT, "include", "clid_sdf.h")).read()
+    names = re.findall(r"^\}\s*(Clid\w+);", header, flags=re.M)
+    assert len(names) >= 15, names
+    missing = [n for n in names if not hasattr(_lib, n)]
+    assert not missing, f"structs without a ctypes mirror: {missing}"
+    body = "\n".join(f'  printf("%zu\\n", sizeof({n}));' for n in names)
+    src = "#include <stdio.h>\n#include \"clid_sdf.h\"\nint main(void) {\n" + body + "\n  return 0;\n}\n"
     with tempfile.TemporaryDirectory() as tmp:
         c_path, exe = os.path.join(tmp, "s.c"), os.path.join(tmp, "s")
         open(c_path, "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c_path, "-o", exe])
         sizes = [int(v) for v in subprocess.check_output([exe]).split()]
-    assert sizes == [C.sizeof(_lib.ClidMap), C.sizeof(_lib.ClidDecoder), C.sizeof(_lib.ClidQueryOut),
-                     C.sizeof(_lib.ClidBricks), C.sizeof(_lib.ClidInsertArgs), C.sizeof(_lib.ClidWindowArgs),
-                     C.sizeof(_lib.ClidWindowRows)]
+    for name, size in zip(names, sizes):
+        assert size == C.sizeof(getattr(_lib, name)), f"{name}: C {size} bytes, ctypes {C.sizeof(getattr(_lib, name))}"
 
 
 def test_product_refuses_cpu_tensors():
